@@ -1,0 +1,265 @@
+/* SPDX-License-Identifier: Apache-2.0
+ *
+ * fssb200.h -- C ABI of the B200-native batched evaluator for the DPF / DCF /
+ * Half-Tree DPF / Grotto DCF PRG-tree hot path of myl7/fss.
+ *
+ * This header is the drop-in boundary: plain pointers and sizes, no C++ or torch
+ * types.  Every entry point names the reference interface it replaces (paths are
+ * relative to the reference checkout, `include/fss/...`).
+ *
+ * Memory layouts are the reference's, byte for byte:
+ *   seed / output / group element : 16 B, CUDA `int4 {x,y,z,w}` little-endian words;
+ *                                   bit 0 of `.w` is the clamp / control bit
+ *                                   (util.cuh:30-38, group.cuh:28-34).
+ *   Dpf::Cw        (dpf.cuh:76-81)          32 B {int4 s; bool tr; pad}      n+1 per key
+ *   Dcf::Cw        (dcf.cuh:91-96)          32 B {int4 s; int4 v}            n+1 per key
+ *   HalfTreeDpf::Cw(half_tree_dpf.cuh:53-57) 32 B {int4 s; bool extra; pad}  n   per key
+ *   GrottoDcf::Cw  (grotto_dcf.cuh:50)      = Dpf::Cw                        n+1 per key
+ *   keys are key-major: key k's correction words start at cws + k*ncw*32.
+ *   inputs x / alpha : `In[nkeys]`, little-endian unsigned of `in_bytes` bytes
+ *                      (1,2,4,8,16) -- the reference's `In` template parameter.
+ *   EvalAll output : `int4 ys[nkeys][2^n]` natural order of x (dpf.cuh:291-301);
+ *                    Grotto: `bool ys[nkeys][2^n]` one byte per leaf
+ *                    (grotto_dcf.cuh:151-163).
+ *
+ * Ownership (dpf.cuh:86,225; eval_all_gpu.cuh:498): the caller allocates every
+ * buffer; the library never allocates or frees device memory inside an eval /
+ * gen call.  The `_host` variants stage through a per-context pinned/device
+ * arena that is created once by fssb200_ctx_reserve_host().
+ *
+ * Errors: every function returns 0 on success, a negative FSSB200_E* code for an
+ * invalid argument, or a positive `cudaError_t`.  Nothing throws or aborts.
+ *
+ * Streams: device-pointer entry points are stream ordered and never synchronise
+ * the device; a context is immutable after creation and can be shared by threads
+ * (eval_all_gpu.cuh:459-460 semantics).  `stream` is a `cudaStream_t` passed as
+ * `void*` (NULL = default stream).
+ */
+#ifndef FSSB200_H_
+#define FSSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSSB200_VERSION 100 /* 0.1.0 */
+
+/* ---- enums --------------------------------------------------------------- */
+
+/* Scheme: which reference class template the context stands for. */
+enum {
+  FSSB200_SCHEME_DPF = 0,      /* fss::Dpf          dpf.cuh:61-304            */
+  FSSB200_SCHEME_DCF = 1,      /* fss::Dcf          dcf.cuh:74-386            */
+  FSSB200_SCHEME_HALFTREE = 2, /* fss::HalfTreeDpf  half_tree_dpf.cuh:39-355  */
+  FSSB200_SCHEME_GROTTO = 3    /* fss::GrottoDcf    grotto_dcf.cuh:45-239     */
+};
+
+/* Output group (the `Group` template parameter, group.cuh:39-45). */
+enum {
+  FSSB200_GROUP_BYTES = 0, /* fss::group::Bytes             group/bytes.cuh:19-43 */
+  FSSB200_GROUP_U8 = 1,    /* fss::group::Uint<uint8_t ,mod> group/uint.cuh:27-88 */
+  FSSB200_GROUP_U16 = 2,   /* fss::group::Uint<uint16_t,mod>                      */
+  FSSB200_GROUP_U32 = 3,   /* fss::group::Uint<uint32_t,mod>                      */
+  FSSB200_GROUP_U64 = 4,   /* fss::group::Uint<uint64_t,mod>                      */
+  FSSB200_GROUP_U128 = 5   /* fss::group::Uint<__uint128_t,mod>, 0 < mod <= 2^127 */
+};
+
+/* PRG (the `Prg` template parameter, prg.cuh:20-23). */
+enum {
+  FSSB200_PRG_AES128_MMO = 0, /* fss::prg::Aes128Mmo<mul> prg/aes128_mmo.cuh:27-94
+                                 (== Aes128MmoRaw == Aes128Soft bit for bit)      */
+  FSSB200_PRG_CHACHA = 1      /* fss::prg::ChaCha<mul,20> prg/chacha.cuh:24-128    */
+};
+
+/* DCF predicate (dcf.cuh:58-61); only Gen depends on it. */
+enum { FSSB200_PRED_LT = 0, FSSB200_PRED_GT = 1 };
+
+/* Error codes (negative).  Positive return values are cudaError_t. */
+enum {
+  FSSB200_OK = 0,
+  FSSB200_EINVAL = -1,     /* NULL pointer / bad enum / bad size                  */
+  FSSB200_EDOMAIN = -2,    /* in_bits outside [1, 8*in_bytes] or unsupported n    */
+  FSSB200_EGROUP = -3,     /* group / modulus combination not representable       */
+  FSSB200_ESCHEME = -4,    /* entry point does not apply to the context's scheme  */
+  FSSB200_EALIGN = -5,     /* pointer not 16-byte aligned                         */
+  FSSB200_ENODEVICE = -6,  /* no CUDA device / device index out of range          */
+  FSSB200_ERANGE = -7,     /* leaf range not aligned / out of the domain          */
+  FSSB200_ENOARENA = -8    /* _host call without fssb200_ctx_reserve_host()       */
+};
+
+/* ---- context --------------------------------------------------------------- */
+
+/* Everything the reference passes as template arguments or scheme members.
+ *   in_bits   : `in_bits`                     (dpf.cuh:61)
+ *   in_bytes  : sizeof(In)                    (dpf.cuh:61; fss_crypto/_jit.py:57-62)
+ *   group,mod : `Group`; mod_hi:mod_lo is the 128-bit modulus, 0 = 2^(8*sizeof(T))
+ *               (group/uint.cuh:27-31).  U128 requires 0 < mod <= 2^127.
+ *   prg       : `Prg`; prg_key = mul 16-byte AES user keys, key i encrypts PRG
+ *               output block i (prg/aes128_mmo.cuh:49-64,79-89) -- mul = 2 (DPF,
+ *               Grotto), 4 (DCF), 1 (Half-Tree); or, for ChaCha, two little-endian
+ *               int32 nonce words in prg_key[0..7] (prg/chacha.cuh:89-93,108-110).
+ *   hash_key  : HalfTreeDpf::hash_key         (half_tree_dpf.cuh:44)
+ *   pred      : DcfPred                       (dcf.cuh:58-61)
+ *   device    : CUDA device ordinal the context's kernels run on.
+ */
+typedef struct fssb200_params {
+  int32_t scheme;
+  int32_t in_bits;
+  int32_t in_bytes;
+  int32_t group;
+  uint64_t mod_lo;
+  uint64_t mod_hi;
+  int32_t prg;
+  int32_t pred;
+  uint8_t prg_key[64];
+  uint8_t hash_key[16];
+  int32_t device;
+  int32_t reserved;
+} fssb200_params;
+
+typedef struct fssb200_ctx fssb200_ctx;
+
+int fssb200_version(void);
+const char *fssb200_strerror(int code);
+
+/* Replaces scheme-object construction `Dpf dpf{prg}` / `HalfTreeDpf{prg,hash_key}`
+ * (dpf.cuh:64-66, README.md:125-126) and `Aes128Mmo::CreateCtxs`
+ * (prg/aes128_mmo.cuh:49-64): expands the AES round keys once, validates the
+ * parameter set.  Key material is copied; the caller may free `p` afterwards. */
+int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out);
+/* Replaces `Aes128Mmo::FreeCtxs` (prg/aes128_mmo.cuh:66-70). */
+void fssb200_ctx_destroy(fssb200_ctx *ctx);
+int fssb200_ctx_params(const fssb200_ctx *ctx, fssb200_params *out);
+/* Number of 32-byte Cw entries per key: n+1 (DPF, DCF, Grotto), n (Half-Tree). */
+int fssb200_ctx_ncw(const fssb200_ctx *ctx);
+
+/* ---- batched key generation (device pointers) ------------------------------
+ * ys-independent dealer step; replaces `Dpf::Gen` dpf.cuh:93-159, `Dcf::Gen`
+ * dcf.cuh:108-194, `HalfTreeDpf::Gen` half_tree_dpf.cuh:68-175, `GrottoDcf::Gen`
+ * grotto_dcf.cuh:63-67 (and the bench kernels src/bench_gpu.cu:72-83,142-153,
+ * 212-223), one key per thread.
+ *   s0s   : int4[nkeys][2]    party-0 and party-1 seeds
+ *   alphas: In[nkeys]
+ *   betas : int4[nkeys]       (ignored, may be NULL, for Grotto: beta = 0)
+ *   cws   : Cw[nkeys][ncw]    out, key-major
+ *   ocws  : int4[nkeys]       out, Half-Tree output correction word; else NULL
+ */
+int fssb200_gen(const fssb200_ctx *ctx, const void *s0s, const void *alphas, const void *betas,
+                void *cws, void *ocws, size_t nkeys, void *stream);
+
+/* ---- batched point evaluation (device pointers) ----------------------------
+ * ys[k] = Eval(party, seeds[k], cws[k], xs[k]).
+ *   fssb200_dpf_eval      replaces `Dpf::Eval` dpf.cuh:170-214 and
+ *                         `fss::gpu::DpfEvalPointGpu` point_eval_gpu.cuh:448-460
+ *                         (without needing DpfRelayoutGpu :346-353)
+ *   fssb200_dcf_eval      replaces `Dcf::Eval` dcf.cuh:205-276 and
+ *                         `fss::gpu::DcfEvalPointGpu` point_eval_gpu.cuh:480-492
+ *   fssb200_halftree_eval replaces `HalfTreeDpf::Eval` half_tree_dpf.cuh:187-231 and
+ *                         `fss::gpu::HalfTreeDpfEvalPointGpu` point_eval_gpu.cuh:416-428
+ *   seeds : int4[nkeys]   the party's seed per key
+ *   cws   : Cw[nkeys][ncw] key-major (the layout Gen writes)
+ *   ocws  : int4[nkeys]   (Half-Tree only)
+ *   xs    : In[nkeys]
+ *   ys    : int4[nkeys]   out
+ * fssb200_eval dispatches on the context's scheme (Grotto is EvalAll-only).
+ */
+int fssb200_eval(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                 const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream);
+int fssb200_dpf_eval(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                     const void *xs, void *ys, size_t nkeys, void *stream);
+int fssb200_dcf_eval(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                     const void *xs, void *ys, size_t nkeys, void *stream);
+int fssb200_halftree_eval(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                          const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream);
+
+/* ---- full-domain evaluation (device pointers) -------------------------------
+ * Writes leaves [leaf_begin, leaf_begin+leaf_count) of every key:
+ *   ys[k*leaf_count + (x-leaf_begin)] = Eval(party, seeds[k], cws[k], x).
+ * leaf_begin/leaf_count select a subtree range so disjoint ranges can be sharded
+ * across GPUs (BASELINE config 4); both must be multiples of the unit returned by
+ * fssb200_eval_all_granule() (a power of two), leaf_count = 0 means "to 2^n".
+ *   DPF      replaces `Dpf::EvalAll` dpf.cuh:232-303 and
+ *            `fss::gpu::DpfEvalAllGpu[Batch]` eval_all_gpu.cuh:483-520
+ *   DCF      replaces `Dcf::EvalAll` dcf.cuh:294-385 (no reference GPU version)
+ *   HALFTREE replaces `HalfTreeDpf::EvalAll` half_tree_dpf.cuh:246-354 and
+ *            `fss::gpu::HalfTreeDpfEvalAllGpu[Batch]` eval_all_gpu.cuh:451-535
+ *   GROTTO   replaces `GrottoDcf::EvalAll` grotto_dcf.cuh:151-163: ys is
+ *            `bool[nkeys][2^n]` (prefix parity of the leaf control bits; a
+ *            sub-range is only allowed with leaf_begin = 0).
+ */
+int fssb200_eval_all(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                     const void *ocws, void *ys, size_t nkeys, uint64_t leaf_begin,
+                     uint64_t leaf_count, void *stream);
+uint64_t fssb200_eval_all_granule(const fssb200_ctx *ctx);
+
+/* Grotto leaf control bits without the scan: t[k][x] (one byte per leaf); replaces
+ * the private `GrottoDcf::ExpandTree` grotto_dcf.cuh:174-238. */
+int fssb200_grotto_expand(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                          void *t, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count,
+                          void *stream);
+/* Replaces `GrottoDcf::Preprocess` grotto_dcf.cuh:94-104: pt[k] is the heap-ordered
+ * parity tree of 2N-1 bytes (root p[0], leaf x at p[N-1+x]). */
+int fssb200_grotto_preprocess(const fssb200_ctx *ctx, int party, const void *seeds,
+                              const void *cws, void *pt, size_t nkeys, void *stream);
+/* Replaces the static `GrottoDcf::Eval` lookup grotto_dcf.cuh:116-135:
+ * ys[k] (1 byte) = prefix parity of pt[k] at xs[k]. */
+int fssb200_grotto_eval(const fssb200_ctx *ctx, const void *pt, const void *xs, void *ys,
+                        size_t nkeys, void *stream);
+
+/* ---- level-major layout (optional pre-pass) ----------------------------------
+ * Replaces `fss::gpu::{Dpf,Dcf,HalfTreeDpf}RelayoutGpu` point_eval_gpu.cuh:324-381:
+ * key-major Cw[nkeys][ncw] -> the compact level-major layout the reference's point
+ * kernels read (cw_s[i*nkeys+k], DCF also cw_v[i*nkeys+k], packed tr bits, out_cw).
+ * Unlike the reference (`uint32_t extra`, n <= 32) the packed control bits are
+ * ceil(n/32) words per key: extra[w*nkeys+k] bit j = level 32*w+j.
+ *   cw_s  : int4[n][nkeys]          out
+ *   cw_v  : int4[n][nkeys]          out (DCF only, else NULL)
+ *   extra : uint32[ceil(n/32)][nkeys] out (DPF: tr bits; Half-Tree: bit 0 = extra)
+ *   out_cw: int4[nkeys]             out (DPF: cws[n].s, DCF: cws[n].v; Half-Tree: unused)
+ */
+int fssb200_relayout(const fssb200_ctx *ctx, const void *cws, void *cw_s, void *cw_v, void *extra,
+                     void *out_cw, size_t nkeys, void *stream);
+/* Replaces `fss::gpu::{Dpf,Dcf,HalfTreeDpf}EvalPointGpu` point_eval_gpu.cuh:416-492
+ * on the layout above (ocws: Half-Tree only). */
+int fssb200_eval_levelmajor(const fssb200_ctx *ctx, int party, const void *seeds, const void *cw_s,
+                            const void *cw_v, const void *extra, const void *out_cw,
+                            const void *ocws, const void *xs, void *ys, size_t nkeys,
+                            void *stream);
+
+/* ---- host-buffer entry points (what a CPU caller of the reference binds) -----
+ * Same semantics with HOST pointers (pageable or pinned): inputs are staged to the
+ * device in chunks, evaluated, and results copied back, with copies and kernels
+ * overlapped on internal streams.  The call returns when ys is complete.
+ * fssb200_ctx_reserve_host() creates the staging arena once (the only allocating
+ * call); max_keys_per_chunk = 0 picks a default. */
+int fssb200_ctx_reserve_host(fssb200_ctx *ctx, size_t max_keys_per_chunk);
+int fssb200_eval_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                      const void *ocws, const void *xs, void *ys, size_t nkeys);
+int fssb200_eval_all_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                          const void *ocws, void *ys, size_t nkeys, uint64_t leaf_begin,
+                          uint64_t leaf_count);
+int fssb200_gen_host(fssb200_ctx *ctx, const void *s0s, const void *alphas, const void *betas,
+                     void *cws, void *ocws, size_t nkeys);
+
+/* ---- introspection / measurement helpers -------------------------------------- */
+
+/* PRG known-answer hook: out[i] = block i of prg.Gen(seed), i < mul, for nseeds
+ * seeds (device pointers).  Replaces a direct `prg.Gen(seed)` call
+ * (prg/aes128_mmo.cuh:72-93, prg/chacha.cuh:95-127). */
+int fssb200_prg_gen(const fssb200_ctx *ctx, const void *seeds, void *out, int mul, size_t nseeds,
+                    void *stream);
+/* Number of kernel launches this context has issued (bench.py's gpu_launches). */
+uint64_t fssb200_ctx_launch_count(const fssb200_ctx *ctx);
+/* Integer-pipe / shared-memory issue-rate microbenchmarks used for the roofline
+ * denominator.  kind: 0 = LOP3 chain, 1 = IMAD chain, 2 = LOP3+IMAD
+ * mixed, 3 = conflict-free LDS.32, 4 = PRMT.  Returns ops (or lookups) per second
+ * through *ops_per_s. */
+int fssb200_microbench(int device, int kind, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSSB200_H_ */
