@@ -1,0 +1,701 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// api.cu -- the extern "C" boundary of include/fssb200.h: context, argument validation, launch
+// geometry, host-buffer staging.  There is no CPU evaluation path in this library: every entry
+// point either launches sm_100a kernels or returns an error code.
+#include <atomic>
+#include <cstring>
+#include <new>
+
+#include "dispatch.h"
+#include "misc_kernels.cuh"
+
+using namespace fssb200;
+
+struct HostArena {
+  size_t chunk_keys = 0;
+  size_t bytes_per_set = 0;
+  uint8_t *dev[2] = {nullptr, nullptr};
+  cudaStream_t stream[2] = {nullptr, nullptr};
+};
+
+struct fssb200_ctx {
+  fssb200_params p;
+  KParams kp;
+  int gk;           // group kind (common.cuh)
+  int ncw;
+  int mul;
+  int sm_count;
+  int max_smem_optin;
+  uint32_t vmask;
+  std::atomic<uint64_t> launches{0};
+  HostArena arena;
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                         \
+  do {                                         \
+    cudaError_t e__ = (expr);                  \
+    if (e__ != cudaSuccess) return int(e__);   \
+  } while (0)
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int group_kind(const fssb200_params &p, uint32_t *vmask) {
+  const bool has_mod = (p.mod_lo | p.mod_hi) != 0;
+  *vmask = 0xffffffffu;
+  switch (p.group) {
+    case FSSB200_GROUP_BYTES: return has_mod ? -1 : kGrpBytes;
+    case FSSB200_GROUP_U8:
+    case FSSB200_GROUP_U16:
+    case FSSB200_GROUP_U32: {
+      const int bits = p.group == FSSB200_GROUP_U8 ? 8 : (p.group == FSSB200_GROUP_U16 ? 16 : 32);
+      *vmask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
+      if (!has_mod) return kGrpU32;
+      if (p.mod_hi || (bits < 32 && (p.mod_lo >> bits)) || (p.mod_lo >> 32)) return -1;
+      return kGrpU32Mod;
+    }
+    case FSSB200_GROUP_U64:
+      if (!has_mod) return kGrpU64;
+      return p.mod_hi ? -1 : kGrpU64Mod;
+    case FSSB200_GROUP_U128:
+      if (!has_mod) return -1;                                       // uint.cuh:29: mod > 0 required
+      if (p.mod_hi == 0x8000000000000000ull && p.mod_lo == 0) return kGrpU127;
+      if (p.mod_hi >> 63) return -1;                                 // mod > 2^127
+      return kGrpU128Mod;
+  }
+  return -1;
+}
+
+// Launch geometry of the point / gen / prg kernels: AES = one persistent 512-thread CTA per SM with
+// the full dynamic shared memory (tables); ChaCha = plain 256-thread CTAs.
+LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s) {
+  LaunchCfg cfg;
+  cfg.stream = s;
+  if (c->p.prg == FSSB200_PRG_AES128_MMO) {
+    const uint64_t want = (n + kPointThreads - 1) / kPointThreads;
+    cfg.grid = dim3(unsigned(want < uint64_t(c->sm_count) ? (want ? want : 1) : c->sm_count));
+    cfg.block = dim3(kPointThreads);
+    cfg.smem = kMaxDynSmem;
+  } else {
+    const uint64_t want = (n + 255) / 256;
+    const uint64_t cap = uint64_t(c->sm_count) * 16;
+    cfg.grid = dim3(unsigned(want < cap ? (want ? want : 1) : cap));
+    cfg.block = dim3(256);
+    cfg.smem = 0;
+  }
+  return cfg;
+}
+
+struct EvalAllPlan {
+  int unit_bits, breadth_bits, dfs_bits;
+};
+EvalAllPlan plan_evalall(int n) {
+  EvalAllPlan pl;
+  int dfs = n - kEvalAllThreadBits;
+  if (dfs < 1) dfs = 1;
+  if (dfs > kMaxDfsBits) dfs = kMaxDfsBits;
+  int bt = n - dfs;
+  if (bt > kEvalAllThreadBits) bt = kEvalAllThreadBits;
+  pl.dfs_bits = dfs;
+  pl.breadth_bits = bt;
+  pl.unit_bits = bt + dfs;
+  return pl;
+}
+
+int check_common(const fssb200_ctx *c) { return c ? 0 : FSSB200_EINVAL; }
+
+}  // namespace
+
+extern "C" {
+
+int fssb200_version(void) { return FSSB200_VERSION; }
+
+const char *fssb200_strerror(int code) {
+  switch (code) {
+    case FSSB200_OK: return "ok";
+    case FSSB200_EINVAL: return "invalid argument";
+    case FSSB200_EDOMAIN: return "in_bits outside the supported domain";
+    case FSSB200_EGROUP: return "unsupported group / modulus";
+    case FSSB200_ESCHEME: return "entry point does not apply to this scheme";
+    case FSSB200_EALIGN: return "pointer is not 16-byte aligned";
+    case FSSB200_ENODEVICE: return "no such CUDA device";
+    case FSSB200_ERANGE: return "leaf range is not unit-aligned or outside the domain";
+    case FSSB200_ENOARENA: return "host staging arena not reserved";
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "unknown error";
+}
+
+int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
+  if (!p || !out) return FSSB200_EINVAL;
+  *out = nullptr;
+  if (p->scheme < FSSB200_SCHEME_DPF || p->scheme > FSSB200_SCHEME_GROTTO) return FSSB200_EINVAL;
+  if (p->prg != FSSB200_PRG_AES128_MMO && p->prg != FSSB200_PRG_CHACHA) return FSSB200_EINVAL;
+  if (p->pred != FSSB200_PRED_LT && p->pred != FSSB200_PRED_GT) return FSSB200_EINVAL;
+  if (p->in_bytes != 1 && p->in_bytes != 2 && p->in_bytes != 4 && p->in_bytes != 8 && p->in_bytes != 16)
+    return FSSB200_EINVAL;
+  if (p->in_bits < 1 || p->in_bits > 8 * p->in_bytes) return FSSB200_EDOMAIN;
+  fssb200_params q = *p;
+  if (q.scheme == FSSB200_SCHEME_GROTTO) {  // GrottoDcf is defined over group::Bytes (grotto_dcf.cuh:46)
+    q.group = FSSB200_GROUP_BYTES;
+    q.mod_lo = q.mod_hi = 0;
+  }
+  uint32_t vmask;
+  const int gk = group_kind(q, &vmask);
+  if (gk < 0 || !grp_kind_instantiated(gk)) return FSSB200_EGROUP;
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return FSSB200_ENODEVICE;
+  if (q.device < 0 || q.device >= ndev) return FSSB200_ENODEVICE;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, q.device));
+  if (prop.major < 10) return FSSB200_ENODEVICE;  // sm_100a only
+  if (size_t(prop.sharedMemPerBlockOptin) < kMaxDynSmem) return FSSB200_ENODEVICE;
+
+  fssb200_ctx *c = new (std::nothrow) fssb200_ctx();
+  if (!c) return FSSB200_EINVAL;
+  c->p = q;
+  c->gk = gk;
+  c->vmask = vmask;
+  c->mul = q.scheme == FSSB200_SCHEME_DCF ? 4 : (q.scheme == FSSB200_SCHEME_HALFTREE ? 1 : 2);
+  c->ncw = q.scheme == FSSB200_SCHEME_HALFTREE ? q.in_bits : q.in_bits + 1;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = int(prop.sharedMemPerBlockOptin);
+  std::memset(&c->kp, 0, sizeof(c->kp));
+  if (q.prg == FSSB200_PRG_AES128_MMO) {
+    for (int i = 0; i < 4; ++i) aes128_expand_le(q.prg_key + 16 * i, c->kp.keys.rk[i]);
+    // per-thread child selection: child bit picks key p (bit 0) or p + mul/2 (bit 1)
+    const int nb = c->mul >= 2 ? c->mul / 2 : 1;
+    for (int pidx = 0; pidx < 2 && pidx < nb; ++pidx)
+      for (int i = 0; i < 44; ++i) c->kp.keys.rkd[pidx][i] = c->kp.keys.rk[pidx][i] ^ c->kp.keys.rk[pidx + nb][i];
+  } else {
+    std::memcpy(c->kp.keys.nonce, q.prg_key, 8);
+  }
+  std::memcpy(c->kp.keys.hash_key, q.hash_key, 16);
+  c->kp.ga.vmask = vmask;
+  c->kp.ga.mod[0] = uint32_t(q.mod_lo);
+  c->kp.ga.mod[1] = uint32_t(q.mod_lo >> 32);
+  c->kp.ga.mod[2] = uint32_t(q.mod_hi);
+  c->kp.ga.mod[3] = uint32_t(q.mod_hi >> 32);
+  *out = c;
+  return 0;
+}
+
+void fssb200_ctx_destroy(fssb200_ctx *c) {
+  if (!c) return;
+  {
+    DeviceGuard g(c->p.device);
+    for (int i = 0; i < 2; ++i) {
+      if (c->arena.dev[i]) cudaFree(c->arena.dev[i]);
+      if (c->arena.stream[i]) cudaStreamDestroy(c->arena.stream[i]);
+    }
+  }
+  delete c;
+}
+
+int fssb200_ctx_params(const fssb200_ctx *c, fssb200_params *out) {
+  if (!c || !out) return FSSB200_EINVAL;
+  *out = c->p;
+  return 0;
+}
+
+int fssb200_ctx_ncw(const fssb200_ctx *c) { return c ? c->ncw : FSSB200_EINVAL; }
+
+uint64_t fssb200_ctx_launch_count(const fssb200_ctx *c) { return c ? c->launches.load() : 0; }
+
+// ---- gen ------------------------------------------------------------------------------------------------------
+int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, const void *betas, void *cws,
+    void *ocws, size_t nkeys, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (!s0s || !alphas || !cws) return FSSB200_EINVAL;
+  const int scheme = c->p.scheme;
+  if (scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
+  if (scheme != FSSB200_SCHEME_GROTTO && !betas) return FSSB200_EINVAL;
+  if (!aligned16(s0s) || !aligned16(cws) || !aligned16(betas) || !aligned16(ocws)) return FSSB200_EALIGN;
+  if (reinterpret_cast<uintptr_t>(alphas) % c->p.in_bytes) return FSSB200_EALIGN;
+  if (nkeys == 0) return 0;
+  // Grotto keys are DPF keys over Bytes with beta = 0 (grotto_dcf.cuh:63-67)
+  const int kscheme = scheme == FSSB200_SCHEME_GROTTO ? FSSB200_SCHEME_DPF : scheme;
+  gen_launch_fn fn = get_gen_launcher(kscheme, c->gk, c->p.prg);
+  if (!fn) return FSSB200_EGROUP;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  GenArgs a;
+  a.s0s = static_cast<const blk *>(s0s);
+  a.alphas = static_cast<const uint8_t *>(alphas);
+  a.betas = scheme == FSSB200_SCHEME_GROTTO ? nullptr : static_cast<const blk *>(betas);
+  a.cws = static_cast<uint8_t *>(cws);
+  a.ocws = static_cast<blk *>(ocws);
+  a.nkeys = nkeys;
+  a.in_bits = c->p.in_bits;
+  a.in_bytes = c->p.in_bytes;
+  a.pred = c->p.pred;
+  a.vmask = c->vmask;
+  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream));
+  c->launches++;
+  return int(fn(c->kp, a, cfg));
+}
+
+// ---- point eval ---------------------------------------------------------------------------------------------------
+static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const void *seeds, const void *cws,
+    const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream, bool level_major, const void *cw_s,
+    const void *cw_v, const void *extra, const void *out_cw) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  const int scheme = c->p.scheme;
+  if (scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;  // Grotto: EvalAll / Preprocess+Eval only
+  if (want_scheme >= 0 && want_scheme != scheme) return FSSB200_ESCHEME;
+  if (party != 0 && party != 1) return FSSB200_EINVAL;
+  if (!seeds || !xs || !ys) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
+  if (level_major) {
+    if (!cw_s) return FSSB200_EINVAL;
+    if (scheme == FSSB200_SCHEME_DCF && (!cw_v || !out_cw)) return FSSB200_EINVAL;
+    if (scheme == FSSB200_SCHEME_DPF && (!extra || !out_cw)) return FSSB200_EINVAL;
+    if (scheme == FSSB200_SCHEME_HALFTREE && !extra) return FSSB200_EINVAL;
+    if (!aligned16(cw_s) || !aligned16(cw_v) || !aligned16(out_cw)) return FSSB200_EALIGN;
+  } else {
+    if (!cws) return FSSB200_EINVAL;
+    if (!aligned16(cws)) return FSSB200_EALIGN;
+  }
+  if (!aligned16(seeds) || !aligned16(ys) || !aligned16(ocws)) return FSSB200_EALIGN;
+  if (reinterpret_cast<uintptr_t>(xs) % c->p.in_bytes) return FSSB200_EALIGN;
+  if (nkeys == 0) return 0;
+  point_launch_fn fn = get_point_launcher(scheme, c->gk, c->p.prg, level_major);
+  if (!fn) return FSSB200_EGROUP;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  PointArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.seeds = static_cast<const blk *>(seeds);
+  a.cws = static_cast<const uint8_t *>(cws);
+  a.ocws = static_cast<const blk *>(ocws);
+  a.xs = static_cast<const uint8_t *>(xs);
+  a.ys = static_cast<blk *>(ys);
+  a.cw_s = static_cast<const blk *>(cw_s);
+  a.cw_v = static_cast<const blk *>(cw_v);
+  a.extra = static_cast<const uint32_t *>(extra);
+  a.out_cw = static_cast<const blk *>(out_cw);
+  a.nkeys = nkeys;
+  a.in_bits = c->p.in_bits;
+  a.in_bytes = c->p.in_bytes;
+  a.party = party;
+  a.vmask = c->vmask;
+  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream));
+  c->launches++;
+  return int(fn(c->kp, a, cfg));
+}
+
+int fssb200_eval(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    const void *xs, void *ys, size_t nkeys, void *stream) {
+  return eval_impl(c, -1, party, seeds, cws, ocws, xs, ys, nkeys, stream, false, nullptr, nullptr, nullptr, nullptr);
+}
+int fssb200_dpf_eval(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *xs, void *ys,
+    size_t nkeys, void *stream) {
+  return eval_impl(c, FSSB200_SCHEME_DPF, party, seeds, cws, nullptr, xs, ys, nkeys, stream, false, nullptr, nullptr,
+      nullptr, nullptr);
+}
+int fssb200_dcf_eval(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *xs, void *ys,
+    size_t nkeys, void *stream) {
+  return eval_impl(c, FSSB200_SCHEME_DCF, party, seeds, cws, nullptr, xs, ys, nkeys, stream, false, nullptr, nullptr,
+      nullptr, nullptr);
+}
+int fssb200_halftree_eval(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    const void *xs, void *ys, size_t nkeys, void *stream) {
+  return eval_impl(c, FSSB200_SCHEME_HALFTREE, party, seeds, cws, ocws, xs, ys, nkeys, stream, false, nullptr,
+      nullptr, nullptr, nullptr);
+}
+int fssb200_eval_levelmajor(const fssb200_ctx *c, int party, const void *seeds, const void *cw_s, const void *cw_v,
+    const void *extra, const void *out_cw, const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream) {
+  return eval_impl(c, -1, party, seeds, nullptr, ocws, xs, ys, nkeys, stream, true, cw_s, cw_v, extra, out_cw);
+}
+
+int fssb200_relayout(const fssb200_ctx *cc, const void *cws, void *cw_s, void *cw_v, void *extra, void *out_cw,
+    size_t nkeys, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  const int scheme = c->p.scheme;
+  if (!cws || !cw_s) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_DCF ? (!cw_v || !out_cw) : !extra) return FSSB200_EINVAL;
+  if ((scheme == FSSB200_SCHEME_DPF || scheme == FSSB200_SCHEME_GROTTO) && !out_cw) return FSSB200_EINVAL;
+  if (!aligned16(cws) || !aligned16(cw_s) || !aligned16(cw_v) || !aligned16(out_cw)) return FSSB200_EALIGN;
+  if (nkeys == 0) return 0;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  c->launches++;
+  return int(launch_relayout(scheme, c->p.in_bits, c->ncw, static_cast<const uint8_t *>(cws),
+      static_cast<blk *>(cw_s), static_cast<blk *>(cw_v), static_cast<uint32_t *>(extra), static_cast<blk *>(out_cw),
+      nkeys, static_cast<cudaStream_t>(stream)));
+}
+
+// ---- full-domain evaluation ---------------------------------------------------------------------------------------
+uint64_t fssb200_eval_all_granule(const fssb200_ctx *c) {
+  if (!c) return 0;
+  return uint64_t(1) << plan_evalall(c->p.in_bits).unit_bits;
+}
+
+static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, const void *cws, const void *ocws,
+    void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count, void *stream) {
+  if (party != 0 && party != 1) return FSSB200_EINVAL;
+  if (!seeds || !cws || !ys) return FSSB200_EINVAL;
+  if (mode == 1 && !ocws) return FSSB200_EINVAL;
+  if (!aligned16(seeds) || !aligned16(cws) || !aligned16(ocws)) return FSSB200_EALIGN;
+  if (mode != 2 && !aligned16(ys)) return FSSB200_EALIGN;  // Grotto bytes: any alignment
+  const int n = c->p.in_bits;
+  if (n > 40) return FSSB200_EDOMAIN;  // 2^40 leaves = 16 TiB per key
+  const uint64_t N = uint64_t(1) << n;
+  if (leaf_begin >= N) return FSSB200_ERANGE;
+  if (leaf_count == 0) leaf_count = N - leaf_begin;
+  if (leaf_begin + leaf_count > N) return FSSB200_ERANGE;
+  const EvalAllPlan pl = plan_evalall(n);
+  const uint64_t granule = uint64_t(1) << pl.unit_bits;
+  if ((leaf_begin | leaf_count) & (granule - 1)) return FSSB200_ERANGE;
+  if (nkeys == 0) return 0;
+  evalall_launch_fn fn = get_evalall_launcher(mode, c->gk, c->p.prg);
+  if (!fn) return FSSB200_EGROUP;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  EvalAllArgs a;
+  a.seeds = static_cast<const blk *>(seeds);
+  a.cws = static_cast<const uint8_t *>(cws);
+  a.ocws = static_cast<const blk *>(ocws);
+  a.ys = ys;
+  a.nkeys = nkeys;
+  a.leaf_begin = leaf_begin;
+  a.leaf_count = leaf_count;
+  a.in_bits = n;
+  a.party = party;
+  a.unit_bits = pl.unit_bits;
+  a.breadth_bits = pl.breadth_bits;
+  a.dfs_bits = pl.dfs_bits;
+  a.vmask = c->vmask;
+  const uint64_t units = nkeys * (leaf_count >> pl.unit_bits);
+  LaunchCfg cfg;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cfg.block = dim3(kEvalAllThreads);
+  if (c->p.prg == FSSB200_PRG_AES128_MMO) {
+    cfg.grid = dim3(unsigned(units < uint64_t(c->sm_count) ? units : uint64_t(c->sm_count)));
+    cfg.smem = kMaxDynSmem;
+  } else {
+    const uint64_t cap = uint64_t(c->sm_count) * 2;
+    cfg.grid = dim3(unsigned(units < cap ? units : cap));
+    // cw copies + two breadth buffers + DFS stack (+ slack for alignment)
+    cfg.smem = size_t(c->ncw + 1) * 32 + 2 * kEvalAllThreads * 16 +
+        size_t(pl.dfs_bits > 1 ? pl.dfs_bits - 1 : 1) * kEvalAllThreads * 16 + 64;
+  }
+  c->launches++;
+  return int(fn(c->kp, a, cfg));
+}
+
+int fssb200_eval_all(const fssb200_ctx *cc, int party, const void *seeds, const void *cws, const void *ocws,
+    void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  switch (c->p.scheme) {
+    case FSSB200_SCHEME_DPF:
+      return evalall_impl(c, 0, party, seeds, cws, nullptr, ys, nkeys, leaf_begin, leaf_count, stream);
+    case FSSB200_SCHEME_HALFTREE:
+      return evalall_impl(c, 1, party, seeds, cws, ocws, ys, nkeys, leaf_begin, leaf_count, stream);
+    case FSSB200_SCHEME_GROTTO: {
+      if (leaf_begin != 0) return FSSB200_ERANGE;
+      int rc = evalall_impl(c, 2, party, seeds, cws, nullptr, ys, nkeys, 0, leaf_count, stream);
+      if (rc) return rc;
+      if (nkeys == 0) return 0;
+      const uint64_t cnt = leaf_count ? leaf_count : (uint64_t(1) << c->p.in_bits);
+      DeviceGuard g(c->p.device);
+      c->launches++;
+      return int(launch_prefix_xor(static_cast<uint8_t *>(ys), nkeys, cnt, static_cast<cudaStream_t>(stream)));
+    }
+    default:
+      return FSSB200_ESCHEME;  // DCF EvalAll: not yet on the device path
+  }
+}
+
+int fssb200_grotto_expand(const fssb200_ctx *cc, int party, const void *seeds, const void *cws, void *t,
+    size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (c->p.scheme != FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  return evalall_impl(c, 2, party, seeds, cws, nullptr, t, nkeys, leaf_begin, leaf_count, stream);
+}
+
+int fssb200_grotto_preprocess(const fssb200_ctx *cc, int party, const void *seeds, const void *cws, void *pt,
+    size_t nkeys, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (c->p.scheme != FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  if (!pt) return FSSB200_EINVAL;
+  const int n = c->p.in_bits;
+  if (n > 31) return FSSB200_EDOMAIN;
+  const uint64_t N = uint64_t(1) << n;
+  // leaf bits of key k go to pt[k*(2N-1) + N-1 ...] (grotto_dcf.cuh:98), then the internal nodes
+  // are filled level by level, bottom-up (grotto_dcf.cuh:100-103)
+  for (size_t k = 0; k < nkeys; ++k) {
+    uint8_t *tree = static_cast<uint8_t *>(pt) + k * (2 * N - 1);
+    int rc = evalall_impl(c, 2, party, static_cast<const blk *>(seeds) + k,
+        static_cast<const uint8_t *>(cws) + k * size_t(c->ncw) * 32, nullptr, tree + (N - 1), 1, 0, N, stream);
+    if (rc) return rc;
+    DeviceGuard g(c->p.device);
+    for (int lvl = n - 1; lvl >= 0; --lvl) {
+      c->launches++;
+      cudaError_t e = launch_parity_level(tree, lvl, static_cast<cudaStream_t>(stream));
+      if (e != cudaSuccess) return int(e);
+    }
+  }
+  return 0;
+}
+
+int fssb200_grotto_eval(const fssb200_ctx *cc, const void *pt, const void *xs, void *ys, size_t nkeys,
+    void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (c->p.scheme != FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  if (!pt || !xs || !ys) return FSSB200_EINVAL;
+  if (c->p.in_bits > 31) return FSSB200_EDOMAIN;
+  if (nkeys == 0) return 0;
+  DeviceGuard g(c->p.device);
+  c->launches++;
+  return int(launch_grotto_lookup(static_cast<const uint8_t *>(pt), static_cast<const uint8_t *>(xs),
+      static_cast<uint8_t *>(ys), nkeys, c->p.in_bits, c->p.in_bytes, static_cast<cudaStream_t>(stream)));
+}
+
+// ---- PRG known-answer hook ------------------------------------------------------------------------------------------
+int fssb200_prg_gen(const fssb200_ctx *cc, const void *seeds, void *out, int mul, size_t nseeds, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (!seeds || !out) return FSSB200_EINVAL;
+  if (!aligned16(seeds) || !aligned16(out)) return FSSB200_EALIGN;
+  prg_launch_fn fn = get_prg_launcher(c->p.prg, mul);
+  if (!fn) return FSSB200_EINVAL;
+  if (nseeds == 0) return 0;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  // the KAT hook uses keys 0..mul-1 as stored (prg_key), independent of the scheme's mul
+  const LaunchCfg cfg = point_cfg(c, nseeds, static_cast<cudaStream_t>(stream));
+  c->launches++;
+  return int(fn(c->kp, static_cast<const blk *>(seeds), static_cast<blk *>(out), nseeds, cfg));
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------------------------------
+int fssb200_ctx_reserve_host(fssb200_ctx *c, size_t max_keys_per_chunk) {
+  if (int rc = check_common(c)) return rc;
+  if (max_keys_per_chunk == 0) max_keys_per_chunk = size_t(1) << 18;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  // per key: seeds(2 for gen) + cws + ocw + x/alpha(16) + beta + y; evalall output is staged in the
+  // same buffers (>= 64 MiB per set)
+  size_t per_key = 32 + size_t(c->ncw) * 32 + 16 + 16 + 16 + 16;
+  size_t bytes = per_key * max_keys_per_chunk;
+  if (bytes < (size_t(64) << 20)) bytes = size_t(64) << 20;
+  bytes = (bytes + 255) & ~size_t(255);
+  for (int i = 0; i < 2; ++i) {
+    if (a.dev[i]) { cudaFree(a.dev[i]); a.dev[i] = nullptr; }
+    CUDA_TRY(cudaMalloc(&a.dev[i], bytes));
+    if (!a.stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking));
+  }
+  a.chunk_keys = max_keys_per_chunk;
+  a.bytes_per_set = bytes;
+  return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    const void *xs, void *ys, size_t nkeys) {
+  if (int rc = check_common(c)) return rc;
+  if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
+  if (c->p.scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  if (!seeds || !cws || !xs || !ys) return FSSB200_EINVAL;
+  if (c->p.scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  const size_t ck = a.chunk_keys, cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = nkeys - k0 < ck ? nkeys - k0 : ck;
+    const int b = int(chunk & 1);
+    cudaStream_t s = a.stream[b];
+    uint8_t *d_seeds = a.dev[b];
+    uint8_t *d_cws = d_seeds + align_up(k * 16, 256);
+    uint8_t *d_ocws = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_ys = d_xs + align_up(k * 16, 256);
+    CUDA_TRY(cudaMemcpyAsync(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, cudaMemcpyHostToDevice, s));
+    if (ocws)
+      CUDA_TRY(cudaMemcpyAsync(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, cudaMemcpyHostToDevice, s));
+    rc = fssb200_eval(c, party, d_seeds, d_cws, ocws ? d_ocws : nullptr, d_xs, d_ys, k, s);
+    if (rc) break;
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(a.stream[i]);
+    if (!rc && e != cudaSuccess) rc = int(e);
+  }
+  return rc;
+}
+
+int fssb200_gen_host(fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *ocws,
+    size_t nkeys) {
+  if (int rc = check_common(c)) return rc;
+  if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
+  if (!s0s || !alphas || !cws) return FSSB200_EINVAL;
+  const bool grotto = c->p.scheme == FSSB200_SCHEME_GROTTO, half = c->p.scheme == FSSB200_SCHEME_HALFTREE;
+  if ((!grotto && !betas) || (half && !ocws)) return FSSB200_EINVAL;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  const size_t ck = a.chunk_keys, cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = nkeys - k0 < ck ? nkeys - k0 : ck;
+    const int b = int(chunk & 1);
+    cudaStream_t s = a.stream[b];
+    uint8_t *d_s0s = a.dev[b];
+    uint8_t *d_cws = d_s0s + align_up(k * 32, 256);
+    uint8_t *d_ocws = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_al = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_be = d_al + align_up(k * 16, 256);
+    CUDA_TRY(cudaMemcpyAsync(d_s0s, static_cast<const uint8_t *>(s0s) + k0 * 32, k * 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_al, static_cast<const uint8_t *>(alphas) + k0 * ib, k * ib, cudaMemcpyHostToDevice, s));
+    if (!grotto)
+      CUDA_TRY(cudaMemcpyAsync(d_be, static_cast<const uint8_t *>(betas) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
+    rc = fssb200_gen(c, d_s0s, d_al, grotto ? nullptr : d_be, d_cws, half ? d_ocws : nullptr, k, s);
+    if (rc) break;
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(cws) + k0 * cwb, d_cws, k * cwb, cudaMemcpyDeviceToHost, s));
+    if (half)
+      CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ocws) + k0 * 16, d_ocws, k * 16, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(a.stream[i]);
+    if (!rc && e != cudaSuccess) rc = int(e);
+  }
+  return rc;
+}
+
+int fssb200_eval_all_host(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count) {
+  if (int rc = check_common(c)) return rc;
+  if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
+  if (c->p.scheme == FSSB200_SCHEME_DCF) return FSSB200_ESCHEME;
+  if (!seeds || !cws || !ys) return FSSB200_EINVAL;
+  const bool half = c->p.scheme == FSSB200_SCHEME_HALFTREE, grotto = c->p.scheme == FSSB200_SCHEME_GROTTO;
+  if (half && !ocws) return FSSB200_EINVAL;
+  const int n = c->p.in_bits;
+  if (n > 40) return FSSB200_EDOMAIN;
+  const uint64_t N = uint64_t(1) << n;
+  if (leaf_begin >= N) return FSSB200_ERANGE;
+  if (leaf_count == 0) leaf_count = N - leaf_begin;
+  if (leaf_begin + leaf_count > N) return FSSB200_ERANGE;
+  const uint64_t granule = fssb200_eval_all_granule(c);
+  if ((leaf_begin | leaf_count) & (granule - 1)) return FSSB200_ERANGE;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  const size_t cwb = size_t(c->ncw) * 32, leaf_bytes = grotto ? 1 : 16;
+  // key material of one key (seed + cws + ocw) at the front of each set, leaves behind it
+  const size_t hdr = align_up(16 + cwb + 16, 256);
+  uint64_t leaves_per_chunk = ((a.bytes_per_set - hdr) / leaf_bytes) / granule * granule;
+  if (leaves_per_chunk == 0) return FSSB200_ENOARENA;
+  if (grotto) leaves_per_chunk = leaf_count <= leaves_per_chunk ? leaf_count : 0;  // the scan needs whole keys
+  if (leaves_per_chunk == 0) return FSSB200_ENOARENA;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k = 0; k < nkeys && !rc; ++k) {
+    for (uint64_t l0 = 0; l0 < leaf_count && !rc; l0 += leaves_per_chunk, ++chunk) {
+      const uint64_t cnt = leaf_count - l0 < leaves_per_chunk ? leaf_count - l0 : leaves_per_chunk;
+      const int b = int(chunk & 1);
+      cudaStream_t s = a.stream[b];
+      uint8_t *d_seed = a.dev[b], *d_cws = d_seed + 16, *d_ocw = d_cws + cwb, *d_ys = a.dev[b] + hdr;
+      CUDA_TRY(cudaMemcpyAsync(d_seed, static_cast<const uint8_t *>(seeds) + k * 16, 16, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(d_cws, static_cast<const uint8_t *>(cws) + k * cwb, cwb, cudaMemcpyHostToDevice, s));
+      if (half)
+        CUDA_TRY(cudaMemcpyAsync(d_ocw, static_cast<const uint8_t *>(ocws) + k * 16, 16, cudaMemcpyHostToDevice, s));
+      rc = fssb200_eval_all(c, party, d_seed, d_cws, half ? d_ocw : nullptr, d_ys, 1, leaf_begin + l0, cnt, s);
+      if (rc) break;
+      CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ys) + (k * leaf_count + l0) * leaf_bytes, d_ys, cnt * leaf_bytes,
+          cudaMemcpyDeviceToHost, s));
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(a.stream[i]);
+    if (!rc && e != cudaSuccess) rc = int(e);
+  }
+  return rc;
+}
+
+int fssb200_microbench(int device, int kind, double *ops_per_s) {
+  if (!ops_per_s) return FSSB200_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FSSB200_ENODEVICE;
+  DeviceGuard g(device);
+  if (g.err != cudaSuccess) return int(g.err);
+  return run_microbench(kind, ops_per_s);
+}
+
+}  // extern "C"
+
+namespace fssb200 {
+
+point_launch_fn get_point_launcher(int scheme, int gk, int prg, bool lm) {
+  if (prg == kPrgAes) {
+    if (scheme == FSSB200_SCHEME_DPF) return point_launcher_aes_dpf(gk, lm);
+    if (scheme == FSSB200_SCHEME_DCF) return point_launcher_aes_dcf(gk, lm);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_aes_ht(gk, lm);
+  } else {
+    if (scheme == FSSB200_SCHEME_DPF) return point_launcher_chacha_dpf(gk, lm);
+    if (scheme == FSSB200_SCHEME_DCF) return point_launcher_chacha_dcf(gk, lm);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_chacha_ht(gk, lm);
+  }
+  return nullptr;
+}
+gen_launch_fn get_gen_launcher(int scheme, int gk, int prg) {
+  if (prg == kPrgAes) {
+    if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_aes_dpf(gk);
+    if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_aes_dcf(gk);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_aes_ht(gk);
+  } else {
+    if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_chacha_dpf(gk);
+    if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_chacha_dcf(gk);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_chacha_ht(gk);
+  }
+  return nullptr;
+}
+evalall_launch_fn get_evalall_launcher(int mode, int gk, int prg) {
+  if (prg == kPrgAes) {
+    if (mode == 0) return evalall_launcher_aes_dpf(gk);
+    if (mode == 1) return evalall_launcher_aes_ht(gk);
+    if (mode == 2) return evalall_launcher_aes_grotto(gk);
+  } else {
+    if (mode == 0) return evalall_launcher_chacha_dpf(gk);
+    if (mode == 1) return evalall_launcher_chacha_ht(gk);
+    if (mode == 2) return evalall_launcher_chacha_grotto(gk);
+  }
+  return nullptr;
+}
+prg_launch_fn get_prg_launcher(int prg, int mul) {
+  return prg == kPrgAes ? prg_launcher_aes(mul) : prg_launcher_chacha(mul);
+}
+
+}  // namespace fssb200

@@ -1,0 +1,302 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// kernels.cuh -- sm_100a kernels: batched point evaluation, key generation, full-domain
+// evaluation.  Instantiated per (scheme, group kind, PRG) in kernels_*.cu.
+//
+// Shared-memory plan of the AES kernels (one persistent CTA per SM, 227 KB dynamic smem):
+//   [a0, a0+128K)    lane-replicated T-tables, a0 = first 64 KiB-aligned shared-window address
+//   [base, a0)       "low" scratch  (63 KB when the driver reserves the first 1 KB)
+//   [a0+128K, end)   "high" scratch (36 KB)
+// ChaCha kernels have no tables; their scratch is one region.
+#pragma once
+#include "schemes.cuh"
+
+namespace fssb200 {
+
+struct KParams {
+  PrgKeys keys;
+  GroupArgs ga;
+};
+
+constexpr int kPointThreads = 512;   // AES point / gen kernels: 16 warps, 1 CTA per SM
+constexpr int kEvalAllThreads = 512;
+constexpr int kEvalAllThreadBits = 9;
+constexpr int kMaxDfsBits = 8;
+constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB opt-in limit on sm_100
+
+// ---- shared-memory helpers ----------------------------------------------------------------------------------
+FSS_D uint32_t smem_base_addr() {
+  extern __shared__ __align__(16) uint8_t fss_dyn_smem[];
+  return static_cast<uint32_t>(__cvta_generic_to_shared(fss_dyn_smem));
+}
+FSS_D uint32_t dyn_smem_size() {
+  uint32_t d;
+  asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(d));
+  return d;
+}
+FSS_D blk lds_blk(uint32_t addr) {
+  blk b;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(addr) : "memory");
+  return b;
+}
+FSS_D void sts_blk(uint32_t addr, blk b) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+// two adjacent leaves with one 256-bit store (STG.E.256)
+FSS_D void stg_blk2(void *p, blk a, blk b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+struct SmemPlan {
+  uint32_t a0;               // table base (AES) -- 64 KiB aligned
+  uint32_t lo, lo_end;       // scratch region below the tables
+  uint32_t hi, hi_end;       // scratch region above the tables
+  // bump allocation, 16-byte aligned; prefers the region given by `want_hi`
+  FSS_D uint32_t alloc(uint32_t bytes, bool want_hi) {
+    bytes = (bytes + 15u) & ~15u;
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool use_hi = (pass == 0) ? want_hi : !want_hi;
+      if (use_hi) {
+        if (hi + bytes <= hi_end) { const uint32_t r = hi; hi += bytes; return r; }
+      } else {
+        if (lo + bytes <= lo_end) { const uint32_t r = lo; lo += bytes; return r; }
+      }
+    }
+    __trap();  // host-side geometry (api.cu: plan_evalall) guarantees this cannot happen
+    return 0;
+  }
+};
+
+template <int PRG>
+FSS_D SmemPlan smem_plan() {
+  SmemPlan p;
+  const uint32_t base = smem_base_addr();
+  const uint32_t end = base + dyn_smem_size();
+  if (Prg<PRG>::kNeedsTables) {
+    p.a0 = (base + 0xffffu) & ~0xffffu;
+    if (p.a0 + kAesTblBytes > end) __trap();
+    p.lo = (base + 15u) & ~15u;
+    p.lo_end = p.a0;
+    p.hi = p.a0 + kAesTblBytes;
+    p.hi_end = end;
+  } else {
+    p.a0 = 0;
+    p.lo = p.lo_end = 0;
+    p.hi = (base + 15u) & ~15u;
+    p.hi_end = end;
+  }
+  return p;
+}
+
+template <int PRG>
+FSS_D typename Prg<PRG>::ctx_t prg_ctx_init(const SmemPlan &sp);
+template <>
+FSS_D AesCtx prg_ctx_init<kPrgAes>(const SmemPlan &sp) {
+  aes_tables_init(sp.a0);
+  __syncthreads();
+  AesCtx c;
+  c.laneoff = sp.a0 | ((threadIdx.x & 31u) << 2);
+  return c;
+}
+template <>
+FSS_D NoCtx prg_ctx_init<kPrgChaCha>(const SmemPlan &) {
+  return NoCtx{};
+}
+
+// ---- batched point evaluation --------------------------------------------------------------------------------
+// One key per thread, grid-stride.  SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE}.
+template <int SCHEME, int G, int PRG, bool LEVEL_MAJOR>
+__global__ void __launch_bounds__(kPointThreads, 1)
+point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArgs A) {
+  SmemPlan sp = smem_plan<PRG>();
+  const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
+  const int n = A.in_bits;
+  const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE) ? n : n + 1;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < A.nkeys; k += stride) {
+    const blk s0 = ld_blk(A.seeds + k);
+    const InVal x = load_in(A.xs + k * uint64_t(A.in_bytes), A.in_bytes);
+    blk y;
+    if (LEVEL_MAJOR) {
+      const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, k};
+      if (SCHEME == FSSB200_SCHEME_DPF) y = dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
+      else if (SCHEME == FSSB200_SCHEME_DCF) y = dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
+      else y = ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
+    } else {
+      const CwKeyMajor cw{A.cws + k * uint64_t(ncw) * 32u};
+      if (SCHEME == FSSB200_SCHEME_DPF) y = dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
+      else if (SCHEME == FSSB200_SCHEME_DCF) y = dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
+      else y = ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
+    }
+    st_blk(A.ys + k, y);
+  }
+}
+
+// ---- batched key generation --------------------------------------------------------------------------------------
+template <int SCHEME, int G, int PRG>
+__global__ void __launch_bounds__(kPointThreads, 1)
+gen_kernel(const __grid_constant__ KParams P, const __grid_constant__ GenArgs A) {
+  SmemPlan sp = smem_plan<PRG>();
+  const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
+  const int n = A.in_bits;
+  const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE) ? n : n + 1;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < A.nkeys; k += stride) {
+    const blk s0 = ld_blk(A.s0s + 2 * k), s1 = ld_blk(A.s0s + 2 * k + 1);
+    const InVal a = load_in(A.alphas + k * uint64_t(A.in_bytes), A.in_bytes);
+    const blk beta = A.betas ? ld_blk(A.betas + k) : zero_blk();
+    uint8_t *cws = A.cws + k * uint64_t(ncw) * 32u;
+    if (SCHEME == FSSB200_SCHEME_DPF) {
+      dpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws);
+    } else if (SCHEME == FSSB200_SCHEME_DCF) {
+      dcf_gen_body<G, PRG>(P.keys, P.ga, pc, n, A.pred, s0, s1, a, beta, cws);
+    } else {
+      blk ocw;
+      ht_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws, &ocw);
+      st_blk(A.ocws + k, ocw);
+    }
+  }
+}
+
+// ---- PRG known-answer kernel ------------------------------------------------------------------------------------------
+template <int PRG, int MUL>
+__global__ void __launch_bounds__(kPointThreads, 1)
+prg_kernel(const __grid_constant__ KParams P, const blk *seeds, blk *out, uint64_t n) {
+  SmemPlan sp = smem_plan<PRG>();
+  const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    blk o[MUL];
+    Prg<PRG>::template gen<MUL>(P.keys, pc, ld_blk(seeds + i), o);
+#pragma unroll
+    for (int j = 0; j < MUL; ++j) st_blk(out + i * MUL + j, o[j]);
+  }
+}
+
+// ---- full-domain evaluation (DPF / Half-Tree / Grotto leaf bits) -----------------------------------------------------------
+// Work unit = the subtree of 2^unit_bits leaves below one node at depth du = n - unit_bits.
+//   phase 0  warp 0 walks the du levels from the key's root to the unit root (1 node / level)
+//   phase 1  breadth-first in shared memory: `breadth_bits` levels, one __syncthreads each
+//   phase 2  every thread owns one node and expands its 2^dfs_bits leaves depth-first: an explicit
+//            stack of right siblings in shared memory ([depth][thread], conflict-free 128-bit
+//            accesses), ONE copy of the node-expansion code; the bottom step turns a node into two
+//            adjacent leaves and writes them with a single 256-bit store.
+// Every node is expanded exactly once (2 PRG blocks per DPF node, 1 per Half-Tree node).
+// MODE: 0 = DPF leaves (16 B), 1 = Half-Tree leaves (16 B), 2 = Grotto leaf control bits (1 B).
+template <int MODE, int G, int PRG>
+__global__ void __launch_bounds__(kEvalAllThreads, 1)
+evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAllArgs A) {
+  SmemPlan sp = smem_plan<PRG>();
+  const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
+  const int n = A.in_bits;
+  const int tid = threadIdx.x;
+  const bool half = (MODE == 1);
+  const int ncw = half ? n : n + 1;
+  const int dfs = A.dfs_bits, bt = A.breadth_bits;
+  const int du = n - A.unit_bits;
+  // scratch: per-level correction words {cwl, cwr}, two breadth buffers, the DFS stack
+  const uint32_t s_cw = sp.alloc(uint32_t(ncw + 1) * 32u, true);
+  const uint32_t s_bfs = sp.alloc(2u * kEvalAllThreads * 16u, true);
+  const uint32_t s_stk = sp.alloc(uint32_t(dfs > 1 ? dfs - 1 : 1) * kEvalAllThreads * 16u, false);
+
+  const uint64_t upk = A.leaf_count >> A.unit_bits;  // units per key
+  const uint64_t total = A.nkeys * upk;
+  uint64_t cur_key = ~uint64_t(0);
+  for (uint64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const uint64_t key = unit / upk;
+    const uint64_t leaf0 = A.leaf_begin + ((unit - key * upk) << A.unit_bits);  // first leaf of the unit
+    __syncthreads();  // previous unit done with s_cw / s_bfs
+    if (key != cur_key) {
+      cur_key = key;
+      const uint8_t *kc = A.cws + key * uint64_t(ncw) * 32u;
+      for (int i = tid; i < ncw; i += kEvalAllThreads) {
+        const blk cs = ld_blk(kc + 32 * i);
+        blk cr = cs;  // right-child correction word: clamp bit := tr_cw (bool at byte 16)
+        if (!half) cr.w = (cs.w & ~1u) | uint32_t(__ldg(kc + 32 * i + 16) != 0);
+        sts_blk(s_cw + 32u * i, cs);
+        sts_blk(s_cw + 32u * i + 16u, half ? ld_blk(kc + 32 * i + 16) : cr);
+      }
+      __syncthreads();
+    }
+    // ---- phase 0: root -> unit root ----
+    if (tid < 32) {
+      blk st = clamp(ld_blk(A.seeds + key));
+      st.w |= uint32_t(A.party);
+      const uint64_t path = leaf0 >> A.unit_bits;
+      for (int i = 0; i < du; ++i) {
+        const uint32_t bit = uint32_t(path >> (du - 1 - i)) & 1u;
+        blk l, r;
+        if (half) ht_expand<PRG>(P.keys, pc, st, lds_blk(s_cw + 32u * i), l, r);
+        else dpf_expand<PRG>(P.keys, pc, st, lds_blk(s_cw + 32u * i), lds_blk(s_cw + 32u * i + 16u), l, r);
+        st = bit ? r : l;
+      }
+      if (tid == 0) sts_blk(s_bfs, st);
+    }
+    __syncthreads();
+    // ---- phase 1: breadth-first, levels du .. du+bt-1 ----
+    for (int j = 0; j < bt; ++j) {
+      const uint32_t src = s_bfs + uint32_t(j & 1) * (kEvalAllThreads * 16u);
+      const uint32_t dst = s_bfs + uint32_t((j + 1) & 1) * (kEvalAllThreads * 16u);
+      if (tid < (1 << j)) {
+        const blk st = lds_blk(src + 16u * tid);
+        const int lvl = du + j;
+        blk l, r;
+        if (half) ht_expand<PRG>(P.keys, pc, st, lds_blk(s_cw + 32u * lvl), l, r);
+        else dpf_expand<PRG>(P.keys, pc, st, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+        sts_blk(dst + 32u * tid, l);
+        sts_blk(dst + 32u * tid + 16u, r);
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: per-thread depth-first over dfs levels ----
+    if (tid < (1 << bt)) {
+      blk cur = lds_blk(s_bfs + uint32_t(bt & 1) * (kEvalAllThreads * 16u) + 16u * tid);
+      const int lvl0 = du + bt;  // tree level of `cur`
+      const uint64_t out0 = key * A.leaf_count + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
+      const uint32_t pairs = 1u << (dfs - 1);
+      uint32_t done = 0;  // leaf pairs emitted
+      int d = 0;
+      while (true) {
+        const int lvl = lvl0 + d;
+        if (d == dfs - 1) {
+          // bottom: node at tree level n-1 -> leaves 2*done, 2*done+1 of this thread
+          if (MODE == 1) {
+            const blk cwl = lds_blk(s_cw + 32u * lvl), ex = lds_blk(s_cw + 32u * lvl + 16u);
+            const blk ocw = ld_blk(A.ocws + key);
+            const blk y0 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), cur, 0u, cwl, cwl.w & 1u, ocw);
+            const blk y1 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), cur, 1u, cwl, uint32_t((ex.x & 0xffu) != 0), ocw);
+            stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, y0, y1);
+          } else {
+            blk l, r;
+            dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+            if (MODE == 0) {
+              const blk ocw = lds_blk(s_cw + 32u * n);
+              stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, dpf_leaf<G>(P.ga, uint32_t(A.party), l, ocw),
+                  dpf_leaf<G>(P.ga, uint32_t(A.party), r, ocw));
+            } else {
+              // Grotto: leaf control bits, one byte per leaf (grotto_dcf.cuh:190-194)
+              uint8_t *o = static_cast<uint8_t *>(A.ys) + out0 + 2 * done;  // any alignment (parity trees)
+              o[0] = uint8_t(lsb(l));
+              o[1] = uint8_t(lsb(r));
+            }
+          }
+          ++done;
+          if (done == pairs) break;
+          d = dfs - 1 - __ffs(int(done)) + 1;  // depth of the pending right sibling: dfs-1 - ctz(done)
+          cur = lds_blk(s_stk + (uint32_t(d - 1) * kEvalAllThreads + tid) * 16u);
+        } else {
+          blk l, r;
+          if (half) ht_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), l, r);
+          else dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          sts_blk(s_stk + (uint32_t(d) * kEvalAllThreads + tid) * 16u, r);  // slot of depth d+1
+          cur = l;
+          ++d;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace fssb200

@@ -1,0 +1,109 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// kernels_inst.cu -- explicit kernel instantiations + launchers.  Compiled once per
+//   -DFSS_INST_KIND={1 point, 2 gen, 3 evalall, 4 prg}
+//   -DFSS_INST_PRG={0 aes, 1 chacha}
+//   -DFSS_INST_SCHEME={0 dpf, 1 dcf, 2 halftree, 3 grotto}   (ignored for kind 4)
+// (see fss_b200/csrc/Makefile) so the ~160 instantiations build in parallel.
+#include "dispatch.h"
+
+namespace fssb200 {
+
+template <class Kern, class... Args>
+static cudaError_t launch_kernel(Kern kern, const LaunchCfg &c, const Args &...args) {
+  if (c.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem));
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<c.grid, c.block, c.smem, c.stream>>>(args...);
+  return cudaGetLastError();
+}
+
+#if FSS_INST_PRG == 0
+#define PRGNAME aes
+constexpr int kInstPrg = kPrgAes;
+#else
+#define PRGNAME chacha
+constexpr int kInstPrg = kPrgChaCha;
+#endif
+
+#if FSS_INST_SCHEME == 0
+#define SCHNAME dpf
+#elif FSS_INST_SCHEME == 1
+#define SCHNAME dcf
+#elif FSS_INST_SCHEME == 2
+#define SCHNAME ht
+#else
+#define SCHNAME grotto
+#endif
+
+#define CAT3_(a, b, c) a##b##_##c
+#define CAT3(a, b, c) CAT3_(a, b, c)
+
+#define FOR_EACH_GK(X) X(kGrpBytes) X(kGrpU32) X(kGrpU64) X(kGrpU127) X(kGrpU32Mod) X(kGrpU64Mod) X(kGrpU128Mod)
+
+#if FSS_INST_KIND == 1
+template <int G, bool LM>
+static cudaError_t point_launch(const KParams &P, const PointArgs &A, const LaunchCfg &c) {
+  return launch_kernel(point_kernel<FSS_INST_SCHEME, G, kInstPrg, LM>, c, P, A);
+}
+point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, bool lm) {
+  switch (gk) {
+#define X(GK) \
+  case GK: return lm ? &point_launch<GK, true> : &point_launch<GK, false>;
+    FOR_EACH_GK(X)
+#undef X
+  }
+  return nullptr;
+}
+#elif FSS_INST_KIND == 2
+template <int G>
+static cudaError_t gen_launch(const KParams &P, const GenArgs &A, const LaunchCfg &c) {
+  return launch_kernel(gen_kernel<FSS_INST_SCHEME, G, kInstPrg>, c, P, A);
+}
+gen_launch_fn CAT3(gen_launcher_, PRGNAME, SCHNAME)(int gk) {
+  switch (gk) {
+#define X(GK) \
+  case GK: return &gen_launch<GK>;
+    FOR_EACH_GK(X)
+#undef X
+  }
+  return nullptr;
+}
+#elif FSS_INST_KIND == 3
+#if FSS_INST_SCHEME == 3
+static cudaError_t evalall_launch_grotto(const KParams &P, const EvalAllArgs &A, const LaunchCfg &c) {
+  return launch_kernel(evalall_kernel<2, kGrpBytes, kInstPrg>, c, P, A);
+}
+evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int) { return &evalall_launch_grotto; }
+#else
+constexpr int kMode = FSS_INST_SCHEME == 2 ? 1 : 0;
+template <int G>
+static cudaError_t evalall_launch(const KParams &P, const EvalAllArgs &A, const LaunchCfg &c) {
+  return launch_kernel(evalall_kernel<kMode, G, kInstPrg>, c, P, A);
+}
+evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int gk) {
+  switch (gk) {
+#define X(GK) \
+  case GK: return &evalall_launch<GK>;
+    FOR_EACH_GK(X)
+#undef X
+  }
+  return nullptr;
+}
+#endif
+#elif FSS_INST_KIND == 4
+template <int MUL>
+static cudaError_t prg_launch(const KParams &P, const blk *seeds, blk *out, uint64_t n, const LaunchCfg &c) {
+  return launch_kernel(prg_kernel<kInstPrg, MUL>, c, P, seeds, out, n);
+}
+#define CAT2_(a, b) a##b
+#define CAT2(a, b) CAT2_(a, b)
+prg_launch_fn CAT2(prg_launcher_, PRGNAME)(int mul) {
+  return mul == 1 ? &prg_launch<1> : (mul == 2 ? &prg_launch<2> : (mul == 4 ? &prg_launch<4> : nullptr));
+}
+#else
+#error "FSS_INST_KIND must be 1..4"
+#endif
+
+}  // namespace fssb200

@@ -1,0 +1,342 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// schemes.cuh -- per-thread bodies of the DPF / DCF / Half-Tree walks and key generation.
+//
+// Node representation: a tree node is ONE packed 16-byte block, seed with the control bit t in
+// the clamp bit (the reference's `st`, dpf.cuh:233-236, eval_all_gpu.cuh:154-178).  Because the
+// stored correction word already carries tl_cw in its clamp bit (dpf.cuh:148), the whole
+// "if (t) { s ^= s_cw; t ^= t_cw }" update of dpf.cuh:189-194 is one masked XOR of the packed
+// block: child = G(s) ^ (-(t) & cw'), with cw' = s_cw whose clamp bit is tl_cw (left) or tr_cw
+// (right).  4 LOP3 per child.
+//
+// Everything here is FSS_HD: the same code runs per CUDA thread and, in tests/host_emul, per key
+// on the CPU.
+#pragma once
+#include "group.cuh"
+#include "prg.cuh"
+
+namespace fssb200 {
+
+FSS_HD blk ld_blk(const void *p) {
+#if FSS_DEVICE_CODE
+  const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+#else
+  const uint4 t = *reinterpret_cast<const uint4 *>(p);
+#endif
+  return make_blk(t.x, t.y, t.z, t.w);
+}
+FSS_HD void st_blk(void *p, blk b) { *reinterpret_cast<uint4 *>(p) = make_uint4(b.x, b.y, b.z, b.w); }
+
+// ---- correction-word accessors ------------------------------------------------------------------------
+// Key-major: the reference's own array-of-structs, 32 B per level (dpf.cuh:76-81, dcf.cuh:91-96).
+struct CwKeyMajor {
+  const uint8_t *base;  // this key's Cw[ncw]
+  FSS_HD blk s(int i) const { return ld_blk(base + 32 * i); }
+  FSS_HD blk v(int i) const { return ld_blk(base + 32 * i + 16); }
+  // Dpf::Cw::tr / HalfTreeDpf::Cw::extra: a C++ bool at byte 16, tested as != 0
+  FSS_HD uint32_t flag(int i) const {
+#if FSS_DEVICE_CODE
+    return __ldg(base + 32 * i + 16) != 0;
+#else
+    return base[32 * i + 16] != 0;
+#endif
+  }
+  FSS_HD blk out_s(int n) const { return s(n); }  // cws[n].s  (DPF)
+  FSS_HD blk out_v(int n) const { return v(n); }  // cws[n].v  (DCF)
+};
+// Level-major (fssb200_relayout; point_eval_gpu.cuh:39-91 with >32-level control words).
+struct CwLevelMajor {
+  const blk *cw_s;
+  const blk *cw_v;
+  const uint32_t *extra;
+  const blk *out_cw;
+  uint64_t nkeys, k;
+  FSS_HD blk s(int i) const { return ld_blk(cw_s + uint64_t(i) * nkeys + k); }
+  FSS_HD blk v(int i) const { return ld_blk(cw_v + uint64_t(i) * nkeys + k); }
+  FSS_HD uint32_t flag(int i) const { return (extra[uint64_t(i >> 5) * nkeys + k] >> (i & 31)) & 1u; }
+  FSS_HD blk out_s(int) const { return ld_blk(out_cw + k); }
+  FSS_HD blk out_v(int) const { return ld_blk(out_cw + k); }
+};
+
+// ---- DPF ------------------------------------------------------------------------------------------------
+// Leaf conversion, dpf.cuh:207-213 / :255-263.
+template <int G>
+FSS_HD blk dpf_leaf(const GroupArgs &ga, uint32_t party, blk st, blk out_cw) {
+  typedef Grp<G> GR;
+  typename GR::V y = GR::from(ga, clamp(st));
+  y = GR::add_masked(ga, y, 0u - lsb(st), GR::from(ga, out_cw));
+  y = GR::cneg(ga, y, party);
+  return GR::into(ga, y);
+}
+
+// Dpf::Eval, dpf.cuh:170-214.  One PRG block per level: only the child on the path.
+template <int G, int PRG, class Cw>
+FSS_HD blk dpf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
+    uint32_t party, blk s0, const InVal &x, const Cw &cw) {
+  blk st = clamp(s0);
+  st.w |= party;                                   // t = b (dpf.cuh:173)
+  blk cs = cw.s(0);
+  uint32_t cf = cw.flag(0);
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    // prefetch the next level's correction word (entry n is the output CW)
+    const blk cs_next = (i + 1 < n) ? cw.s(i + 1) : cw.out_s(n);
+    const uint32_t cf_next = (i + 1 < n) ? cw.flag(i + 1) : 0u;
+    const uint32_t xb = in_bit(x, n - 1 - i);      // MSB first (dpf.cuh:196)
+    const uint32_t tm = 0u - lsb(st);
+    blk c[1];
+    Prg<PRG>::template gen_child<1>(K, pc, clamp(st), xb, c);
+    blk cwp = cs;                                  // clamp bit := (xb ? tr_cw : tl_cw)
+    cwp.w = (cs.w & ~1u) | (xb ? cf : (cs.w & 1u));
+    st = xor_masked(c[0], tm, cwp);
+    cs = cs_next;
+    cf = cf_next;
+  }
+  return dpf_leaf<G>(ga, party, st, cs);           // cs == cws[n].s
+}
+
+// Dpf::Gen, dpf.cuh:93-159.  Writes Cw[n+1] (32 B each, padding zeroed).
+template <int G, int PRG>
+FSS_HD void dpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
+    blk s0, blk s1, const InVal &a, blk beta, uint8_t *cws) {
+  typedef Grp<G> GR;
+  s0 = clamp(s0);
+  s1 = clamp(s1);
+  uint32_t t0 = 0, t1 = 1;
+  beta = clamp(beta);
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    blk g0[2], g1[2];
+    Prg<PRG>::template gen<2>(K, pc, s0, g0);
+    Prg<PRG>::template gen<2>(K, pc, s1, g1);
+    const uint32_t ab = in_bit(a, n - 1 - i);
+    const uint32_t am = 0u - ab;
+    // keep = child on alpha's path, lose = the other one
+    const blk lose0 = xor_masked(g0[1], am, g0[0] ^ g0[1]);   // ab ? g0[0] : g0[1]
+    const blk lose1 = xor_masked(g1[1], am, g1[0] ^ g1[1]);
+    const blk keep0 = xor_masked(g0[0], am, g0[0] ^ g0[1]);   // ab ? g0[1] : g0[0]
+    const blk keep1 = xor_masked(g1[0], am, g1[0] ^ g1[1]);
+    blk s_cw = clamp(lose0 ^ lose1);                           // dpf.cuh:115-117
+    const uint32_t tl_cw = (lsb(g0[0]) ^ lsb(g1[0]) ^ ab ^ 1u) & 1u;  // :119
+    const uint32_t tr_cw = (lsb(g0[1]) ^ lsb(g1[1]) ^ ab) & 1u;       // :120
+    const uint32_t tk_cw = ab ? tr_cw : tl_cw;
+    const blk ns0 = xor_masked(clamp(keep0), 0u - t0, s_cw);
+    const blk ns1 = xor_masked(clamp(keep1), 0u - t1, s_cw);
+    t0 = lsb(keep0) ^ (t0 & tk_cw);
+    t1 = lsb(keep1) ^ (t1 & tk_cw);
+    s0 = ns0;
+    s1 = ns1;
+    s_cw.w |= tl_cw;
+    st_blk(cws + 32 * i, s_cw);
+    st_blk(cws + 32 * i + 16, make_blk(tr_cw, 0, 0, 0));       // :151-153
+  }
+  typename GR::V v = GR::add(ga, GR::add(ga, GR::from(ga, beta), GR::neg(ga, GR::from(ga, s0))), GR::from(ga, s1));
+  v = GR::cneg(ga, v, t1);                                      // :156-157
+  st_blk(cws + 32 * n, GR::into(ga, v));
+  st_blk(cws + 32 * n + 16, zero_blk());
+}
+
+// ---- DCF ------------------------------------------------------------------------------------------------
+// Dcf::Eval, dcf.cuh:205-276.  Two PRG blocks per level (s and v of the chosen side).  The running
+// value is accumulated without the party sign; -(a+b) = (-a)+(-b) in every supported group, so the
+// sign of dcf.cuh:244-252 is applied once at the end.
+template <int G, int PRG, class Cw>
+FSS_HD blk dcf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
+    uint32_t party, blk s0, const InVal &x, const Cw &cw) {
+  typedef Grp<G> GR;
+  blk st = clamp(s0);
+  st.w |= party;
+  typename GR::V acc = GR::zero(ga);
+  blk cs = cw.s(0), cv = cw.v(0);
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const blk cs_next = (i + 1 < n) ? cw.s(i + 1) : zero_blk();
+    const blk cv_next = (i + 1 < n) ? cw.v(i + 1) : cw.out_v(n);  // entry n = {0, v_cw_{n+1}}
+    const uint32_t xb = in_bit(x, n - 1 - i);
+    const uint32_t t = lsb(st);
+    const uint32_t tm = 0u - t;
+    blk c[2];
+    Prg<PRG>::template gen_child<2>(K, pc, clamp(st), xb, c);
+    // value: v += v_side (+ v_cw if t)   (t of the CURRENT node, dcf.cuh:244-252)
+    acc = GR::add(ga, acc, GR::from(ga, clamp(c[1])));
+    acc = GR::add_masked(ga, acc, tm, GR::from(ga, clamp(cv)));
+    // seed: tl_cw = lsb(cw.s), tr_cw = lsb(cw.v)  (dcf.cuh:214-220)
+    blk cwp = cs;
+    cwp.w = (cs.w & ~1u) | ((xb ? cv.w : cs.w) & 1u);
+    st = xor_masked(c[0], tm, cwp);
+    cs = cs_next;
+    cv = cv_next;
+  }
+  acc = GR::add(ga, acc, GR::from(ga, clamp(st)));              // dcf.cuh:263-275
+  acc = GR::add_masked(ga, acc, 0u - lsb(st), GR::from(ga, cv));
+  return GR::into(ga, GR::cneg(ga, acc, party));
+}
+
+// Dcf::Gen, dcf.cuh:108-194.
+template <int G, int PRG>
+FSS_HD void dcf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
+    int pred, blk s0, blk s1, const InVal &a, blk beta, uint8_t *cws) {
+  typedef Grp<G> GR;
+  typedef typename GR::V V;
+  s0 = clamp(s0);
+  s1 = clamp(s1);
+  uint32_t t0 = 0, t1 = 1;
+  V v = GR::zero(ga);
+  const V vbeta = GR::from(ga, clamp(beta));
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    blk g0[4], g1[4];  // {s_l, v_l, s_r, v_r}  (dcf.cuh:122)
+    Prg<PRG>::template gen<4>(K, pc, s0, g0);
+    Prg<PRG>::template gen<4>(K, pc, s1, g1);
+    const uint32_t ab = in_bit(a, n - 1 - i);
+    const blk s0l = g0[0], s0r = g0[2], s1l = g1[0], s1r = g1[2];
+    const V v0l = GR::from(ga, clamp(g0[1])), v0r = GR::from(ga, clamp(g0[3]));
+    const V v1l = GR::from(ga, clamp(g1[1])), v1r = GR::from(ga, clamp(g1[3]));
+    blk s_cw = ab ? clamp(s0l ^ s1l) : clamp(s0r ^ s1r);       // :143-145
+    V v_cw = GR::neg(ga, v);                                    // :147
+    if (!ab) {
+      v_cw = GR::add(ga, GR::add(ga, v_cw, v1r), GR::neg(ga, v0r));
+      if (pred == FSSB200_PRED_GT) v_cw = GR::add(ga, v_cw, vbeta);
+    } else {
+      v_cw = GR::add(ga, GR::add(ga, v_cw, v1l), GR::neg(ga, v0l));
+      if (pred == FSSB200_PRED_LT) v_cw = GR::add(ga, v_cw, vbeta);
+    }
+    v_cw = GR::cneg(ga, v_cw, t1);                              // :155
+    if (!ab) v = GR::add(ga, GR::add(ga, v, GR::neg(ga, v1l)), v0l);
+    else v = GR::add(ga, GR::add(ga, v, GR::neg(ga, v1r)), v0r);
+    v = GR::add(ga, v, GR::cneg(ga, v_cw, t1));                 // :159-160
+    const uint32_t tl_cw = (lsb(s0l) ^ lsb(s1l) ^ ab ^ 1u) & 1u;
+    const uint32_t tr_cw = (lsb(s0r) ^ lsb(s1r) ^ ab) & 1u;
+    const uint32_t tk_cw = ab ? tr_cw : tl_cw;
+    const blk keep0 = ab ? s0r : s0l, keep1 = ab ? s1r : s1l;
+    const blk ns0 = xor_masked(clamp(keep0), 0u - t0, s_cw);
+    const blk ns1 = xor_masked(clamp(keep1), 0u - t1, s_cw);
+    t0 = lsb(keep0) ^ (t0 & tk_cw);
+    t1 = lsb(keep1) ^ (t1 & tk_cw);
+    s0 = ns0;
+    s1 = ns1;
+    s_cw.w |= tl_cw;
+    blk v_buf = GR::into(ga, v_cw);
+    v_buf.w = (v_buf.w & ~1u) | tr_cw;                          // :187-189
+    st_blk(cws + 32 * i, s_cw);
+    st_blk(cws + 32 * i + 16, v_buf);
+  }
+  V vn = GR::add(ga, GR::add(ga, GR::from(ga, s1), GR::neg(ga, GR::from(ga, s0))), GR::neg(ga, v));
+  vn = GR::cneg(ga, vn, t1);                                    // :191-193
+  st_blk(cws + 32 * n, zero_blk());
+  st_blk(cws + 32 * n + 16, GR::into(ga, vn));
+}
+
+// ---- Half-Tree DPF ---------------------------------------------------------------------------------------
+FSS_HD blk hash_key_blk(const PrgKeys &K) {
+  return make_blk(K.hash_key[0], K.hash_key[1], K.hash_key[2], K.hash_key[3]);
+}
+// H(node) = prg.Gen(hash_key ^ node)[0]   (half_tree_dpf.cuh:195)
+template <int PRG>
+FSS_HD blk ht_hash(const PrgKeys &K, const typename Prg<PRG>::ctx_t &pc, blk node) {
+  return Prg<PRG>::gen1(K, pc, hash_key_blk(K) ^ node);
+}
+// Last level + Convert, half_tree_dpf.cuh:208-230 / :325-354.  lcw = LCW_sigma.
+template <int G, int PRG>
+FSS_HD blk ht_last(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, uint32_t party,
+    blk node, uint32_t sigma, blk cw_last, uint32_t lcw, blk ocw) {
+  typedef Grp<G> GR;
+  const uint32_t tm = 0u - lsb(node);
+  blk in = node;
+  in.w = (node.w & ~1u) | sigma;
+  blk h = ht_hash<PRG>(K, pc, in);
+  blk corr = cw_last;                                           // SetLsb(HCW, LCW_sigma)
+  corr.w = (cw_last.w & ~1u) | lcw;
+  h = xor_masked(h, tm, corr);                                  // high ^= hcw, low ^= lcw
+  typename GR::V y = GR::from(ga, clamp(h));
+  y = GR::add_masked(ga, y, 0u - lsb(h), GR::from(ga, ocw));
+  return GR::into(ga, GR::cneg(ga, y, party));
+}
+// HalfTreeDpf::Eval, half_tree_dpf.cuh:187-231.  n hashes per evaluation.
+template <int G, int PRG, class Cw>
+FSS_HD blk ht_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
+    uint32_t party, blk s0, const InVal &x, const Cw &cw, blk ocw) {
+  blk node = clamp(s0);
+  node.w |= party;
+  blk cs = cw.s(0);
+#pragma unroll 1
+  for (int i = 0; i < n - 1; ++i) {
+    const blk cs_next = cw.s(i + 1);
+    const uint32_t xm = 0u - in_bit(x, n - 1 - i);
+    const uint32_t tm = 0u - lsb(node);
+    const blk h = ht_hash<PRG>(K, pc, node);
+    node = xor_masked(xor_masked(h, xm, node), tm, cs);          // :202-204 (cw lsb included)
+    cs = cs_next;
+  }
+  const uint32_t xn = in_bit(x, 0);
+  const uint32_t lcw = xn ? cw.flag(n - 1) : (cs.w & 1u);        // :213-216
+  return ht_last<G, PRG>(K, ga, pc, party, node, xn, cs, lcw, ocw);
+}
+// HalfTreeDpf::Gen, half_tree_dpf.cuh:68-175.
+template <int G, int PRG>
+FSS_HD void ht_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n, blk s0,
+    blk s1, const InVal &a, blk beta, uint8_t *cws, blk *ocw) {
+  typedef Grp<G> GR;
+  beta = clamp(beta);
+  blk node0 = clamp(s0), node1 = clamp(s1);
+  node1.w |= 1u;
+  blk delta = node0 ^ node1;
+#pragma unroll 1
+  for (int i = 0; i < n - 1; ++i) {
+    const blk h0 = ht_hash<PRG>(K, pc, node0), h1 = ht_hash<PRG>(K, pc, node1);
+    const uint32_t am = 0u - in_bit(a, n - 1 - i);
+    const blk cw = xor_masked(h0 ^ h1, ~am, delta);              // :83-84
+    st_blk(cws + 32 * i, cw);
+    st_blk(cws + 32 * i + 16, zero_blk());
+    const uint32_t t0m = 0u - lsb(node0), t1m = 0u - lsb(node1);
+    node0 = xor_masked(xor_masked(h0, am, node0), t0m, cw);
+    node1 = xor_masked(xor_masked(h1, am, node1), t1m, cw);
+    delta = node0 ^ node1;
+  }
+  const uint32_t an = in_bit(a, 0);
+  const uint32_t t0 = lsb(node0), t1 = lsb(node1);
+  blk in;
+  in = clamp(node0); const blk h0_0 = ht_hash<PRG>(K, pc, in);
+  in.w |= 1u;        const blk h0_1 = ht_hash<PRG>(K, pc, in);
+  in = clamp(node1); const blk h1_0 = ht_hash<PRG>(K, pc, in);
+  in.w |= 1u;        const blk h1_1 = ht_hash<PRG>(K, pc, in);
+  const blk hcw = an ? clamp(h0_0 ^ h1_0) : clamp(h0_1 ^ h1_1);   // :123-125
+  const uint32_t lcw0 = (lsb(h0_0) ^ lsb(h1_0) ^ an ^ 1u) & 1u;   // :132
+  const uint32_t lcw1 = (lsb(h0_1) ^ lsb(h1_1) ^ an) & 1u;        // :133
+  blk cwn = hcw;
+  cwn.w |= lcw0;
+  st_blk(cws + 32 * (n - 1), cwn);
+  st_blk(cws + 32 * (n - 1) + 16, make_blk(lcw1, 0, 0, 0));       // :139-141
+  blk leaf0 = an ? h0_1 : h0_0, leaf1 = an ? h1_1 : h1_0;          // packed high||low
+  blk leaf_cw = hcw;
+  leaf_cw.w |= an ? lcw1 : lcw0;
+  leaf0 = xor_masked(leaf0, 0u - t0, leaf_cw);
+  leaf1 = xor_masked(leaf1, 0u - t1, leaf_cw);
+  typename GR::V v = GR::add(ga, GR::add(ga, GR::from(ga, beta), GR::neg(ga, GR::from(ga, clamp(leaf0)))),
+      GR::from(ga, clamp(leaf1)));
+  v = GR::cneg(ga, v, lsb(leaf1));                                 // :171-173
+  *ocw = GR::into(ga, v);
+}
+
+// ---- full-domain node expansion (dpf.cuh:265-288, eval_all_gpu.cuh:154-178) ------------------------------
+// cwl / cwr: the level's s_cw with tl_cw resp. tr_cw in the clamp bit.
+template <int PRG>
+FSS_HD void dpf_expand(const PrgKeys &K, const typename Prg<PRG>::ctx_t &pc, blk st, blk cwl, blk cwr, blk &left,
+    blk &right) {
+  const uint32_t tm = 0u - lsb(st);
+  blk g[2];
+  Prg<PRG>::template gen<2>(K, pc, clamp(st), g);
+  left = xor_masked(g[0], tm, cwl);
+  right = xor_masked(g[1], tm, cwr);
+}
+// half_tree_dpf.cuh:292-302, eval_all_gpu.cuh:46-52
+template <int PRG>
+FSS_HD void ht_expand(const PrgKeys &K, const typename Prg<PRG>::ctx_t &pc, blk node, blk cw, blk &left,
+    blk &right) {
+  const uint32_t tm = 0u - lsb(node);
+  const blk h = ht_hash<PRG>(K, pc, node);
+  left = xor_masked(h, tm, cw);
+  right = left ^ node;
+}
+
+}  // namespace fssb200

@@ -217,7 +217,8 @@ int fssb200_grotto_eval(const fssb200_ctx *ctx, const void *pt, const void *xs, 
  * ceil(n/32) words per key: extra[w*nkeys+k] bit j = level 32*w+j.
  *   cw_s  : int4[n][nkeys]          out
  *   cw_v  : int4[n][nkeys]          out (DCF only, else NULL)
- *   extra : uint32[ceil(n/32)][nkeys] out (DPF: tr bits; Half-Tree: bit 0 = extra)
+ *   extra : uint32[ceil(n/32)][nkeys] out (bit i = the bool at byte 16 of Cw[i]: DPF tr bits;
+ *                                     Half-Tree: only bit n-1, the last level's `extra`; DCF: NULL)
  *   out_cw: int4[nkeys]             out (DPF: cws[n].s, DCF: cws[n].v; Half-Tree: unused)
  */
 int fssb200_relayout(const fssb200_ctx *ctx, const void *cws, void *cw_s, void *cw_v, void *extra,

@@ -658,9 +658,7 @@ int orc_relayout(const fssb200_params *p, size_t nkeys, const void *cws, void *c
     for (int i = 0; i < n; ++i) {
       ((blk *)cw_s)[(size_t)i * nkeys + k] = kc[i].s;
       if (p->scheme == FSSB200_SCHEME_DCF) ((blk *)cw_v)[(size_t)i * nkeys + k] = kc[i].v;
-      else if (p->scheme == FSSB200_SCHEME_HALFTREE) {
-        if (i == n - 1 && cw_tr(&kc[i])) ((uint32_t *)extra)[k] |= 1u;
-      } else if (cw_tr(&kc[i])) ((uint32_t *)extra)[(size_t)(i / 32) * nkeys + k] |= 1u << (i % 32);
+      else if (cw_tr(&kc[i])) ((uint32_t *)extra)[(size_t)(i / 32) * nkeys + k] |= 1u << (i % 32);
     }
     if (p->scheme == FSSB200_SCHEME_DCF) ((blk *)out_cw)[k] = kc[n].v;
     else if (p->scheme != FSSB200_SCHEME_HALFTREE) ((blk *)out_cw)[k] = kc[n].s;
