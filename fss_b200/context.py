@@ -1,0 +1,294 @@
+"""Torch-facing wrapper of the C ABI (include/fssb200.h): one ``Context`` per parameter set.
+
+PyTorch is plumbing here (device memory, streams); every method below ends in a call into
+libfssb200.so -- there is no Python / CPU evaluation path.
+
+Tensor conventions (the reference binding's, fss_crypto/_csrc/dpf_binding_impl.cuh:44-46):
+  seeds  (N, 4) int32       s0s (N, 2, 4) int32       betas (N, 4) int32
+  cws    (N, ncw, 8) int32  row = 8 int32: words 0-3 ``s``; word 4 = ``tr`` (DPF) / words 4-7 ``v`` (DCF)
+  ys     (N, 4) int32       eval_all: (N, L, 4) int32, Grotto (N, L) uint8
+  xs / alphas: Python ints, or an int32 / int64 / uint8[N, in_bytes] tensor (little-endian ``In``)
+CUDA tensors run stream-ordered on torch's current stream; CPU tensors go through the
+``*_host`` entry points (chunked H2D / kernel / D2H pipeline inside the library).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import torch
+
+from . import _lib as L
+
+_SCHEMES = {"dpf": L.SCHEME_DPF, "dcf": L.SCHEME_DCF, "halftree": L.SCHEME_HALFTREE, "grotto": L.SCHEME_GROTTO}
+_GROUPS = {"bytes": L.GROUP_BYTES, "u8": L.GROUP_U8, "u16": L.GROUP_U16, "u32": L.GROUP_U32, "u64": L.GROUP_U64,
+           "u128": L.GROUP_U128}
+_PRGS = {"aes128_mmo": L.PRG_AES128_MMO, "chacha": L.PRG_CHACHA}
+_PREDS = {"lt": L.PRED_LT, "gt": L.PRED_GT}
+
+# fixtures of the reference's samples/tests (samples/dpf_dcf_cpu.cu:39-42,98-101; src/dpf_test.cu:35)
+DEFAULT_AES_KEYS = bytes(range(1, 17)) + bytes(range(16, 0, -1)) + bytes(
+    [1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8]) + bytes([8, 8, 7, 7, 6, 6, 5, 5, 4, 4, 3, 3, 2, 2, 1, 1])
+DEFAULT_CHACHA_NONCE = (0x12345678).to_bytes(4, "little") + (0x9ABCDEF0).to_bytes(4, "little")
+DEFAULT_HASH_KEY = b"".join(v.to_bytes(4, "little") for v in (0x12345678, 0x9ABCDEF0, 0x0FEDCBA9, 0x87654321))
+
+IntLike = Union[int, Sequence[int], torch.Tensor]
+
+
+def in_bytes_for(in_bits: int) -> int:
+    """``In`` by in_bits as the reference binding picks it (fss_crypto/_jit.py:57-62)."""
+    return 4 if in_bits <= 32 else (8 if in_bits <= 64 else 16)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Context:
+    def __init__(self, scheme: str, in_bits: int, group: str = "bytes", mod: int = 0, prg: str = "aes128_mmo",
+                 pred: str = "lt", prg_key: Optional[bytes] = None, hash_key: Optional[bytes] = None,
+                 in_bytes: Optional[int] = None):
+        self.scheme, self.in_bits, self.group, self.prg, self.pred = scheme, in_bits, group, prg, pred
+        if group == "u128" and mod == 0:
+            mod = 1 << 127
+        self.mod = mod
+        self.in_bytes = in_bytes or in_bytes_for(in_bits)
+        self.prg_key = prg_key if prg_key is not None else (
+            DEFAULT_AES_KEYS if prg == "aes128_mmo" else DEFAULT_CHACHA_NONCE)
+        self.hash_key = hash_key if hash_key is not None else DEFAULT_HASH_KEY
+        self.ncw = in_bits if scheme == "halftree" else in_bits + 1
+        self.mul = {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2}[scheme]
+        self._handles: dict[int, C.c_void_p] = {}
+        self._host_reserved: dict[int, int] = {}
+
+    # ---- context handles -------------------------------------------------------------------------
+    def _params(self, device: int) -> L.Params:
+        p = L.Params()
+        p.scheme, p.in_bits, p.in_bytes, p.group = _SCHEMES[self.scheme], self.in_bits, self.in_bytes, _GROUPS[
+            self.group]
+        p.mod_lo, p.mod_hi = self.mod & (2 ** 64 - 1), self.mod >> 64
+        p.prg, p.pred, p.device = _PRGS[self.prg], _PREDS[self.pred], device
+        key = bytes(self.prg_key).ljust(64, b"\0")
+        C.memmove(p.prg_key, key, 64)
+        C.memmove(p.hash_key, bytes(self.hash_key), 16)
+        return p
+
+    def handle(self, device: Optional[int] = None) -> C.c_void_p:
+        if device is None:
+            device = torch.cuda.current_device()
+        h = self._handles.get(device)
+        if h is None:
+            p = self._params(device)
+            h = C.c_void_p()
+            L.check(L.lib.fssb200_ctx_create(C.byref(p), C.byref(h)), "fssb200_ctx_create")
+            self._handles[device] = h
+        return h
+
+    def close(self) -> None:
+        for h in self._handles.values():
+            L.lib.fssb200_ctx_destroy(h)
+        self._handles.clear()
+        self._host_reserved.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self, device: Optional[int] = None) -> int:
+        return int(L.lib.fssb200_ctx_launch_count(self.handle(device)))
+
+    def granule(self, device: Optional[int] = None) -> int:
+        return int(L.lib.fssb200_eval_all_granule(self.handle(device)))
+
+    def reserve_host(self, max_keys_per_chunk: int = 0, device: Optional[int] = None) -> None:
+        if device is None:
+            device = torch.cuda.current_device()
+        L.check(L.lib.fssb200_ctx_reserve_host(self.handle(device), max_keys_per_chunk), "fssb200_ctx_reserve_host")
+        self._host_reserved[device] = max_keys_per_chunk or (1 << 18)
+
+    def _ensure_host(self, device: int) -> None:
+        if device not in self._host_reserved:
+            self.reserve_host(0, device)
+
+    # ---- helpers -----------------------------------------------------------------------------------------
+    def in_tensor(self, vals: IntLike, device: torch.device) -> torch.Tensor:
+        """Domain values -> contiguous little-endian ``In[N]`` tensor on ``device``."""
+        nb = self.in_bytes
+        if isinstance(vals, torch.Tensor):
+            t = vals
+            if t.dtype == torch.uint8 and t.dim() == 2 and t.shape[1] == nb:
+                return t.contiguous().to(device)
+            if t.dim() != 1 or t.dtype not in (torch.int32, torch.int64):
+                raise TypeError(f"domain values must be int32/int64 (N,) or uint8 (N, {nb}), got "
+                                f"shape {tuple(t.shape)} dtype {t.dtype}")
+            if nb == 4:
+                return t.to(torch.int32).contiguous().to(device)
+            if nb == 8:
+                return t.to(torch.int64).contiguous().to(device)
+            if nb == 16:
+                t64 = t.to(torch.int64)
+                return torch.stack([t64, torch.zeros_like(t64)], dim=1).contiguous().to(device)
+            return t.to(torch.int64).view(torch.uint8).reshape(-1, 8)[:, :nb].contiguous().to(device)
+        if isinstance(vals, int):
+            vals = [vals]
+        raw = b"".join(int(v).to_bytes(nb, "little") for v in vals)
+        return torch.frombuffer(bytearray(raw), dtype=torch.uint8).reshape(len(vals), nb).to(device)
+
+    @staticmethod
+    def _dev(t: torch.Tensor) -> tuple[bool, int]:
+        if t.device.type == "cuda":
+            return True, t.device.index if t.device.index is not None else torch.cuda.current_device()
+        return False, torch.cuda.current_device()
+
+    @staticmethod
+    def _stream(dev: int) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    # ---- Gen (dpf.cuh:93-159, dcf.cuh:108-194, half_tree_dpf.cuh:68-175, grotto_dcf.cuh:63-67) ---------------
+    def gen(self, s0s: torch.Tensor, alphas: IntLike, betas: Optional[torch.Tensor] = None):
+        s0s = s0s.contiguous()
+        n = s0s.shape[0]
+        on_gpu, dev = self._dev(s0s)
+        al = self.in_tensor(alphas, s0s.device)
+        if self.scheme != "grotto":
+            betas = betas.contiguous()
+        cws = torch.empty((n, self.ncw, 8), dtype=torch.int32, device=s0s.device)
+        ocws = torch.empty((n, 4), dtype=torch.int32, device=s0s.device) if self.scheme == "halftree" else None
+        h = self.handle(dev)
+        if on_gpu:
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_gen(h, _ptr(s0s), _ptr(al), _ptr(betas), _ptr(cws), _ptr(ocws), n,
+                                          self._stream(dev)), "fssb200_gen")
+        else:
+            self._ensure_host(dev)
+            L.check(L.lib.fssb200_gen_host(h, _ptr(s0s), _ptr(al), _ptr(betas), _ptr(cws), _ptr(ocws), n),
+                    "fssb200_gen_host")
+        return (cws, ocws) if self.scheme == "halftree" else cws
+
+    # ---- Eval (dpf.cuh:170-214, dcf.cuh:205-276, half_tree_dpf.cuh:187-231) ----------------------------------
+    def eval(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, xs: IntLike,
+             ocws: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        seeds, cws = seeds.contiguous(), cws.contiguous()
+        n = seeds.shape[0]
+        on_gpu, dev = self._dev(seeds)
+        x = self.in_tensor(xs, seeds.device)
+        ocws = None if ocws is None else ocws.contiguous()
+        ys = out if out is not None else torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
+        h = self.handle(dev)
+        if on_gpu:
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_eval(h, party, _ptr(seeds), _ptr(cws), _ptr(ocws), _ptr(x), _ptr(ys), n,
+                                           self._stream(dev)), "fssb200_eval")
+        else:
+            self._ensure_host(dev)
+            L.check(L.lib.fssb200_eval_host(h, party, _ptr(seeds), _ptr(cws), _ptr(ocws), _ptr(x), _ptr(ys), n),
+                    "fssb200_eval_host")
+        return ys
+
+    # ---- EvalAll (dpf.cuh:232-303, half_tree_dpf.cuh:246-354, grotto_dcf.cuh:151-163) --------------------------
+    def eval_all(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, ocws: Optional[torch.Tensor] = None,
+                 leaf_begin: int = 0, leaf_count: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        seeds, cws = seeds.contiguous(), cws.contiguous()
+        n = seeds.shape[0]
+        on_gpu, dev = self._dev(seeds)
+        cnt = leaf_count or ((1 << self.in_bits) - leaf_begin)
+        ocws = None if ocws is None else ocws.contiguous()
+        if out is not None:
+            ys = out
+        elif self.scheme == "grotto":
+            ys = torch.empty((n, cnt), dtype=torch.uint8, device=seeds.device)
+        else:
+            ys = torch.empty((n, cnt, 4), dtype=torch.int32, device=seeds.device)
+        h = self.handle(dev)
+        if on_gpu:
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_eval_all(h, party, _ptr(seeds), _ptr(cws), _ptr(ocws), _ptr(ys), n, leaf_begin,
+                                               leaf_count, self._stream(dev)), "fssb200_eval_all")
+        else:
+            self._ensure_host(dev)
+            L.check(L.lib.fssb200_eval_all_host(h, party, _ptr(seeds), _ptr(cws), _ptr(ocws), _ptr(ys), n,
+                                                leaf_begin, leaf_count), "fssb200_eval_all_host")
+        return ys
+
+    # ---- level-major layout (point_eval_gpu.cuh:324-492) ----------------------------------------------------------
+    def relayout(self, cws: torch.Tensor):
+        cws = cws.contiguous()
+        n, nb = cws.shape[0], self.in_bits
+        _, dev = self._dev(cws)
+        d = cws.device
+        cw_s = torch.empty((nb, n, 4), dtype=torch.int32, device=d)
+        cw_v = torch.empty((nb, n, 4), dtype=torch.int32, device=d) if self.scheme == "dcf" else None
+        extra = torch.zeros(((nb + 31) // 32, n), dtype=torch.int32, device=d) if self.scheme != "dcf" else None
+        out_cw = torch.empty((n, 4), dtype=torch.int32, device=d) if self.scheme != "halftree" else None
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_relayout(self.handle(dev), _ptr(cws), _ptr(cw_s), _ptr(cw_v), _ptr(extra),
+                                           _ptr(out_cw), n, self._stream(dev)), "fssb200_relayout")
+        return cw_s, cw_v, extra, out_cw
+
+    def eval_levelmajor(self, party: int, seeds: torch.Tensor, layout, xs: IntLike,
+                        ocws: Optional[torch.Tensor] = None) -> torch.Tensor:
+        cw_s, cw_v, extra, out_cw = layout
+        seeds = seeds.contiguous()
+        n = seeds.shape[0]
+        _, dev = self._dev(seeds)
+        x = self.in_tensor(xs, seeds.device)
+        ys = torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_eval_levelmajor(self.handle(dev), party, _ptr(seeds), _ptr(cw_s), _ptr(cw_v),
+                                                  _ptr(extra), _ptr(out_cw), _ptr(ocws), _ptr(x), _ptr(ys), n,
+                                                  self._stream(dev)), "fssb200_eval_levelmajor")
+        return ys
+
+    # ---- Grotto (grotto_dcf.cuh:94-135,174-238) ---------------------------------------------------------------------
+    def grotto_expand(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, leaf_begin: int = 0,
+                      leaf_count: int = 0) -> torch.Tensor:
+        seeds, cws = seeds.contiguous(), cws.contiguous()
+        n = seeds.shape[0]
+        _, dev = self._dev(seeds)
+        cnt = leaf_count or ((1 << self.in_bits) - leaf_begin)
+        t = torch.empty((n, cnt), dtype=torch.uint8, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_grotto_expand(self.handle(dev), party, _ptr(seeds), _ptr(cws), _ptr(t), n,
+                                                leaf_begin, leaf_count, self._stream(dev)), "fssb200_grotto_expand")
+        return t
+
+    def grotto_preprocess(self, party: int, seeds: torch.Tensor, cws: torch.Tensor) -> torch.Tensor:
+        seeds, cws = seeds.contiguous(), cws.contiguous()
+        n = seeds.shape[0]
+        _, dev = self._dev(seeds)
+        pt = torch.empty((n, (2 << self.in_bits) - 1), dtype=torch.uint8, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_grotto_preprocess(self.handle(dev), party, _ptr(seeds), _ptr(cws), _ptr(pt), n,
+                                                    self._stream(dev)), "fssb200_grotto_preprocess")
+        return pt
+
+    def grotto_lookup(self, pt: torch.Tensor, xs: IntLike) -> torch.Tensor:
+        pt = pt.contiguous()
+        n = pt.shape[0]
+        _, dev = self._dev(pt)
+        x = self.in_tensor(xs, pt.device)
+        ys = torch.empty((n,), dtype=torch.uint8, device=pt.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_grotto_eval(self.handle(dev), _ptr(pt), _ptr(x), _ptr(ys), n, self._stream(dev)),
+                    "fssb200_grotto_eval")
+        return ys
+
+    # ---- PRG known-answer hook -----------------------------------------------------------------------------------------
+    def prg_gen(self, seeds: torch.Tensor, mul: int) -> torch.Tensor:
+        seeds = seeds.contiguous()
+        n = seeds.shape[0]
+        _, dev = self._dev(seeds)
+        out = torch.empty((n, mul, 4), dtype=torch.int32, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_prg_gen(self.handle(dev), _ptr(seeds), _ptr(out), mul, n, self._stream(dev)),
+                    "fssb200_prg_gen")
+        return out
+
+
+def microbench(kind: int, device: int = 0) -> float:
+    """Issue-rate microbenchmark (ops/s): 0 LOP3, 1 IMAD, 2 LOP3+IMAD, 3 conflict-free LDS.32, 4 PRMT."""
+    v = C.c_double(0.0)
+    L.check(L.lib.fssb200_microbench(device, kind, C.byref(v)), "fssb200_microbench")
+    return float(v.value)

@@ -1,0 +1,127 @@
+"""CPU check of the CUDA kernels' per-thread bodies.
+
+tests/host_emul/host_emul.cpp compiles the `__host__ __device__` code of fss_b200/csrc/{aes,prg,group,
+schemes}.cuh for the host (same T-table image, PRMT address formation, lane replication, packed-node
+correction, group arithmetic) and this test compares it bit for bit with the oracle.  It is how the
+kernel logic is validated in the GPU-less build container; the `-m gpu` tests then cover the real
+kernels through the C ABI.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import HASH_KEY_BENCH, Params, _vp, pack_ints, synth_inputs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "host_emul.cpp")
+LIB = os.path.join(HERE, "host_emul", "_host_emul.so")
+CSRC = os.path.join(os.path.dirname(HERE), "fss_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("common.cuh", "aes.cuh", "prg.cuh", "group.cuh", "schemes.cuh")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", "-w", "-I/usr/local/cuda/include",
+                        SRC, "-o", LIB], check=True)
+    return C.CDLL(LIB)
+
+
+def emul_gen(emu, p, s0s, alphas, betas):
+    k = len(s0s)
+    cws, ocws = np.zeros((k, p.ncw, 8), np.uint32), np.zeros((k, 4), np.uint32)
+    cp, al = p.c(), pack_ints(alphas, p.in_bytes)
+    emu.emul_gen(C.byref(cp), C.c_size_t(k), _vp(np.ascontiguousarray(s0s)), _vp(al), _vp(betas), _vp(cws), _vp(ocws))
+    return cws, ocws
+
+
+def emul_eval(emu, p, party, seeds, cws, xs, ocws=None, lm=None):
+    k = len(seeds)
+    ys, cp, xb = np.zeros((k, 4), np.uint32), p.c(), pack_ints(xs, p.in_bytes)
+    seeds = np.ascontiguousarray(seeds)
+    if lm is None:
+        emu.emul_eval(C.byref(cp), party, C.c_size_t(k), _vp(seeds), _vp(cws), _vp(ocws), _vp(xb), _vp(ys), 0, None,
+                      None, None, None)
+    else:
+        emu.emul_eval(C.byref(cp), party, C.c_size_t(k), _vp(seeds), None, _vp(ocws), _vp(xb), _vp(ys), 1,
+                      _vp(lm[0]), _vp(lm[1]), _vp(lm[2]), _vp(lm[3]))
+    return ys
+
+
+def emul_all(emu, p, party, seeds, cws, ocws=None, lb=0, cnt=0):
+    k, n = len(seeds), cnt or ((1 << p.in_bits) - lb)
+    ys = np.zeros((k, n), np.uint8) if p.scheme == "grotto" else np.zeros((k, n, 4), np.uint32)
+    cp = p.c()
+    rc = emu.emul_evalall(C.byref(cp), party, C.c_size_t(k), _vp(np.ascontiguousarray(seeds)), _vp(cws), _vp(ocws),
+                          _vp(ys), C.c_uint64(lb), C.c_uint64(cnt))
+    assert rc == 0
+    return ys
+
+
+@pytest.mark.parametrize("prg", ["aes128_mmo", "chacha"])
+def test_prg_blocks(emu, orc, golden, prg):
+    seeds = golden.arrays["prg/seeds"]
+    for mul in (1, 2, 4):
+        p = Params(prg=prg)
+        out = np.zeros((len(seeds), mul, 4), np.uint32)
+        cp = p.c()
+        emu.emul_prg_gen(C.byref(cp), mul, C.c_size_t(len(seeds)), _vp(seeds), _vp(out))
+        assert np.array_equal(out, golden.arrays[f"prg/{prg}_{mul}"])   # reference-generated
+        assert np.array_equal(out, orc.prg_gen(p, mul, seeds))
+
+
+MODS = {"bytes": [0], "u8": [0, 251], "u16": [65521], "u32": [0, 4294967291, 7], "u64": [0, 18446744073709551557],
+        "u128": [1 << 127, (1 << 127) - 1, 5, (1 << 64) + 13]}
+
+
+@pytest.mark.parametrize("prg", ["aes128_mmo", "chacha"])
+@pytest.mark.parametrize("scheme", ["dpf", "dcf", "halftree", "grotto"])
+def test_kernel_bodies_match_oracle(emu, orc, prg, scheme):
+    for n in (1, 2, 5, 8, 12, 32, 33, 64, 65, 128):
+        for group, mods in MODS.items():
+            if scheme == "grotto" and group != "bytes":
+                continue
+            if n not in (8, 32, 64) and group not in ("bytes", "u64", "u128"):
+                continue
+            for mod in mods:
+                for pred in (("lt", "gt") if scheme == "dcf" and n in (8, 64) else ("lt",)):
+                    p = Params(scheme=scheme, in_bits=n, group=group, mod=mod, prg=prg, pred=pred,
+                               hash_key=HASH_KEY_BENCH)
+                    k = 40  # > 32 so that every table replica (lane) is exercised
+                    s0s, alphas, betas, xs = synth_inputs(p, k, seed=n + len(group))
+                    xs[1], xs[2], alphas[3], xs[3], alphas[4], xs[4] = 0, (1 << n) - 1, 0, 0, (1 << n) - 1, (1 << n) - 1
+                    o = orc.gen(p, s0s, alphas, betas)
+                    oc, ooc = o if scheme == "halftree" else (o, None)
+                    ec, eoc = emul_gen(emu, p, s0s, alphas, None if scheme == "grotto" else betas)
+                    tag = (scheme, n, group, hex(mod), prg, pred)
+                    assert np.array_equal(oc, ec), ("gen",) + tag
+                    assert ooc is None or np.array_equal(ooc, eoc), ("gen ocw",) + tag
+                    if scheme != "grotto":
+                        lm = orc.relayout(p, oc)
+                        for party in (0, 1):
+                            want = orc.eval(p, party, s0s[:, party], oc, xs, ooc)
+                            assert np.array_equal(want, emul_eval(emu, p, party, s0s[:, party], oc, xs, ooc)), tag
+                            assert np.array_equal(want, emul_eval(emu, p, party, s0s[:, party], oc, xs, ooc, lm)), tag
+                    if n <= 12 and scheme != "dcf":
+                        for party in (0, 1):
+                            so = None if ooc is None else ooc[:3]
+                            want = (orc.grotto_expand(p, party, s0s[:3, party], oc[:3]) if scheme == "grotto" else
+                                    orc.evalall(p, party, s0s[:3, party], oc[:3], so))
+                            assert np.array_equal(want, emul_all(emu, p, party, s0s[:3, party], oc[:3], so)), tag
+
+
+def test_golden_through_kernel_bodies(emu, golden):
+    """Reference-generated fixtures replayed through the kernel bodies (no oracle in the loop)."""
+    for c in golden.cases:
+        p = c.p
+        if p.scheme == "grotto":
+            continue
+        ocws = c["ocws"] if p.scheme == "halftree" else None
+        for party in (0, 1):
+            got = emul_eval(emu, p, party, c["s0s"][:, party], c["cws"], c.xs, ocws)
+            assert np.array_equal(got, c[f"ys{party}"]), (c.name, party)
+        ec, eoc = emul_gen(emu, p, c["s0s"], c.alphas, c.betas)
+        assert np.array_equal(c.masked_cws(ec), c.masked_cws(c["cws"])), c.name
