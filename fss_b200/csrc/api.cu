@@ -4,6 +4,7 @@
 // geometry, host-buffer staging.  There is no CPU evaluation path in this library: every entry
 // point either launches sm_100a kernels or returns an error code.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -28,6 +29,7 @@ struct fssb200_ctx {
   int sm_count;
   int max_smem_optin;
   uint32_t vmask;
+  int point_mode;   // PointMode of the key-major point kernels (kernels.cuh); FSSB200_POINT_MODE overrides
   std::atomic<uint64_t> launches{0};
   HostArena arena;
 };
@@ -83,20 +85,23 @@ int group_kind(const fssb200_params &p, uint32_t *vmask) {
 
 // Launch geometry of the point / gen / prg kernels: AES = one persistent 512-thread CTA per SM with
 // the full dynamic shared memory (tables); ChaCha = plain 256-thread CTAs.
-LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s) {
+// `mode` < 0: gen / prg kernels (no correction-word staging).
+LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode = -1) {
   LaunchCfg cfg;
   cfg.stream = s;
   if (c->p.prg == FSSB200_PRG_AES128_MMO) {
-    const uint64_t want = (n + kPointThreads - 1) / kPointThreads;
+    const unsigned threads = mode == 1 ? 1024u : unsigned(kPointThreads);
+    const uint64_t want = (n + threads - 1) / threads;
     cfg.grid = dim3(unsigned(want < uint64_t(c->sm_count) ? (want ? want : 1) : c->sm_count));
-    cfg.block = dim3(kPointThreads);
+    cfg.block = dim3(threads);
     cfg.smem = kMaxDynSmem;
   } else {
     const uint64_t want = (n + 255) / 256;
-    const uint64_t cap = uint64_t(c->sm_count) * 16;
+    const uint64_t cap = uint64_t(c->sm_count) * 6;
     cfg.grid = dim3(unsigned(want < cap ? (want ? want : 1) : cap));
     cfg.block = dim3(256);
-    cfg.smem = 0;
+    // staged correction words: one slab per warp (L = 4, or L = 2 in mode 1)
+    cfg.smem = (mode == 0 || mode == 1) ? 8 * (mode == 1 ? CwStagedWarp<2>::kWarpBytes : CwStagedWarp<4>::kWarpBytes) + 32 : 0;
   }
   return cfg;
 }
@@ -176,6 +181,13 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   c->ncw = q.scheme == FSSB200_SCHEME_HALFTREE ? q.in_bits : q.in_bits + 1;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = int(prop.sharedMemPerBlockOptin);
+  // measured on B200 (profiles/r01_point_modes.md): DPF (one AES per level, 64 registers) gains 3 % from
+  // 32 warps per SM; DCF / Half-Tree are faster with 16 warps and no register cap
+  c->point_mode = (q.scheme == FSSB200_SCHEME_DPF && q.prg == FSSB200_PRG_AES128_MMO) ? 1 : 0;
+  if (const char *e = std::getenv("FSSB200_POINT_MODE")) {  // A/B measurement knob
+    const int m = std::atoi(e);
+    if (m == 0 || m == 1 || m == 3) c->point_mode = m;
+  }
   std::memset(&c->kp, 0, sizeof(c->kp));
   if (q.prg == FSSB200_PRG_AES128_MMO) {
     for (int i = 0; i < 4; ++i) aes128_expand_le(q.prg_key + 16 * i, c->kp.keys.rk[i]);
@@ -277,7 +289,8 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   if (!aligned16(seeds) || !aligned16(ys) || !aligned16(ocws)) return FSSB200_EALIGN;
   if (reinterpret_cast<uintptr_t>(xs) % c->p.in_bytes) return FSSB200_EALIGN;
   if (nkeys == 0) return 0;
-  point_launch_fn fn = get_point_launcher(scheme, c->gk, c->p.prg, level_major);
+  const int mode = level_major ? 2 : c->point_mode;
+  point_launch_fn fn = get_point_launcher(scheme, c->gk, c->p.prg, mode);
   if (!fn) return FSSB200_EGROUP;
   DeviceGuard g(c->p.device);
   if (g.err != cudaSuccess) return int(g.err);
@@ -297,7 +310,7 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   a.in_bytes = c->p.in_bytes;
   a.party = party;
   a.vmask = c->vmask;
-  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream));
+  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream), mode);
   c->launches++;
   return int(fn(c->kp, a, cfg));
 }
@@ -658,15 +671,15 @@ int fssb200_microbench(int device, int kind, double *ops_per_s) {
 
 namespace fssb200 {
 
-point_launch_fn get_point_launcher(int scheme, int gk, int prg, bool lm) {
+point_launch_fn get_point_launcher(int scheme, int gk, int prg, int mode) {
   if (prg == kPrgAes) {
-    if (scheme == FSSB200_SCHEME_DPF) return point_launcher_aes_dpf(gk, lm);
-    if (scheme == FSSB200_SCHEME_DCF) return point_launcher_aes_dcf(gk, lm);
-    if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_aes_ht(gk, lm);
+    if (scheme == FSSB200_SCHEME_DPF) return point_launcher_aes_dpf(gk, mode);
+    if (scheme == FSSB200_SCHEME_DCF) return point_launcher_aes_dcf(gk, mode);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_aes_ht(gk, mode);
   } else {
-    if (scheme == FSSB200_SCHEME_DPF) return point_launcher_chacha_dpf(gk, lm);
-    if (scheme == FSSB200_SCHEME_DCF) return point_launcher_chacha_dcf(gk, lm);
-    if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_chacha_ht(gk, lm);
+    if (scheme == FSSB200_SCHEME_DPF) return point_launcher_chacha_dpf(gk, mode);
+    if (scheme == FSSB200_SCHEME_DCF) return point_launcher_chacha_dcf(gk, mode);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_chacha_ht(gk, mode);
   }
   return nullptr;
 }

@@ -26,14 +26,15 @@ inline bool grp_kind_instantiated(int gk) {
 }
 
 // scheme in {DPF, DCF, HALFTREE}; returns nullptr when not instantiated.
-point_launch_fn get_point_launcher(int scheme, int gk, int prg, bool level_major);
+// mode: see PointMode in kernels.cuh (0/1 staged key-major, 2 level-major, 3 direct key-major)
+point_launch_fn get_point_launcher(int scheme, int gk, int prg, int mode);
 gen_launch_fn get_gen_launcher(int scheme, int gk, int prg);
 // mode 0 = DPF leaves, 1 = Half-Tree leaves, 2 = Grotto leaf bits (gk ignored)
 evalall_launch_fn get_evalall_launcher(int mode, int gk, int prg);
 prg_launch_fn get_prg_launcher(int prg, int mul);
 
 #define FSS_DECL_POINT(PRGNAME, SCHNAME) \
-  point_launch_fn point_launcher_##PRGNAME##_##SCHNAME(int gk, bool level_major);
+  point_launch_fn point_launcher_##PRGNAME##_##SCHNAME(int gk, int mode);
 #define FSS_DECL_GEN(PRGNAME, SCHNAME) gen_launch_fn gen_launcher_##PRGNAME##_##SCHNAME(int gk);
 #define FSS_DECL_EVALALL(PRGNAME, MODENAME) evalall_launch_fn evalall_launcher_##PRGNAME##_##MODENAME(int gk);
 FSS_DECL_POINT(aes, dpf) FSS_DECL_POINT(aes, dcf) FSS_DECL_POINT(aes, ht)

@@ -105,32 +105,127 @@ FSS_D NoCtx prg_ctx_init<kPrgChaCha>(const SmemPlan &) {
   return NoCtx{};
 }
 
+// ---- correction words staged through shared memory -------------------------------------------------------------
+// The reference layout is key-major (stride (n+1)*32 B per key), so a lane-per-key walk touches 32 different
+// lines per level, and -- worse -- a per-level global load issued next to the AES code shares a hardware
+// scoreboard slot with the table lookups: ncu showed 35 % of all stall samples on one LOP3 waiting for
+// the *prefetch* (profiles/r01_dpf_point_v1.md).  Here each warp copies the next L levels of its 32 keys
+// into its own shared-memory slab with cp.async (LDGSTS, no registers, no scoreboard): 2L consecutive
+// 16-byte pieces per key are read by 2L adjacent lanes (full 32*L-byte segments), the slab slot stride of
+// 32L+16 bytes makes the later lane-per-key 128-bit reads conflict-free, and the chunk after the next is
+// prefetched into L2 while this one is consumed.
+template <int L>
+struct CwStagedWarp {
+  static constexpr uint32_t kSlot = 32u * L + 16u;
+  static constexpr uint32_t kWarpBytes = 32u * kSlot;
+  uint32_t buf;          // shared-window address of this warp's slab
+  const uint8_t *gsrc;   // first key of the warp's tile: Cw[.][ncw]
+  uint32_t key_bytes;    // ncw * 32
+  int ncw;
+  int nvalid;            // keys of the tile that exist (1..32)
+  uint32_t lane;
+
+  FSS_D void load(int i0) const {
+    __syncwarp();  // every lane has taken what it needs from the previous chunk
+#pragma unroll
+    for (int j = 0; j < 2 * L; ++j) {
+      const uint32_t pidx = uint32_t(j) * 32u + lane;
+      const uint32_t key = pidx / (2u * L), piece = pidx % (2u * L);
+      const bool ok = int(key) < nvalid && i0 + int(piece >> 1) < ncw;
+      const uint8_t *src = gsrc + (ok ? uint64_t(key) * key_bytes + uint64_t(i0) * 32u + piece * 16u : 0u);
+      const uint32_t dst = buf + key * kSlot + piece * 16u;
+      const uint32_t nbytes = ok ? 16u : 0u;  // 0: zero-fill, nothing is read
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+      if (ok && i0 + int(piece >> 1) + L < ncw)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 32u * L));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  FSS_D void begin_level(int i) const {
+    if ((i & (L - 1)) == 0 && i < ncw) load(i);
+  }
+  FSS_D uint32_t at(int i) const { return buf + lane * kSlot + uint32_t(i & (L - 1)) * 32u; }
+  FSS_D blk s(int i) const { return lds_blk(at(i)); }
+  FSS_D blk v(int i) const { return lds_blk(at(i) + 16u); }
+  FSS_D uint32_t flag(int i) const {  // the C++ bool at byte 16 of Dpf::Cw / HalfTreeDpf::Cw
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(at(i) + 16u) : "memory");
+    return (w & 0xffu) != 0;
+  }
+  FSS_D blk out_s(int n) const { return s(n); }
+  FSS_D blk out_v(int n) const { return v(n); }
+};
+
 // ---- batched point evaluation --------------------------------------------------------------------------------
-// One key per thread, grid-stride.  SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE}.
-template <int SCHEME, int G, int PRG, bool LEVEL_MAJOR>
-__global__ void __launch_bounds__(kPointThreads, 1)
+// One key per thread; warps own tiles of 32 consecutive keys (grid-stride over tiles).
+// SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE}.
+// MODE: 0 = key-major, staged, <= 512 threads, L = 4      (default)
+//       1 = key-major, staged, 1024 threads (<= 64 regs), L = 2
+//       2 = level-major arrays (fssb200_eval_levelmajor), direct coalesced loads
+//       3 = key-major, direct per-thread global loads (the round-1 first version; kept for A/B runs)
+constexpr int kPointModes = 4;
+template <int MODE>
+struct PointMode {
+  static constexpr int kMaxThreads = MODE == 1 ? 1024 : 512;
+  static constexpr int kL = MODE == 1 ? 2 : 4;
+  static constexpr bool kStaged = MODE <= 1;
+};
+
+template <int SCHEME, int G, int PRG, class Cw>
+FSS_D blk point_eval_one(const KParams &P, const typename Prg<PRG>::ctx_t &pc, const PointArgs &A, blk s0,
+    const InVal &x, const Cw &cw, uint64_t k) {
+  const int n = A.in_bits;
+  if (SCHEME == FSSB200_SCHEME_DPF) return dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
+  if (SCHEME == FSSB200_SCHEME_DCF) return dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
+  return ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
+}
+
+template <int SCHEME, int G, int PRG, int MODE>
+__global__ void __launch_bounds__(PointMode<MODE>::kMaxThreads, 1)
 point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArgs A) {
+  typedef PointMode<MODE> PM;
   SmemPlan sp = smem_plan<PRG>();
   const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
   const int n = A.in_bits;
   const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE) ? n : n + 1;
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < A.nkeys; k += stride) {
-    const blk s0 = ld_blk(A.seeds + k);
-    const InVal x = load_in(A.xs + k * uint64_t(A.in_bytes), A.in_bytes);
-    blk y;
-    if (LEVEL_MAJOR) {
-      const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, k};
-      if (SCHEME == FSSB200_SCHEME_DPF) y = dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
-      else if (SCHEME == FSSB200_SCHEME_DCF) y = dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
-      else y = ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
-    } else {
-      const CwKeyMajor cw{A.cws + k * uint64_t(ncw) * 32u};
-      if (SCHEME == FSSB200_SCHEME_DPF) y = dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
-      else if (SCHEME == FSSB200_SCHEME_DCF) y = dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
-      else y = ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint32_t slab = 0;
+  if (PM::kStaged) {
+    for (uint32_t w = 0; w < nwarps; ++w) {  // same allocation sequence in every thread
+      const uint32_t a = sp.alloc(CwStagedWarp<PM::kL>::kWarpBytes, false);
+      if (w == wid) slab = a;
     }
-    st_blk(A.ys + k, y);
+  }
+  const uint64_t ntiles = (A.nkeys + 31) >> 5;
+  const uint64_t tile_stride = uint64_t(gridDim.x) * nwarps;
+  for (uint64_t tile = uint64_t(blockIdx.x) * nwarps + wid; tile < ntiles; tile += tile_stride) {
+    const uint64_t k = tile * 32 + lane;
+    const bool valid = k < A.nkeys;
+    const uint64_t kk = valid ? k : A.nkeys - 1;  // idle lanes of a ragged tile shadow the last key
+    const blk s0 = ld_blk(A.seeds + kk);
+    const InVal x = load_in(A.xs + kk * uint64_t(A.in_bytes), A.in_bytes);
+    blk y;
+    if (PM::kStaged) {
+      CwStagedWarp<PM::kL> cw;
+      cw.buf = slab;
+      cw.gsrc = A.cws + tile * 32u * uint64_t(ncw) * 32u;
+      cw.key_bytes = uint32_t(ncw) * 32u;
+      cw.ncw = ncw;
+      const uint64_t left = A.nkeys - tile * 32;
+      cw.nvalid = left < 32 ? int(left) : 32;
+      cw.lane = lane;
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+      __syncwarp();
+    } else if (MODE == 2) {
+      const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, kk};
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+    } else {
+      const CwKeyMajor cw{A.cws + kk * uint64_t(ncw) * 32u};
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+    }
+    if (valid) st_blk(A.ys + k, y);
   }
 }
 

@@ -43,14 +43,21 @@ constexpr int kInstPrg = kPrgChaCha;
 #define FOR_EACH_GK(X) X(kGrpBytes) X(kGrpU32) X(kGrpU64) X(kGrpU127) X(kGrpU32Mod) X(kGrpU64Mod) X(kGrpU128Mod)
 
 #if FSS_INST_KIND == 1
-template <int G, bool LM>
+template <int G, int MODE>
 static cudaError_t point_launch(const KParams &P, const PointArgs &A, const LaunchCfg &c) {
-  return launch_kernel(point_kernel<FSS_INST_SCHEME, G, kInstPrg, LM>, c, P, A);
+  return launch_kernel(point_kernel<FSS_INST_SCHEME, G, kInstPrg, MODE>, c, P, A);
 }
-point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, bool lm) {
+point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, int mode) {
   switch (gk) {
-#define X(GK) \
-  case GK: return lm ? &point_launch<GK, true> : &point_launch<GK, false>;
+#define X(GK)                                                   \
+  case GK:                                                      \
+    switch (mode) {                                             \
+      case 0: return &point_launch<GK, 0>;                      \
+      case 1: return &point_launch<GK, 1>;                      \
+      case 2: return &point_launch<GK, 2>;                      \
+      case 3: return &point_launch<GK, 3>;                      \
+    }                                                           \
+    return nullptr;
     FOR_EACH_GK(X)
 #undef X
   }

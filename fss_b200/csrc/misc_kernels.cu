@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(1024, 1) microbench_kernel(uint32_t *sink, uin
         else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c));
       } else if (KIND == 3) {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(128 * 0));
+        // ld.volatile: ptxas must not merge or hoist the loads (a plain ld.shared of a loop-invariant
+        // address is hoisted out of the loop and the kernel then measures the XOR instead).
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + uint32_t(j) * 128u));
         a[j] ^= v;  // conflict-free: lane l reads bank l; 8 independent loads per iteration
       } else {
         asm volatile("prmt.b32 %0, %0, %1, 0x7604;" : "+r"(a[j]) : "r"(b));
