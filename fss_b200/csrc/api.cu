@@ -109,13 +109,14 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
 struct EvalAllPlan {
   int unit_bits, breadth_bits, dfs_bits;
 };
-EvalAllPlan plan_evalall(int n) {
+// thread_bits: log2(threads per CTA) of the kernel (9; 8 for the DCF kernel whose nodes carry a value)
+EvalAllPlan plan_evalall(int n, int thread_bits = kEvalAllThreadBits) {
   EvalAllPlan pl;
-  int dfs = n - kEvalAllThreadBits;
+  int dfs = n - thread_bits;
   if (dfs < 1) dfs = 1;
   if (dfs > kMaxDfsBits) dfs = kMaxDfsBits;
   int bt = n - dfs;
-  if (bt > kEvalAllThreadBits) bt = kEvalAllThreadBits;
+  if (bt > thread_bits) bt = thread_bits;
   pl.dfs_bits = dfs;
   pl.breadth_bits = bt;
   pl.unit_bits = bt + dfs;
@@ -358,9 +359,12 @@ int fssb200_relayout(const fssb200_ctx *cc, const void *cws, void *cw_s, void *c
 }
 
 // ---- full-domain evaluation ---------------------------------------------------------------------------------------
+static int evalall_thread_bits(const fssb200_ctx *c) {
+  return c->p.scheme == FSSB200_SCHEME_DCF ? kDcfAllThreadBits : kEvalAllThreadBits;
+}
 uint64_t fssb200_eval_all_granule(const fssb200_ctx *c) {
   if (!c) return 0;
-  return uint64_t(1) << plan_evalall(c->p.in_bits).unit_bits;
+  return uint64_t(1) << plan_evalall(c->p.in_bits, evalall_thread_bits(c)).unit_bits;
 }
 
 static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, const void *cws, const void *ocws,
@@ -376,7 +380,8 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
   if (leaf_begin >= N) return FSSB200_ERANGE;
   if (leaf_count == 0) leaf_count = N - leaf_begin;
   if (leaf_begin + leaf_count > N) return FSSB200_ERANGE;
-  const EvalAllPlan pl = plan_evalall(n);
+  const int tbits = mode == 3 ? kDcfAllThreadBits : kEvalAllThreadBits;
+  const EvalAllPlan pl = plan_evalall(n, tbits);
   const uint64_t granule = uint64_t(1) << pl.unit_bits;
   if ((leaf_begin | leaf_count) & (granule - 1)) return FSSB200_ERANGE;
   if (nkeys == 0) return 0;
@@ -401,7 +406,9 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
   const uint64_t units = nkeys * (leaf_count >> pl.unit_bits);
   LaunchCfg cfg;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cfg.block = dim3(kEvalAllThreads);
+  const unsigned threads = 1u << tbits;
+  const size_t node_bytes = mode == 3 ? 32 : 16;  // DCF nodes carry their value share
+  cfg.block = dim3(threads);
   if (c->p.prg == FSSB200_PRG_AES128_MMO) {
     cfg.grid = dim3(unsigned(units < uint64_t(c->sm_count) ? units : uint64_t(c->sm_count)));
     cfg.smem = kMaxDynSmem;
@@ -409,8 +416,8 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
     const uint64_t cap = uint64_t(c->sm_count) * 2;
     cfg.grid = dim3(unsigned(units < cap ? units : cap));
     // cw copies + two breadth buffers + DFS stack (+ slack for alignment)
-    cfg.smem = size_t(c->ncw + 1) * 32 + 2 * kEvalAllThreads * 16 +
-        size_t(pl.dfs_bits > 1 ? pl.dfs_bits - 1 : 1) * kEvalAllThreads * 16 + 64;
+    cfg.smem = size_t(c->ncw + 1) * 48 + 2 * threads * node_bytes +
+        size_t(pl.dfs_bits > 1 ? pl.dfs_bits - 1 : 1) * threads * node_bytes + 64;
   }
   c->launches++;
   return int(fn(c->kp, a, cfg));
@@ -425,6 +432,8 @@ int fssb200_eval_all(const fssb200_ctx *cc, int party, const void *seeds, const 
       return evalall_impl(c, 0, party, seeds, cws, nullptr, ys, nkeys, leaf_begin, leaf_count, stream);
     case FSSB200_SCHEME_HALFTREE:
       return evalall_impl(c, 1, party, seeds, cws, ocws, ys, nkeys, leaf_begin, leaf_count, stream);
+    case FSSB200_SCHEME_DCF:
+      return evalall_impl(c, 3, party, seeds, cws, nullptr, ys, nkeys, leaf_begin, leaf_count, stream);
     case FSSB200_SCHEME_GROTTO: {
       if (leaf_begin != 0) return FSSB200_ERANGE;
       int rc = evalall_impl(c, 2, party, seeds, cws, nullptr, ys, nkeys, 0, leaf_count, stream);
@@ -436,7 +445,7 @@ int fssb200_eval_all(const fssb200_ctx *cc, int party, const void *seeds, const 
       return int(launch_prefix_xor(static_cast<uint8_t *>(ys), nkeys, cnt, static_cast<cudaStream_t>(stream)));
     }
     default:
-      return FSSB200_ESCHEME;  // DCF EvalAll: not yet on the device path
+      return FSSB200_ESCHEME;
   }
 }
 
@@ -611,7 +620,6 @@ int fssb200_eval_all_host(fssb200_ctx *c, int party, const void *seeds, const vo
     void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count) {
   if (int rc = check_common(c)) return rc;
   if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
-  if (c->p.scheme == FSSB200_SCHEME_DCF) return FSSB200_ESCHEME;
   if (!seeds || !cws || !ys) return FSSB200_EINVAL;
   const bool half = c->p.scheme == FSSB200_SCHEME_HALFTREE, grotto = c->p.scheme == FSSB200_SCHEME_GROTTO;
   if (half && !ocws) return FSSB200_EINVAL;
@@ -700,10 +708,12 @@ evalall_launch_fn get_evalall_launcher(int mode, int gk, int prg) {
     if (mode == 0) return evalall_launcher_aes_dpf(gk);
     if (mode == 1) return evalall_launcher_aes_ht(gk);
     if (mode == 2) return evalall_launcher_aes_grotto(gk);
+    if (mode == 3) return evalall_launcher_aes_dcf(gk);
   } else {
     if (mode == 0) return evalall_launcher_chacha_dpf(gk);
     if (mode == 1) return evalall_launcher_chacha_ht(gk);
     if (mode == 2) return evalall_launcher_chacha_grotto(gk);
+    if (mode == 3) return evalall_launcher_chacha_dcf(gk);
   }
   return nullptr;
 }

@@ -394,4 +394,130 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
   }
 }
 
+// ---- DCF full-domain evaluation (Dcf::EvalAll, dcf.cuh:294-385; the reference has no GPU version) ---------------------
+// Same three phases as evalall_kernel with 256 threads per CTA: a node carries its running value share
+// (32 bytes per stack / frontier entry), four AES blocks per node with fixed keys 0..3.
+constexpr int kDcfAllThreads = 256;
+constexpr int kDcfAllThreadBits = 8;
+
+// group values travel through shared memory in their Into() form
+template <int G>
+FSS_D typename Grp<G>::V smem_load_val(const GroupArgs &ga, uint32_t addr) {
+  return Grp<G>::from(ga, lds_blk(addr));
+}
+template <int G>
+FSS_D void smem_store_val(const GroupArgs &ga, uint32_t addr, typename Grp<G>::V v) {
+  sts_blk(addr, Grp<G>::into(ga, v));
+}
+
+template <int G, int PRG>
+__global__ void __launch_bounds__(kDcfAllThreads, 1)
+dcf_evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAllArgs A) {
+  typedef Grp<G> GR;
+  typedef typename GR::V V;
+  constexpr uint32_t T = kDcfAllThreads;
+  SmemPlan sp = smem_plan<PRG>();
+  const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
+  const int n = A.in_bits, ncw = n + 1;
+  const int tid = threadIdx.x;
+  const int dfs = A.dfs_bits, bt = A.breadth_bits;
+  const int du = n - A.unit_bits;
+  const uint32_t s_cw = sp.alloc(uint32_t(ncw) * 48u, true);            // {cwl, cwr, Into(vcw)} per level
+  const uint32_t s_bfs = sp.alloc(2u * T * 32u, true);                    // {node, value} x 2 buffers
+  const uint32_t s_stk = sp.alloc(uint32_t(dfs > 1 ? dfs - 1 : 1) * T * 32u, false);
+
+  const uint64_t upk = A.leaf_count >> A.unit_bits;
+  const uint64_t total = A.nkeys * upk;
+  uint64_t cur_key = ~uint64_t(0);
+  for (uint64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const uint64_t key = unit / upk;
+    const uint64_t leaf0 = A.leaf_begin + ((unit - key * upk) << A.unit_bits);
+    __syncthreads();
+    if (key != cur_key) {
+      cur_key = key;
+      const uint8_t *kc = A.cws + key * uint64_t(ncw) * 32u;
+      for (int i = tid; i < ncw; i += int(T)) {
+        const blk cs = ld_blk(kc + 32 * i), cv = ld_blk(kc + 32 * i + 16);
+        blk cr = cs;
+        cr.w = (cs.w & ~1u) | (cv.w & 1u);                                  // tr_cw = lsb(cw.v), dcf.cuh:217-219
+        sts_blk(s_cw + 48u * i, cs);
+        sts_blk(s_cw + 48u * i + 16u, cr);
+        sts_blk(s_cw + 48u * i + 32u, GR::into(P.ga, GR::from(P.ga, clamp(cv))));
+      }
+      __syncthreads();
+    }
+#define FSS_DCF_EXPAND(st, u, lvl, l, r, ul, ur)                                                          \
+  dcf_expand<G, PRG>(P.keys, P.ga, pc, st, u, lds_blk(s_cw + 48u * (lvl)), lds_blk(s_cw + 48u * (lvl) + 16u), \
+      smem_load_val<G>(P.ga, s_cw + 48u * (lvl) + 32u), l, r, ul, ur)
+    if (tid < 32) {  // phase 0: root -> unit root
+      blk st = clamp(ld_blk(A.seeds + key));
+      st.w |= uint32_t(A.party);
+      V u = GR::zero(P.ga);
+      const uint64_t path = leaf0 >> A.unit_bits;
+      for (int i = 0; i < du; ++i) {
+        blk l, r;
+        V ul, ur;
+        FSS_DCF_EXPAND(st, u, i, l, r, ul, ur);
+        const bool bit = (path >> (du - 1 - i)) & 1;
+        st = bit ? r : l;
+        u = bit ? ur : ul;
+      }
+      if (tid == 0) {
+        sts_blk(s_bfs, st);
+        smem_store_val<G>(P.ga, s_bfs + 16u, u);
+      }
+    }
+    __syncthreads();
+    for (int j = 0; j < bt; ++j) {  // phase 1: breadth-first
+      const uint32_t src = s_bfs + uint32_t(j & 1) * (T * 32u), dst = s_bfs + uint32_t((j + 1) & 1) * (T * 32u);
+      if (tid < (1 << j)) {
+        const blk st = lds_blk(src + 32u * tid);
+        const V u = smem_load_val<G>(P.ga, src + 32u * tid + 16u);
+        blk l, r;
+        V ul, ur;
+        FSS_DCF_EXPAND(st, u, du + j, l, r, ul, ur);
+        sts_blk(dst + 64u * tid, l);
+        smem_store_val<G>(P.ga, dst + 64u * tid + 16u, ul);
+        sts_blk(dst + 64u * tid + 32u, r);
+        smem_store_val<G>(P.ga, dst + 64u * tid + 48u, ur);
+      }
+      __syncthreads();
+    }
+    if (tid < (1 << bt)) {  // phase 2: depth-first per thread
+      const uint32_t slot = s_bfs + uint32_t(bt & 1) * (T * 32u) + 32u * tid;
+      blk cur = lds_blk(slot);
+      V u = smem_load_val<G>(P.ga, slot + 16u);
+      const int lvl0 = du + bt;
+      const uint64_t out0 = key * A.leaf_count + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
+      const uint32_t pairs = 1u << (dfs - 1);
+      const blk out_v = ld_blk(A.cws + key * uint64_t(ncw) * 32u + 32u * n + 16u);  // cws[n].v
+      uint32_t done = 0;
+      int d = 0;
+      while (true) {
+        blk l, r;
+        V ul, ur;
+        FSS_DCF_EXPAND(cur, u, lvl0 + d, l, r, ul, ur);
+        if (d == dfs - 1) {
+          stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, dcf_leaf<G>(P.ga, uint32_t(A.party), l, ul, out_v),
+              dcf_leaf<G>(P.ga, uint32_t(A.party), r, ur, out_v));
+          ++done;
+          if (done == pairs) break;
+          d = dfs - __ffs(int(done));
+          const uint32_t e = s_stk + (uint32_t(d - 1) * T + tid) * 32u;
+          cur = lds_blk(e);
+          u = smem_load_val<G>(P.ga, e + 16u);
+        } else {
+          const uint32_t e = s_stk + (uint32_t(d) * T + tid) * 32u;
+          sts_blk(e, r);
+          smem_store_val<G>(P.ga, e + 16u, ur);
+          cur = l;
+          u = ul;
+          ++d;
+        }
+      }
+    }
+#undef FSS_DCF_EXPAND
+  }
+}
+
 }  // namespace fssb200

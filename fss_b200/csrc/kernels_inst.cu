@@ -83,6 +83,20 @@ static cudaError_t evalall_launch_grotto(const KParams &P, const EvalAllArgs &A,
   return launch_kernel(evalall_kernel<2, kGrpBytes, kInstPrg>, c, P, A);
 }
 evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int) { return &evalall_launch_grotto; }
+#elif FSS_INST_SCHEME == 1
+template <int G>
+static cudaError_t evalall_launch_dcf(const KParams &P, const EvalAllArgs &A, const LaunchCfg &c) {
+  return launch_kernel(dcf_evalall_kernel<G, kInstPrg>, c, P, A);
+}
+evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int gk) {
+  switch (gk) {
+#define X(GK) \
+  case GK: return &evalall_launch_dcf<GK>;
+    FOR_EACH_GK(X)
+#undef X
+  }
+  return nullptr;
+}
 #else
 constexpr int kMode = FSS_INST_SCHEME == 2 ? 1 : 0;
 template <int G>

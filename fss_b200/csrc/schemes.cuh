@@ -347,4 +347,29 @@ FSS_HD void ht_expand(const PrgKeys &K, const typename Prg<PRG>::ctx_t &pc, blk 
   right = left ^ node;
 }
 
+// Dcf::EvalTree node (dcf.cuh:338-371) with the value share carried WITHOUT the party sign (see
+// dcf_eval_body): children values u + v_side (+ v_cw if t).  cwl / cwr as in dpf_expand; vcw = From(clamp(cw.v)).
+template <int G, int PRG>
+FSS_HD void dcf_expand(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, blk st,
+    typename Grp<G>::V u, blk cwl, blk cwr, typename Grp<G>::V vcw, blk &left, blk &right, typename Grp<G>::V &ul,
+    typename Grp<G>::V &ur) {
+  typedef Grp<G> GR;
+  const uint32_t tm = 0u - lsb(st);
+  blk g[4];  // {s_l, v_l, s_r, v_r}
+  Prg<PRG>::template gen<4>(K, pc, clamp(st), g);
+  left = xor_masked(g[0], tm, cwl);
+  right = xor_masked(g[2], tm, cwr);
+  const typename GR::V base = GR::add_masked(ga, u, tm, vcw);
+  ul = GR::add(ga, base, GR::from(ga, clamp(g[1])));
+  ur = GR::add(ga, base, GR::from(ga, clamp(g[3])));
+}
+// Dcf leaf (dcf.cuh:319-329): y = sign * (u + From(s) + (t ? v_cw_{n+1} : 0))
+template <int G>
+FSS_HD blk dcf_leaf(const GroupArgs &ga, uint32_t party, blk st, typename Grp<G>::V u, blk out_v) {
+  typedef Grp<G> GR;
+  typename GR::V y = GR::add(ga, u, GR::from(ga, clamp(st)));
+  y = GR::add_masked(ga, y, 0u - lsb(st), GR::from(ga, out_v));
+  return GR::into(ga, GR::cneg(ga, y, party));
+}
+
 }  // namespace fssb200

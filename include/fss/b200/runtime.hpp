@@ -1,0 +1,77 @@
+// SPDX-License-Identifier: Apache-2.0
+// fss/b200/runtime.hpp -- glue between the header-only C++ surface and the C ABI (include/fssb200.h):
+// a process-wide cache of evaluator contexts keyed by the full parameter set, and error translation.
+// The C ABI never throws; this C++ layer turns non-zero return codes into std::runtime_error (the
+// reference only asserts, dpf.cuh:209).
+#pragma once
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <cuda_runtime.h>
+
+#include "../../fssb200.h"
+
+namespace fss::b200 {
+
+inline void Check(int rc, const char *what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + fssb200_strerror(rc));
+}
+
+struct ParamsLess {
+  bool operator()(const fssb200_params &a, const fssb200_params &b) const { return std::memcmp(&a, &b, sizeof(a)) < 0; }
+};
+
+// Contexts are immutable and shareable between threads / streams; they live until process exit.
+inline fssb200_ctx *ContextFor(fssb200_params p) {
+  static std::mutex mu;
+  static std::map<fssb200_params, fssb200_ctx *, ParamsLess> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  p.device = dev;
+  p.reserved = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(p);
+  if (it != cache.end()) return it->second;
+  fssb200_ctx *ctx = nullptr;
+  Check(fssb200_ctx_create(&p, &ctx), "fssb200_ctx_create");
+  Check(fssb200_ctx_reserve_host(ctx, 0), "fssb200_ctx_reserve_host");
+  cache.emplace(p, ctx);
+  return ctx;
+}
+
+template <int in_bits, typename Group, typename Prg, typename In>
+fssb200_params MakeParams(int scheme, const Prg &prg, int pred = FSSB200_PRED_LT, const int4 *hash_key = nullptr) {
+  static_assert(sizeof(In) == 1 || sizeof(In) == 2 || sizeof(In) == 4 || sizeof(In) == 8 || sizeof(In) == 16);
+  fssb200_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.scheme = scheme;
+  p.in_bits = in_bits;
+  p.in_bytes = sizeof(In);
+  p.group = Group::kFssB200Group;
+  p.mod_lo = Group::kFssB200ModLo;
+  p.mod_hi = Group::kFssB200ModHi;
+  p.prg = Prg::kFssB200Prg;
+  p.pred = pred;
+  prg.FssB200Key(p.prg_key);
+  if (hash_key) std::memcpy(p.hash_key, hash_key, 16);
+  return p;
+}
+
+// A 16-byte value the reference passes by value (a seed, an output CW) as a stream-ordered device temp.
+struct DeviceBlock {
+  int4 *ptr = nullptr;
+  cudaStream_t stream;
+  DeviceBlock(int4 v, cudaStream_t s) : stream(s) {
+    if (cudaMallocAsync(reinterpret_cast<void **>(&ptr), sizeof(int4), s) != cudaSuccess) throw std::bad_alloc();
+    cudaMemcpyAsync(ptr, &v, sizeof(int4), cudaMemcpyHostToDevice, s);  // pageable source: staged before return
+  }
+  ~DeviceBlock() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+  DeviceBlock(const DeviceBlock &) = delete;
+  DeviceBlock &operator=(const DeviceBlock &) = delete;
+};
+
+}  // namespace fss::b200
