@@ -273,7 +273,8 @@ def run_own_arm(args) -> None:
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     peaks = {}
     if rank == 0:
-        for kind, name in ((0, "lop3"), (1, "imad"), (2, "lop3_imad_mixed"), (3, "lds32_conflict_free"), (4, "prmt")):
+        for kind, name in ((0, "lop3"), (1, "imad"), (2, "lop3_imad_mixed"), (3, "lds32_conflict_free"), (4, "prmt"),
+                           (5, "idp4a"), (6, "prmt_idp4a_mixed")):
             peaks[name] = fss_b200.microbench(kind, local)
     measured = {}
     try:

@@ -11,12 +11,15 @@
 //    replicated 32x so that lane l only ever touches bank l: every lookup is one conflict-free
 //    shared-memory wavefront regardless of the (pseudo-random) indices.  A single table indexed
 //    by random bytes averages ~3.15-way conflicts.
-//  * Layout: entry x of table pair {U0,U1} sits at A0 + x*256 + t*128 + lane*4, pair {U2,U3} at
-//    A0 + 65536 + ..., with A0 a 64 KiB-aligned shared-window address.  Then the address of a
-//    lookup is ONE instruction:  PRMT(word, laneoff, 0x76k4) drops state byte k into byte 1 of
-//    (A0 | lane*4); the table select is the LDS immediate offset.  (Generic code needs
-//    shift + mask (+ add) per lookup -- 2-3 integer ops; the reference compiles to 68 integer
-//    instructions per round, this is 16 PRMT + 8 LOP3.)
+//  * The address of a lookup is ONE instruction, and the 16 address computations of a round are split
+//    between the two integer issue pipes (ncu of the first version: ALU pipe 91 % busy, FMA pipe 3 %):
+//      - pair {U0,U1}: entry x at A0 + x*256 + t*128 + lane*4 with A0 a 64 KiB-aligned shared-window
+//        address:  PRMT(word, laneoff, 0x76k4) drops state byte k into byte 1 of (A0 | lane*4)  [ALU pipe];
+//      - U2 at A0 + 64K + x*128 + lane*4, U3 at A0 + 96K + x*128 + lane*4:
+//        IDP.4A(word, 128 << 8k, laneoff) = byte_k(word)*128 + laneoff                       [FMA pipe];
+//    the table select is the LDS immediate offset.  (Generic code needs shift + mask (+ add) per
+//    lookup -- 2-3 integer ops; the reference compiles to 68 integer instructions per round, this is
+//    8 PRMT + 8 IDP.4A + 8 LOP3.)
 //  * Round keys are warp-uniform constant-bank operands (PrgKeys in the kernel parameter block).
 //  * Last round takes S[x] out of the byte lane of the table that already has it in place.
 //
@@ -72,8 +75,17 @@ constexpr U0Table make_u0() {
 }
 static_assert(sbox_of(0) == 0x63 && sbox_of(1) == 0x7c && sbox_of(0x53) == 0xed, "AES S-box");
 
-constexpr int kAesTblBytes = 131072;        // two 64 KiB regions
-constexpr uint32_t kOffU0 = 0, kOffU1 = 128, kOffU2 = 65536, kOffU3 = 65536 + 128;
+constexpr int kAesTblBytes = 131072;        // 64 KiB pair region {U0,U1} + 32 KiB U2 + 32 KiB U3
+constexpr uint32_t kOffU0 = 0, kOffU1 = 128, kOffU2 = 65536, kOffU3 = 98304;
+// Byte offset (from A0) of entry x of table t in lane `lane`'s bank.
+__host__ __device__ constexpr uint32_t aes_tbl_offset(int t, uint32_t x, uint32_t lane) {
+  return t == 0 ? kOffU0 + x * 256u + lane * 4u
+       : t == 1 ? kOffU1 + x * 256u + lane * 4u
+       : t == 2 ? kOffU2 + x * 128u + lane * 4u
+                : kOffU3 + x * 128u + lane * 4u;
+}
+// U_t[x] from U0[x]: rotate left by 8*t bits.
+__host__ __device__ constexpr uint32_t aes_tbl_word(uint32_t u0, int t) { return t == 0 ? u0 : ((u0 << (8 * t)) | (u0 >> (32 - 8 * t))); }
 
 // Host side: key expansion (FIPS-197 5.2) into little-endian words, used by ctx_create.
 inline void aes128_expand_le(const uint8_t key[16], uint32_t rk[44]) {
@@ -103,6 +115,7 @@ __device__ __constant__ U0Table c_u0 = make_u0();
 // ---- lookup primitives -------------------------------------------------------------------------------
 #if FSS_DEVICE_CODE
 FSS_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+FSS_D uint32_t dp4a_u32(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 template <uint32_t OFF>
 FSS_D uint32_t tlookup(uint32_t addr) {
   uint32_t v;
@@ -121,7 +134,11 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   }
   return r;
 }
-// host emulation of the shared-memory table image (tests/host_emul only)
+inline uint32_t dp4a_u32(uint32_t a, uint32_t b, uint32_t c) {
+  for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+  return c;
+}
+// host emulation of the shared-memory table image (tests/host_emul only; A0 = 0 there)
 uint8_t *host_aes_tables();
 template <uint32_t OFF>
 inline uint32_t tlookup(uint32_t addr) {
@@ -133,10 +150,14 @@ struct AesCtx {
   uint32_t laneoff;  // (A0 | lane*4): byte 1 is zero and receives the table index
 };
 
-// Address of table entry [byte K of w] for this lane (one PRMT).
-template <int K>
-FSS_HD uint32_t taddr(const AesCtx &c, uint32_t w) {
-  return prmt(w, c.laneoff, 0x7604u | (uint32_t(K) << 4));
+// U_T[byte K of w] for this lane: one address instruction (PRMT for the pair region, IDP.4A for U2 / U3)
+// + one LDS.32 whose immediate selects the table.
+template <int T, int K>
+FSS_HD uint32_t tl(const AesCtx &c, uint32_t w) {
+  if (T == 0) return tlookup<kOffU0>(prmt(w, c.laneoff, 0x7604u | (uint32_t(K) << 4)));
+  if (T == 1) return tlookup<kOffU1>(prmt(w, c.laneoff, 0x7604u | (uint32_t(K) << 4)));
+  if (T == 2) return tlookup<kOffU2>(dp4a_u32(w, 128u << (8 * K), c.laneoff));
+  return tlookup<kOffU3>(dp4a_u32(w, 128u << (8 * K), c.laneoff));
 }
 
 // Round-key providers.  r = round 0..10, j = word 0..3.
@@ -157,20 +178,16 @@ FSS_HD blk aes128_mmo(const AesCtx &c, const Key &key, const blk s) {
   uint32_t a0 = s.x ^ key(0, 0), a1 = s.y ^ key(0, 1), a2 = s.z ^ key(0, 2), a3 = s.w ^ key(0, 3);
 #pragma unroll
   for (int r = 1; r <= 9; ++r) {
-    const uint32_t t0 = tlookup<kOffU0>(taddr<0>(c, a0)) ^ tlookup<kOffU1>(taddr<1>(c, a1)) ^
-        tlookup<kOffU2>(taddr<2>(c, a2)) ^ tlookup<kOffU3>(taddr<3>(c, a3)) ^ key(r, 0);
-    const uint32_t t1 = tlookup<kOffU0>(taddr<0>(c, a1)) ^ tlookup<kOffU1>(taddr<1>(c, a2)) ^
-        tlookup<kOffU2>(taddr<2>(c, a3)) ^ tlookup<kOffU3>(taddr<3>(c, a0)) ^ key(r, 1);
-    const uint32_t t2 = tlookup<kOffU0>(taddr<0>(c, a2)) ^ tlookup<kOffU1>(taddr<1>(c, a3)) ^
-        tlookup<kOffU2>(taddr<2>(c, a0)) ^ tlookup<kOffU3>(taddr<3>(c, a1)) ^ key(r, 2);
-    const uint32_t t3 = tlookup<kOffU0>(taddr<0>(c, a3)) ^ tlookup<kOffU1>(taddr<1>(c, a0)) ^
-        tlookup<kOffU2>(taddr<2>(c, a1)) ^ tlookup<kOffU3>(taddr<3>(c, a2)) ^ key(r, 3);
+    const uint32_t t0 = tl<0, 0>(c, a0) ^ tl<1, 1>(c, a1) ^ tl<2, 2>(c, a2) ^ tl<3, 3>(c, a3) ^ key(r, 0);
+    const uint32_t t1 = tl<0, 0>(c, a1) ^ tl<1, 1>(c, a2) ^ tl<2, 2>(c, a3) ^ tl<3, 3>(c, a0) ^ key(r, 1);
+    const uint32_t t2 = tl<0, 0>(c, a2) ^ tl<1, 1>(c, a3) ^ tl<2, 2>(c, a0) ^ tl<3, 3>(c, a1) ^ key(r, 2);
+    const uint32_t t3 = tl<0, 0>(c, a3) ^ tl<1, 1>(c, a0) ^ tl<2, 2>(c, a1) ^ tl<3, 3>(c, a2) ^ key(r, 3);
     a0 = t0; a1 = t1; a2 = t2; a3 = t3;
   }
   // Last round (no MixColumns): S[x] sits in byte 0 of U2, byte 1 of U3, byte 2 of U0, byte 3 of U1.
 #define FSS_AES_LAST(w0, w1, w2, w3, kj, sj)                                              \
-  ((prmt(prmt(tlookup<kOffU2>(taddr<0>(c, w0)), tlookup<kOffU3>(taddr<1>(c, w1)), 0x0050u), \
-         prmt(tlookup<kOffU0>(taddr<2>(c, w2)), tlookup<kOffU1>(taddr<3>(c, w3)), 0x7200u), 0x7610u)) ^ (kj) ^ (sj))
+  ((prmt(prmt(tl<2, 0>(c, w0), tl<3, 1>(c, w1), 0x0050u), prmt(tl<0, 2>(c, w2), tl<1, 3>(c, w3), 0x7200u), 0x7610u)) ^ \
+   (kj) ^ (sj))
   blk o;
   o.x = FSS_AES_LAST(a0, a1, a2, a3, key(10, 0), s.x);
   o.y = FSS_AES_LAST(a1, a2, a3, a0, key(10, 1), s.y);
@@ -187,14 +204,9 @@ __device__ inline void aes_tables_init(uint32_t a0) {
   for (uint32_t e = threadIdx.x; e < 256u * 32u; e += blockDim.x) {
     const uint32_t x = e >> 5, lane = e & 31u;
     const uint32_t u0 = c_u0.v[x];
-    const uint32_t u1 = (u0 << 8) | (u0 >> 24);
-    const uint32_t u2 = (u0 << 16) | (u0 >> 16);
-    const uint32_t u3 = (u0 << 24) | (u0 >> 8);
-    const uint32_t addr = a0 + x * 256u + lane * 4u;
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + kOffU0), "r"(u0) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + kOffU1), "r"(u1) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + kOffU2), "r"(u2) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + kOffU3), "r"(u3) : "memory");
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(a0 + aes_tbl_offset(t, x, lane)), "r"(aes_tbl_word(u0, t)) : "memory");
   }
 }
 #endif

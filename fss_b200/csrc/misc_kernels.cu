@@ -239,8 +239,13 @@ __global__ void __launch_bounds__(1024, 1) microbench_kernel(uint32_t *sink, uin
         // address is hoisted out of the loop and the kernel then measures the XOR instead).
         asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + uint32_t(j) * 128u));
         a[j] ^= v;  // conflict-free: lane l reads bank l; 8 independent loads per iteration
-      } else {
+      } else if (KIND == 4) {
         asm volatile("prmt.b32 %0, %0, %1, 0x7604;" : "+r"(a[j]) : "r"(b));
+      } else if (KIND == 5) {
+        asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+      } else {
+        if (j & 1) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+        else asm volatile("prmt.b32 %0, %0, %1, 0x7604;" : "+r"(a[j]) : "r"(b));
       }
     }
   }
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(1024, 1) microbench_kernel(uint32_t *sink, uin
 }
 
 int run_microbench(int kind, double *ops_per_s) {
-  if (kind < 0 || kind > 4) return FSSB200_EINVAL;
+  if (kind < 0 || kind > 6) return FSSB200_EINVAL;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -270,7 +275,9 @@ int run_microbench(int kind, double *ops_per_s) {
       case 1: microbench_kernel<1><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
       case 2: microbench_kernel<2><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
       case 3: microbench_kernel<3><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
-      default: microbench_kernel<4><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
+      case 4: microbench_kernel<4><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
+      case 5: microbench_kernel<5><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
+      default: microbench_kernel<6><<<grid, block>>>(sink, 0x9e3779b9u, 0x7f4a7c15u); break;
     }
     cudaEventRecord(t1);
     e = cudaEventSynchronize(t1);

@@ -256,7 +256,7 @@ int fssb200_prg_gen(const fssb200_ctx *ctx, const void *seeds, void *out, int mu
 uint64_t fssb200_ctx_launch_count(const fssb200_ctx *ctx);
 /* Integer-pipe / shared-memory issue-rate microbenchmarks used for the roofline
  * denominator.  kind: 0 = LOP3 chain, 1 = IMAD chain, 2 = LOP3+IMAD
- * mixed, 3 = conflict-free LDS.32, 4 = PRMT.  Returns ops (or lookups) per second
+ * mixed, 3 = conflict-free LDS.32, 4 = PRMT, 5 = IDP.4A, 6 = PRMT+IDP.4A mixed.  Returns ops (or lookups) per second
  * through *ops_per_s. */
 int fssb200_microbench(int device, int kind, double *ops_per_s);
 

@@ -24,13 +24,10 @@ uint8_t *host_aes_tables() {
     constexpr U0Table u0t = make_u0();
     for (uint32_t x = 0; x < 256; ++x)
       for (uint32_t lane = 0; lane < 32; ++lane) {
-        const uint32_t u0 = u0t.v[x];
-        const uint32_t u1 = (u0 << 8) | (u0 >> 24), u2 = (u0 << 16) | (u0 >> 16), u3 = (u0 << 24) | (u0 >> 8);
-        const uint32_t a = x * 256u + lane * 4u;
-        std::memcpy(&g_tables[a + kOffU0], &u0, 4);
-        std::memcpy(&g_tables[a + kOffU1], &u1, 4);
-        std::memcpy(&g_tables[a + kOffU2], &u2, 4);
-        std::memcpy(&g_tables[a + kOffU3], &u3, 4);
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t w = aes_tbl_word(u0t.v[x], t);
+          std::memcpy(&g_tables[aes_tbl_offset(t, x, lane)], &w, 4);
+        }
       }
   }
   return g_tables.data();
