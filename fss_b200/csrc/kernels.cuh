@@ -146,6 +146,7 @@ struct CwStagedWarp {
   FSS_D void begin_level(int i) const {
     if ((i & (L - 1)) == 0 && i < ncw) load(i);
   }
+  FSS_D void done_level(int) const {}
   FSS_D uint32_t at(int i) const { return buf + lane * kSlot + uint32_t(i & (L - 1)) * 32u; }
   FSS_D blk s(int i) const { return lds_blk(at(i)); }
   FSS_D blk v(int i) const { return lds_blk(at(i) + 16u); }

@@ -43,7 +43,8 @@ struct CwKeyMajor {
   }
   FSS_HD blk out_s(int n) const { return s(n); }  // cws[n].s  (DPF)
   FSS_HD blk out_v(int n) const { return v(n); }  // cws[n].v  (DCF)
-  FSS_HD void begin_level(int) const {}           // (staged accessors load a chunk here)
+  FSS_HD void begin_level(int) const {}           // (the staged accessor waits for the level here ...
+  FSS_HD void done_level(int) const {}            //  ... and starts the next level's copy here)
 };
 // Level-major (fssb200_relayout; point_eval_gpu.cuh:39-91 with >32-level control words).
 struct CwLevelMajor {
@@ -58,6 +59,7 @@ struct CwLevelMajor {
   FSS_HD blk out_s(int) const { return ld_blk(out_cw + k); }
   FSS_HD blk out_v(int) const { return ld_blk(out_cw + k); }
   FSS_HD void begin_level(int) const {}
+  FSS_HD void done_level(int) const {}
 };
 
 // ---- DPF ------------------------------------------------------------------------------------------------
@@ -80,12 +82,14 @@ FSS_HD blk dpf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename P
   cw.begin_level(0);
   blk cs = cw.s(0);
   uint32_t cf = cw.flag(0);
+  cw.done_level(0);
 #pragma unroll 1
   for (int i = 0; i < n; ++i) {
     // fetch the next level's correction word before this level's PRG call (entry n is the output CW)
     cw.begin_level(i + 1);
     const blk cs_next = (i + 1 < n) ? cw.s(i + 1) : cw.out_s(n);
     const uint32_t cf_next = (i + 1 < n) ? cw.flag(i + 1) : 0u;
+    cw.done_level(i + 1);
     const uint32_t xb = in_bit(x, n - 1 - i);      // MSB first (dpf.cuh:196)
     const uint32_t tm = 0u - lsb(st);
     blk c[1];
@@ -153,11 +157,13 @@ FSS_HD blk dcf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename P
   typename GR::V acc = GR::zero(ga);
   cw.begin_level(0);
   blk cs = cw.s(0), cv = cw.v(0);
+  cw.done_level(0);
 #pragma unroll 1
   for (int i = 0; i < n; ++i) {
     cw.begin_level(i + 1);
     const blk cs_next = (i + 1 < n) ? cw.s(i + 1) : zero_blk();
     const blk cv_next = (i + 1 < n) ? cw.v(i + 1) : cw.out_v(n);  // entry n = {0, v_cw_{n+1}}
+    cw.done_level(i + 1);
     const uint32_t xb = in_bit(x, n - 1 - i);
     const uint32_t t = lsb(st);
     const uint32_t tm = 0u - t;
@@ -266,10 +272,12 @@ FSS_HD blk ht_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename Pr
   node.w |= party;
   cw.begin_level(0);
   blk cs = cw.s(0);
+  cw.done_level(0);
 #pragma unroll 1
   for (int i = 0; i < n - 1; ++i) {
     cw.begin_level(i + 1);
     const blk cs_next = cw.s(i + 1);
+    cw.done_level(i + 1);
     const uint32_t xm = 0u - in_bit(x, n - 1 - i);
     const uint32_t tm = 0u - lsb(node);
     const blk h = ht_hash<PRG>(K, pc, node);
