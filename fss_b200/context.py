@@ -228,17 +228,25 @@ class Context:
         return cw_s, cw_v, extra, out_cw
 
     def eval_levelmajor(self, party: int, seeds: torch.Tensor, layout, xs: IntLike,
-                        ocws: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        ocws: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Point evaluation on the level-major (compact) key layout; CPU tensors go through
+        ``fssb200_eval_levelmajor_host`` (strided chunk copies inside the library)."""
         cw_s, cw_v, extra, out_cw = layout
         seeds = seeds.contiguous()
         n = seeds.shape[0]
-        _, dev = self._dev(seeds)
+        on_gpu, dev = self._dev(seeds)
         x = self.in_tensor(xs, seeds.device)
-        ys = torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
-        with torch.cuda.device(dev):
-            L.check(L.lib.fssb200_eval_levelmajor(self.handle(dev), party, _ptr(seeds), _ptr(cw_s), _ptr(cw_v),
-                                                  _ptr(extra), _ptr(out_cw), _ptr(ocws), _ptr(x), _ptr(ys), n,
-                                                  self._stream(dev)), "fssb200_eval_levelmajor")
+        ys = out if out is not None else torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
+        if on_gpu:
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_eval_levelmajor(self.handle(dev), party, _ptr(seeds), _ptr(cw_s), _ptr(cw_v),
+                                                      _ptr(extra), _ptr(out_cw), _ptr(ocws), _ptr(x), _ptr(ys), n,
+                                                      self._stream(dev)), "fssb200_eval_levelmajor")
+        else:
+            self._ensure_host(dev)
+            L.check(L.lib.fssb200_eval_levelmajor_host(self.handle(dev), party, _ptr(seeds), _ptr(cw_s), _ptr(cw_v),
+                                                       _ptr(extra), _ptr(out_cw), _ptr(ocws), _ptr(x), _ptr(ys), n),
+                    "fssb200_eval_levelmajor_host")
         return ys
 
     # ---- Grotto (grotto_dcf.cuh:94-135,174-238) ---------------------------------------------------------------------

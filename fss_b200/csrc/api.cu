@@ -577,6 +577,59 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
   return rc;
 }
 
+int fssb200_eval_levelmajor_host(fssb200_ctx *c, int party, const void *seeds, const void *cw_s, const void *cw_v,
+    const void *extra, const void *out_cw, const void *ocws, const void *xs, void *ys, size_t nkeys) {
+  if (int rc = check_common(c)) return rc;
+  if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
+  const int scheme = c->p.scheme;
+  if (scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  if (!seeds || !cw_s || !xs || !ys) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_DCF && (!cw_v || !out_cw)) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_DPF && (!extra || !out_cw)) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_HALFTREE && (!extra || !ocws)) return FSSB200_EINVAL;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  const size_t ck = a.chunk_keys, ib = size_t(c->p.in_bytes), n = size_t(c->p.in_bits), nw = (n + 31) / 32;
+  const uint8_t *h_s = static_cast<const uint8_t *>(cw_s), *h_v = static_cast<const uint8_t *>(cw_v),
+                *h_e = static_cast<const uint8_t *>(extra);
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = nkeys - k0 < ck ? nkeys - k0 : ck;
+    const int b = int(chunk & 1);
+    cudaStream_t st = a.stream[b];
+    // one set: seeds | cw_s[n][k] | cw_v[n][k] | extra[nw][k] | out_cw | ocws | xs | ys   (<= bytes_per_set by construction)
+    uint8_t *d_seeds = a.dev[b];
+    uint8_t *d_s = d_seeds + align_up(k * 16, 256);
+    uint8_t *d_v = d_s + align_up(n * k * 16, 256);
+    uint8_t *d_e = d_v + (cw_v ? align_up(n * k * 16, 256) : 0);
+    uint8_t *d_oc = d_e + (extra ? align_up(nw * k * 4, 256) : 0);
+    uint8_t *d_ocws = d_oc + align_up(k * 16, 256);
+    uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_ys = d_xs + align_up(k * 16, 256);
+    if (size_t(d_ys + k * 16 - a.dev[b]) > a.bytes_per_set) return FSSB200_ENOARENA;
+    CUDA_TRY(cudaMemcpyAsync(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(d_s, k * 16, h_s + k0 * 16, nkeys * 16, k * 16, n, cudaMemcpyHostToDevice, st));
+    if (cw_v) CUDA_TRY(cudaMemcpy2DAsync(d_v, k * 16, h_v + k0 * 16, nkeys * 16, k * 16, n, cudaMemcpyHostToDevice, st));
+    if (extra) CUDA_TRY(cudaMemcpy2DAsync(d_e, k * 4, h_e + k0 * 4, nkeys * 4, k * 4, nw, cudaMemcpyHostToDevice, st));
+    if (out_cw)
+      CUDA_TRY(cudaMemcpyAsync(d_oc, static_cast<const uint8_t *>(out_cw) + k0 * 16, k * 16, cudaMemcpyHostToDevice, st));
+    if (ocws)
+      CUDA_TRY(cudaMemcpyAsync(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, cudaMemcpyHostToDevice, st));
+    rc = fssb200_eval_levelmajor(c, party, d_seeds, d_s, cw_v ? d_v : nullptr, extra ? d_e : nullptr,
+        out_cw ? d_oc : nullptr, ocws ? d_ocws : nullptr, d_xs, d_ys, k, st);
+    if (rc) break;
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(a.stream[i]);
+    if (!rc && e != cudaSuccess) rc = int(e);
+  }
+  return rc;
+}
+
 int fssb200_gen_host(fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *ocws,
     size_t nkeys) {
   if (int rc = check_common(c)) return rc;

@@ -244,6 +244,13 @@ int fssb200_eval_all_host(fssb200_ctx *ctx, int party, const void *seeds, const 
                           uint64_t leaf_count);
 int fssb200_gen_host(fssb200_ctx *ctx, const void *s0s, const void *alphas, const void *betas,
                      void *cws, void *ocws, size_t nkeys);
+/* fssb200_eval_levelmajor with HOST arrays in the level-major layout of fssb200_relayout (the compact
+ * key format: 16 B + 1 bit per level instead of the 32-byte Cw): chunks of
+ * keys are gathered from the [level][key] arrays with strided copies.  Same NULL rules as
+ * fssb200_eval_levelmajor. */
+int fssb200_eval_levelmajor_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cw_s,
+                                 const void *cw_v, const void *extra, const void *out_cw,
+                                 const void *ocws, const void *xs, void *ys, size_t nkeys);
 
 /* ---- introspection / measurement helpers -------------------------------------- */
 

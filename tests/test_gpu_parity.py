@@ -148,7 +148,13 @@ def test_random_batches(dev, orc, scheme, n, group, mod, prg, nkeys):
     if scheme != "halftree":
         assert np.array_equal(N(lay[3]), want[3])
     ys_lm = ctx.eval_levelmajor(1, T(s0s[:, 1], dev), lay, xs, ocws)
-    assert np.array_equal(N(ys_lm), N(ctx.eval(1, T(s0s[:, 1], dev), cws, xs, ocws)))
+    want_ys = N(ctx.eval(1, T(s0s[:, 1], dev), cws, xs, ocws))
+    assert np.array_equal(N(ys_lm), want_ys)
+    # the same layout from HOST arrays (fssb200_eval_levelmajor_host), in chunks smaller than the batch
+    ctx.reserve_host(max(1, nkeys // 3))
+    lay_h = tuple(None if t is None else t.cpu() for t in lay)
+    ys_h = ctx.eval_levelmajor(1, T(s0s[:, 1], "cpu"), lay_h, xs, None if ocws is None else ocws.cpu())
+    assert ys_h.device.type == "cpu" and np.array_equal(N(ys_h), want_ys)
     assert ctx.launch_count() >= 5
 
 
