@@ -4,6 +4,7 @@
 // geometry, host-buffer staging.  There is no CPU evaluation path in this library: every entry
 // point either launches sm_100a kernels or returns an error code.
 #include <atomic>
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no libcuda link dependency)
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -43,6 +44,34 @@ namespace {
   } while (0)
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Tensor map of the key-major Cw array for the TMA-fed point kernels (CwTile in kernels.cuh).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_cw_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, int ncw) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return int(e);
+    if (q != cudaDriverEntryPointSuccess || !p) return int(cudaErrorNotSupported);
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "PointArgs::tmap size");
+  alignas(64) CUtensorMap m;
+  const cuuint64_t gdim[2] = {cuuint64_t(ncw) * 32u, cuuint64_t(nkeys)};
+  const cuuint64_t gstride[1] = {cuuint64_t(ncw) * 32u};
+  const cuuint32_t box[2] = {64u, 32u};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(cws), gdim, gstride, box, estride,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return int(cudaErrorInvalidValue);
+  std::memcpy(out, &m, 128);
+  return 0;
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -90,7 +119,7 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
   LaunchCfg cfg;
   cfg.stream = s;
   if (c->p.prg == FSSB200_PRG_AES128_MMO) {
-    const unsigned threads = mode == 1 ? 1024u : unsigned(kPointThreads);
+    const unsigned threads = mode == 1 ? 1024u : (mode == 5 ? 768u : unsigned(kPointThreads));
     const uint64_t want = (n + threads - 1) / threads;
     cfg.grid = dim3(unsigned(want < uint64_t(c->sm_count) ? (want ? want : 1) : c->sm_count));
     cfg.block = dim3(threads);
@@ -101,7 +130,8 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
     cfg.grid = dim3(unsigned(want < cap ? (want ? want : 1) : cap));
     cfg.block = dim3(256);
     // staged correction words: one slab per warp (L = 4, or L = 2 in mode 1)
-    cfg.smem = (mode == 0 || mode == 1) ? 8 * (mode == 1 ? CwStagedWarp<2>::kWarpBytes : CwStagedWarp<4>::kWarpBytes) + 32 : 0;
+    cfg.smem = (mode == 0 || mode == 1) ? 8 * (mode == 1 ? CwStagedWarp<2>::kWarpBytes : CwStagedWarp<4>::kWarpBytes) + 32
+        : (mode == 4 || mode == 5) ? 8 * CwTile::kWarpBytes + 8 * 16 + 512 + 32 : 0;
   }
   return cfg;
 }
@@ -182,12 +212,12 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   c->ncw = q.scheme == FSSB200_SCHEME_HALFTREE ? q.in_bits : q.in_bits + 1;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = int(prop.sharedMemPerBlockOptin);
-  // measured on B200 (profiles/r01_point_modes.md): DPF (one AES per level, 64 registers) gains 3 % from
-  // 32 warps per SM; DCF / Half-Tree are faster with 16 warps and no register cap
-  c->point_mode = (q.scheme == FSSB200_SCHEME_DPF && q.prg == FSSB200_PRG_AES128_MMO) ? 1 : 0;
+  // measured on B200 (profiles/r01_point_modes.md): correction words fetched by the TMA unit (CwTile) beat the
+  // cp.async slabs for every scheme; DPF / DCF gain another 1-3 % from 24 warps per SM, Half-Tree does not
+  c->point_mode = q.scheme == FSSB200_SCHEME_HALFTREE ? 4 : 5;
   if (const char *e = std::getenv("FSSB200_POINT_MODE")) {  // A/B measurement knob
     const int m = std::atoi(e);
-    if (m == 0 || m == 1 || m == 3) c->point_mode = m;
+    if (m == 0 || m == 1 || m == 3 || m == 4 || m == 5) c->point_mode = m;
   }
   std::memset(&c->kp, 0, sizeof(c->kp));
   if (q.prg == FSSB200_PRG_AES128_MMO) {
@@ -311,6 +341,10 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   a.in_bytes = c->p.in_bytes;
   a.party = party;
   a.vmask = c->vmask;
+  if (mode == 4 || mode == 5) {
+    if (nkeys >> 31) return FSSB200_EINVAL;  // TMA coordinates are 32-bit
+    if (int rc = make_cw_tensor_map(a.tmap, cws, nkeys, c->ncw)) return rc;
+  }
   const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream), mode);
   c->launches++;
   return int(fn(c->kp, a, cfg));

@@ -93,6 +93,9 @@ struct PointArgs {
   int in_bytes;
   int party;
   uint32_t vmask;         // value mask for <= 32-bit groups
+  // CUtensorMap of the key-major Cw array as a 2-D byte tensor [nkeys][ncw*32], box 32 keys x 64 B,
+  // SWIZZLE_64B (point modes 4 / 5: correction words fetched by the TMA unit); opaque here
+  alignas(64) uint8_t tmap[128];
 };
 
 struct GenArgs {

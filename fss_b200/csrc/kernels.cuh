@@ -53,15 +53,17 @@ struct SmemPlan {
   uint32_t a0;               // table base (AES) -- 64 KiB aligned
   uint32_t lo, lo_end;       // scratch region below the tables
   uint32_t hi, hi_end;       // scratch region above the tables
-  // bump allocation, 16-byte aligned; prefers the region given by `want_hi`
-  FSS_D uint32_t alloc(uint32_t bytes, bool want_hi) {
+  // bump allocation, `align`-byte aligned (power of two >= 16); prefers the region given by `want_hi`
+  FSS_D uint32_t alloc(uint32_t bytes, bool want_hi, uint32_t align = 16u) {
     bytes = (bytes + 15u) & ~15u;
     for (int pass = 0; pass < 2; ++pass) {
       const bool use_hi = (pass == 0) ? want_hi : !want_hi;
       if (use_hi) {
-        if (hi + bytes <= hi_end) { const uint32_t r = hi; hi += bytes; return r; }
+        const uint32_t r = (hi + align - 1u) & ~(align - 1u);
+        if (r + bytes <= hi_end) { hi = r + bytes; return r; }
       } else {
-        if (lo + bytes <= lo_end) { const uint32_t r = lo; lo += bytes; return r; }
+        const uint32_t r = (lo + align - 1u) & ~(align - 1u);
+        if (r + bytes <= lo_end) { lo = r + bytes; return r; }
       }
     }
     __trap();  // host-side geometry (api.cu: plan_evalall) guarantees this cannot happen
@@ -159,6 +161,83 @@ struct CwStagedWarp {
   FSS_D blk out_v(int n) const { return v(n); }
 };
 
+// ---- correction words fetched by the TMA unit (point modes 4 / 5) ---------------------------------------------------
+// ncu of the cp.async version above (profiles/r01_ncu_full.md): LSU data pipe 91 % busy, 7.9 % of its shared-memory
+// wavefronts are the LDGSTS writes, their 2-way conflicts and the slab reads, plus ~30 integer instructions of
+// address / predicate glue per level and a warp-wide wait per chunk.  Here the key-major Cw array is described to
+// the TMA unit as a 2-D byte tensor [nkeys][ncw*32] and ONE `cp.async.bulk.tensor.2d` per warp and chunk brings the
+// next two levels of the warp's 32 keys (box = 32 rows x 64 B) into a double-buffered 2 KB tile, completion counted
+// on a per-warp mbarrier.  No LSU instructions, registers or address arithmetic for the copy; the chunk after the
+// current one (also across tiles) is always in flight, so the wait does not stall; SWIZZLE_64B (16-byte chunk index
+// ^= address bits 7..8) makes the lane-per-key 128-bit reads conflict-free without padding; rows / levels outside
+// the tensor are zero-filled by the hardware, so ragged tiles and odd ncw need no predicates.
+struct CwTile {
+  static constexpr uint32_t kBuf = 2048u;          // 32 keys x 2 levels x 32 B
+  static constexpr uint32_t kWarpBytes = 2u * kBuf;
+  uint32_t buf;        // the warp's two tiles (512-byte aligned)
+  uint32_t mbar;       // the warp's two mbarriers
+  const void *tmap;
+  uint32_t lane, rowoff, sw;
+  int row0, next_row0;  // first key of this tile / of the warp's next tile (-1: none)
+  int nchunks;
+  uint32_t *seq;       // chunks this warp has waited for so far (kernel lifetime; buffer = seq & 1, parity = seq >> 1)
+
+  static FSS_D void init_barriers(uint32_t mbar, uint32_t lane) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar + 8u) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  // lane 0: request levels [2c, 2c+2) of keys [row, row+32) into buffer (q & 1)
+  static FSS_D void issue(const void *tmap, uint32_t buf, uint32_t mbar, uint32_t q, int c, int row) {
+    const uint32_t b = q & 1u, mb = mbar + 8u * b;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(kBuf) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            buf + b * kBuf),
+        "l"(tmap), "r"(c * 64), "r"(row), "r"(mb)
+        : "memory");
+  }
+  FSS_D void begin_level(int j) const {
+    if (j & 1) return;
+    const int c = j >> 1;
+    const uint32_t q = *seq;
+    __syncwarp();  // every lane is done with chunk q-1, whose buffer the next request overwrites
+    if (lane == 0) {
+      if (c + 1 < nchunks) issue(tmap, buf, mbar, q + 1u, c + 1, row0);
+      else if (next_row0 >= 0) issue(tmap, buf, mbar, q + 1u, 0, next_row0);
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FSS_TILE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra FSS_TILE_WAIT;\n"
+        "}\n" ::"r"(mbar + 8u * (q & 1u)),
+        "r"((q >> 1) & 1u)
+        : "memory");
+    *seq = q + 1u;
+  }
+  FSS_D void done_level(int) const {}
+  // 16-byte piece h (0 = s, 1 = v / flag word) of level j in this lane's row of the current tile
+  FSS_D uint32_t at(int j, uint32_t h) const {
+    const uint32_t b = (*seq - 1u) & 1u;
+    return buf + b * kBuf + rowoff + ((((uint32_t(j) & 1u) * 2u + h) ^ sw) << 4);
+  }
+  FSS_D blk s(int j) const { return lds_blk(at(j, 0)); }
+  FSS_D blk v(int j) const { return lds_blk(at(j, 1)); }
+  FSS_D uint32_t flag(int j) const {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(at(j, 1)) : "memory");
+    return (w & 0xffu) != 0;
+  }
+  FSS_D blk out_s(int n) const { return s(n); }
+  FSS_D blk out_v(int n) const { return v(n); }
+};
+
 // ---- batched point evaluation --------------------------------------------------------------------------------
 // One key per thread; warps own tiles of 32 consecutive keys (grid-stride over tiles).
 // SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE}.
@@ -166,12 +245,15 @@ struct CwStagedWarp {
 //       1 = key-major, staged, 1024 threads (<= 64 regs), L = 2
 //       2 = level-major arrays (fssb200_eval_levelmajor), direct coalesced loads
 //       3 = key-major, direct per-thread global loads (the round-1 first version; kept for A/B runs)
-constexpr int kPointModes = 4;
+//       4 = key-major, TMA tiles (CwTile), 512 threads
+//       5 = key-major, TMA tiles (CwTile), 768 threads (<= 85 regs)
+constexpr int kPointModes = 6;
 template <int MODE>
 struct PointMode {
-  static constexpr int kMaxThreads = MODE == 1 ? 1024 : 512;
+  static constexpr int kMaxThreads = MODE == 1 ? 1024 : (MODE == 5 ? 768 : 512);
   static constexpr int kL = MODE == 1 ? 2 : 4;
   static constexpr bool kStaged = MODE <= 1;
+  static constexpr bool kTma = MODE >= 4;
 };
 
 template <int SCHEME, int G, int PRG, class Cw>
@@ -192,7 +274,7 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
   const int n = A.in_bits;
   const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE) ? n : n + 1;
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  uint32_t slab = 0;
+  uint32_t slab = 0, mbar = 0;
   if (PM::kStaged) {
     for (uint32_t w = 0; w < nwarps; ++w) {  // same allocation sequence in every thread
       const uint32_t a = sp.alloc(CwStagedWarp<PM::kL>::kWarpBytes, false);
@@ -201,7 +283,18 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
   }
   const uint64_t ntiles = (A.nkeys + 31) >> 5;
   const uint64_t tile_stride = uint64_t(gridDim.x) * nwarps;
-  for (uint64_t tile = uint64_t(blockIdx.x) * nwarps + wid; tile < ntiles; tile += tile_stride) {
+  const uint64_t tile0 = uint64_t(blockIdx.x) * nwarps + wid;
+  uint32_t tma_seq = 0;
+  if (PM::kTma) {
+    mbar = sp.alloc(16u * nwarps, false) + 16u * wid;
+    for (uint32_t w = 0; w < nwarps; ++w) {
+      const uint32_t a = sp.alloc(CwTile::kWarpBytes, false, 512u);
+      if (w == wid) slab = a;
+    }
+    CwTile::init_barriers(mbar, lane);
+    if (lane == 0 && tile0 < ntiles) CwTile::issue(A.tmap, slab, mbar, 0u, 0, int(tile0 * 32));
+  }
+  for (uint64_t tile = tile0; tile < ntiles; tile += tile_stride) {
     const uint64_t k = tile * 32 + lane;
     const bool valid = k < A.nkeys;
     const uint64_t kk = valid ? k : A.nkeys - 1;  // idle lanes of a ragged tile shadow the last key
@@ -219,6 +312,19 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       cw.lane = lane;
       y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
       __syncwarp();
+    } else if (PM::kTma) {
+      CwTile cw;
+      cw.buf = slab;
+      cw.mbar = mbar;
+      cw.tmap = A.tmap;
+      cw.lane = lane;
+      cw.rowoff = lane * 64u;
+      cw.sw = (lane >> 1) & 3u;
+      cw.row0 = int(tile * 32);
+      cw.next_row0 = tile + tile_stride < ntiles ? int((tile + tile_stride) * 32) : -1;
+      cw.nchunks = (ncw + 1) >> 1;
+      cw.seq = &tma_seq;
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
     } else if (MODE == 2) {
       const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, kk};
       y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);

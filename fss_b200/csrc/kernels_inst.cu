@@ -56,6 +56,8 @@ point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, int mode) {
       case 1: return &point_launch<GK, 1>;                      \
       case 2: return &point_launch<GK, 2>;                      \
       case 3: return &point_launch<GK, 3>;                      \
+      case 4: return &point_launch<GK, 4>;                      \
+      case 5: return &point_launch<GK, 5>;                      \
     }                                                           \
     return nullptr;
     FOR_EACH_GK(X)
