@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfssb200.so")
 
-SCHEME_DPF, SCHEME_DCF, SCHEME_HALFTREE, SCHEME_GROTTO = 0, 1, 2, 3
+SCHEME_DPF, SCHEME_DCF, SCHEME_HALFTREE, SCHEME_GROTTO, SCHEME_VDPF = 0, 1, 2, 3, 4
 GROUP_BYTES, GROUP_U8, GROUP_U16, GROUP_U32, GROUP_U64, GROUP_U128 = 0, 1, 2, 3, 4, 5
 PRG_AES128_MMO, PRG_CHACHA = 0, 1
 PRED_LT, PRED_GT = 0, 1
@@ -24,7 +24,7 @@ class Params(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("in_bits", C.c_int32), ("in_bytes", C.c_int32), ("group", C.c_int32),
                 ("mod_lo", C.c_uint64), ("mod_hi", C.c_uint64), ("prg", C.c_int32), ("pred", C.c_int32),
                 ("prg_key", C.c_uint8 * 64), ("hash_key", C.c_uint8 * 16), ("device", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("hash_iv", C.c_uint8 * 64)]
 
 
 class FssError(RuntimeError):
@@ -52,6 +52,14 @@ SYMBOLS = {
     "fssb200_grotto_expand": (_I, [_VP, _I, _VP, _VP, _VP, _SZ, _U64, _U64, _VP]),
     "fssb200_grotto_preprocess": (_I, [_VP, _I, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_grotto_eval": (_I, [_VP, _VP, _VP, _VP, _SZ, _VP]),
+    "fssb200_vdpf_gen": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "fssb200_vdpf_eval": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "fssb200_vdpf_eval_levelmajor": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "fssb200_vdpf_prove": (_I, [_VP, _VP, _VP, _SZ, _VP, _SZ, _VP]),
+    "fssb200_vdpf_eval_all": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "fssb200_hash": (_I, [_VP, _I, _VP, _VP, _SZ, _VP]),
+    "fssb200_vdpf_gen_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
+    "fssb200_vdpf_eval_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
     "fssb200_relayout": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_eval_levelmajor": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_ctx_reserve_host": (_I, [_VP, _SZ]),

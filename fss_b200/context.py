@@ -20,7 +20,8 @@ import torch
 
 from . import _lib as L
 
-_SCHEMES = {"dpf": L.SCHEME_DPF, "dcf": L.SCHEME_DCF, "halftree": L.SCHEME_HALFTREE, "grotto": L.SCHEME_GROTTO}
+_SCHEMES = {"dpf": L.SCHEME_DPF, "dcf": L.SCHEME_DCF, "halftree": L.SCHEME_HALFTREE, "grotto": L.SCHEME_GROTTO,
+            "vdpf": L.SCHEME_VDPF}
 _GROUPS = {"bytes": L.GROUP_BYTES, "u8": L.GROUP_U8, "u16": L.GROUP_U16, "u32": L.GROUP_U32, "u64": L.GROUP_U64,
            "u128": L.GROUP_U128}
 _PRGS = {"aes128_mmo": L.PRG_AES128_MMO, "chacha": L.PRG_CHACHA}
@@ -31,6 +32,10 @@ DEFAULT_AES_KEYS = bytes(range(1, 17)) + bytes(range(16, 0, -1)) + bytes(
     [1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8]) + bytes([8, 8, 7, 7, 6, 6, 5, 5, 4, 4, 3, 3, 2, 2, 1, 1])
 DEFAULT_CHACHA_NONCE = (0x12345678).to_bytes(4, "little") + (0x9ABCDEF0).to_bytes(4, "little")
 DEFAULT_HASH_KEY = b"".join(v.to_bytes(4, "little") for v in (0x12345678, 0x9ABCDEF0, 0x0FEDCBA9, 0x87654321))
+# VDPF: IVs of the XorHash / Hash Blake3 plugins (first one = the reference tests' constant, src/vdpf_test.cu:35-36)
+DEFAULT_HASH_IVS = b"".join(v.to_bytes(4, "little") for v in (
+    0x11111111, 0x22222222, 0x33333333, 0x44444444, 0x55555555, 0x66666666, 0x77777777, 0x88888888,
+    0x99999999, 0xAAAAAAAA, 0xBBBBBBBB, 0xCCCCCCCC, 0xDDDDDDDD, 0xEEEEEEEE, 0xFFFFFFFF, 0x01234567))
 
 IntLike = Union[int, Sequence[int], torch.Tensor]
 
@@ -47,7 +52,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class Context:
     def __init__(self, scheme: str, in_bits: int, group: str = "bytes", mod: int = 0, prg: str = "aes128_mmo",
                  pred: str = "lt", prg_key: Optional[bytes] = None, hash_key: Optional[bytes] = None,
-                 in_bytes: Optional[int] = None):
+                 in_bytes: Optional[int] = None, hash_iv: Optional[bytes] = None):
         self.scheme, self.in_bits, self.group, self.prg, self.pred = scheme, in_bits, group, prg, pred
         if group == "u128" and mod == 0:
             mod = 1 << 127
@@ -56,8 +61,11 @@ class Context:
         self.prg_key = prg_key if prg_key is not None else (
             DEFAULT_AES_KEYS if prg == "aes128_mmo" else DEFAULT_CHACHA_NONCE)
         self.hash_key = hash_key if hash_key is not None else DEFAULT_HASH_KEY
-        self.ncw = in_bits if scheme == "halftree" else in_bits + 1
-        self.mul = {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2}[scheme]
+        self.hash_iv = hash_iv if hash_iv is not None else DEFAULT_HASH_IVS
+        if len(self.hash_iv) != 64:
+            raise ValueError("hash_iv must be 64 bytes (XorHash IV || Hash IV)")
+        self.ncw = in_bits if scheme in ("halftree", "vdpf") else in_bits + 1
+        self.mul = {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2, "vdpf": 2}[scheme]
         self._handles: dict[int, C.c_void_p] = {}
         self._host_reserved: dict[int, int] = {}
 
@@ -71,6 +79,7 @@ class Context:
         key = bytes(self.prg_key).ljust(64, b"\0")
         C.memmove(p.prg_key, key, 64)
         C.memmove(p.hash_key, bytes(self.hash_key), 16)
+        C.memmove(p.hash_iv, bytes(self.hash_iv), 64)
         return p
 
     def handle(self, device: Optional[int] = None) -> C.c_void_p:
@@ -221,7 +230,7 @@ class Context:
         cw_s = torch.empty((nb, n, 4), dtype=torch.int32, device=d)
         cw_v = torch.empty((nb, n, 4), dtype=torch.int32, device=d) if self.scheme == "dcf" else None
         extra = torch.zeros(((nb + 31) // 32, n), dtype=torch.int32, device=d) if self.scheme != "dcf" else None
-        out_cw = torch.empty((n, 4), dtype=torch.int32, device=d) if self.scheme != "halftree" else None
+        out_cw = torch.empty((n, 4), dtype=torch.int32, device=d) if self.scheme not in ("halftree", "vdpf") else None
         with torch.cuda.device(dev):
             L.check(L.lib.fssb200_relayout(self.handle(dev), _ptr(cws), _ptr(cw_s), _ptr(cw_v), _ptr(extra),
                                            _ptr(out_cw), n, self._stream(dev)), "fssb200_relayout")
@@ -282,6 +291,100 @@ class Context:
             L.check(L.lib.fssb200_grotto_eval(self.handle(dev), _ptr(pt), _ptr(x), _ptr(ys), n, self._stream(dev)),
                     "fssb200_grotto_eval")
         return ys
+
+    # ---- VDPF (vdpf.cuh) ---------------------------------------------------------------------------------------------
+    def vdpf_gen(self, s0s: torch.Tensor, alphas: IntLike, betas: torch.Tensor):
+        """Vdpf::Gen (vdpf.cuh:97-177) -> cws (N,n,8), cs (N,4,4), ocws (N,4), status (N,) int32
+        (1 = t0 == t1: resample that key's seeds; its ocw row is zero)."""
+        s0s, betas = s0s.contiguous(), betas.contiguous()
+        n = s0s.shape[0]
+        on_gpu, dev = self._dev(s0s)
+        d = s0s.device
+        al = self.in_tensor(alphas, d)
+        cws = torch.empty((n, self.ncw, 8), dtype=torch.int32, device=d)
+        cs = torch.empty((n, 4, 4), dtype=torch.int32, device=d)
+        ocws = torch.zeros((n, 4), dtype=torch.int32, device=d)
+        status = torch.empty((n,), dtype=torch.int32, device=d)
+        h = self.handle(dev)
+        if on_gpu:
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_vdpf_gen(h, _ptr(s0s), _ptr(al), _ptr(betas), _ptr(cws), _ptr(cs), _ptr(ocws),
+                                               _ptr(status), n, self._stream(dev)), "fssb200_vdpf_gen")
+        else:
+            self._ensure_host(dev)
+            L.check(L.lib.fssb200_vdpf_gen_host(h, _ptr(s0s), _ptr(al), _ptr(betas), _ptr(cws), _ptr(cs), _ptr(ocws),
+                                                _ptr(status), n), "fssb200_vdpf_gen_host")
+        return cws, cs, ocws, status
+
+    def vdpf_eval(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, cs: torch.Tensor, ocws: torch.Tensor,
+                  xs: IntLike, layout=None):
+        """Vdpf::Eval (vdpf.cuh:191-243) -> ys (N,4), pi_tildes (N,4,4).  ``layout`` = (cw_s, extra) from
+        ``relayout`` selects the level-major kernel (point_eval_gpu.cuh:514-527)."""
+        seeds, cs, ocws = seeds.contiguous(), cs.contiguous(), ocws.contiguous()
+        n = seeds.shape[0]
+        on_gpu, dev = self._dev(seeds)
+        d = seeds.device
+        x = self.in_tensor(xs, d)
+        ys = torch.empty((n, 4), dtype=torch.int32, device=d)
+        pis = torch.empty((n, 4, 4), dtype=torch.int32, device=d)
+        h = self.handle(dev)
+        if layout is not None:
+            cw_s, extra = layout
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_vdpf_eval_levelmajor(h, party, _ptr(seeds), _ptr(cw_s), _ptr(extra), _ptr(cs),
+                                                           _ptr(ocws), _ptr(x), _ptr(ys), _ptr(pis), n,
+                                                           self._stream(dev)), "fssb200_vdpf_eval_levelmajor")
+            return ys, pis
+        cws = cws.contiguous()
+        if on_gpu:
+            with torch.cuda.device(dev):
+                L.check(L.lib.fssb200_vdpf_eval(h, party, _ptr(seeds), _ptr(cws), _ptr(cs), _ptr(ocws), _ptr(x),
+                                                _ptr(ys), _ptr(pis), n, self._stream(dev)), "fssb200_vdpf_eval")
+        else:
+            self._ensure_host(dev)
+            L.check(L.lib.fssb200_vdpf_eval_host(h, party, _ptr(seeds), _ptr(cws), _ptr(cs), _ptr(ocws), _ptr(x),
+                                                 _ptr(ys), _ptr(pis), n), "fssb200_vdpf_eval_host")
+        return ys, pis
+
+    def vdpf_prove(self, pi_tildes: torch.Tensor, cs: torch.Tensor) -> torch.Tensor:
+        """Vdpf::Prove (vdpf.cuh:254-264): pi_tildes (N,m,4,4), cs (N,4,4) -> proofs (N,4,4)."""
+        pi_tildes, cs = pi_tildes.contiguous(), cs.contiguous()
+        n, m = cs.shape[0], pi_tildes.shape[1]
+        _, dev = self._dev(cs)
+        pis = torch.empty((n, 4, 4), dtype=torch.int32, device=cs.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_vdpf_prove(self.handle(dev), _ptr(pi_tildes), _ptr(cs), m, _ptr(pis), n,
+                                             self._stream(dev)), "fssb200_vdpf_prove")
+        return pis
+
+    def vdpf_eval_all(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, cs: torch.Tensor,
+                      ocws: torch.Tensor):
+        """Vdpf::EvalAll (vdpf.cuh:294-342) -> ys (N,2^n,4), proofs (N,4,4)."""
+        seeds, cws, cs, ocws = seeds.contiguous(), cws.contiguous(), cs.contiguous(), ocws.contiguous()
+        n = seeds.shape[0]
+        _, dev = self._dev(seeds)
+        ys = torch.empty((n, 1 << self.in_bits, 4), dtype=torch.int32, device=seeds.device)
+        pis = torch.empty((n, 4, 4), dtype=torch.int32, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_vdpf_eval_all(self.handle(dev), party, _ptr(seeds), _ptr(cws), _ptr(cs), _ptr(ocws),
+                                                _ptr(ys), _ptr(pis), n, self._stream(dev)), "fssb200_vdpf_eval_all")
+        return ys, pis
+
+    @staticmethod
+    def vdpf_verify(pi0: torch.Tensor, pi1: torch.Tensor) -> torch.Tensor:
+        """Vdpf::Verify (vdpf.cuh:271-276): per-key equality of two proofs (N,4,4) -> bool (N,)."""
+        return (pi0 == pi1).flatten(1).all(dim=1)
+
+    def hash(self, which: int, msgs: torch.Tensor) -> torch.Tensor:
+        """Blake3 plugin known-answer hook: which 0 = XorHash (N,2,4)->(N,4,4), 1 = Hash (N,4,4)->(N,2,4)."""
+        msgs = msgs.contiguous()
+        n = msgs.shape[0]
+        _, dev = self._dev(msgs)
+        out = torch.empty((n, 4 if which == 0 else 2, 4), dtype=torch.int32, device=msgs.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_hash(self.handle(dev), which, _ptr(msgs), _ptr(out), n, self._stream(dev)),
+                    "fssb200_hash")
+        return out
 
     # ---- PRG known-answer hook -----------------------------------------------------------------------------------------
     def prg_gen(self, seeds: torch.Tensor, mul: int) -> torch.Tensor:

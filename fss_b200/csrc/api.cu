@@ -11,6 +11,7 @@
 
 #include "dispatch.h"
 #include "misc_kernels.cuh"
+#include "vdpf_kernels.cuh"
 
 using namespace fssb200;
 
@@ -180,7 +181,7 @@ const char *fssb200_strerror(int code) {
 int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   if (!p || !out) return FSSB200_EINVAL;
   *out = nullptr;
-  if (p->scheme < FSSB200_SCHEME_DPF || p->scheme > FSSB200_SCHEME_GROTTO) return FSSB200_EINVAL;
+  if (p->scheme < FSSB200_SCHEME_DPF || p->scheme > FSSB200_SCHEME_VDPF) return FSSB200_EINVAL;
   if (p->prg != FSSB200_PRG_AES128_MMO && p->prg != FSSB200_PRG_CHACHA) return FSSB200_EINVAL;
   if (p->pred != FSSB200_PRED_LT && p->pred != FSSB200_PRED_GT) return FSSB200_EINVAL;
   if (p->in_bytes != 1 && p->in_bytes != 2 && p->in_bytes != 4 && p->in_bytes != 8 && p->in_bytes != 16)
@@ -209,7 +210,7 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   c->gk = gk;
   c->vmask = vmask;
   c->mul = q.scheme == FSSB200_SCHEME_DCF ? 4 : (q.scheme == FSSB200_SCHEME_HALFTREE ? 1 : 2);
-  c->ncw = q.scheme == FSSB200_SCHEME_HALFTREE ? q.in_bits : q.in_bits + 1;
+  c->ncw = (q.scheme == FSSB200_SCHEME_HALFTREE || q.scheme == FSSB200_SCHEME_VDPF) ? q.in_bits : q.in_bits + 1;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = int(prop.sharedMemPerBlockOptin);
   // measured on B200 (profiles/r01_point_modes.md): correction words fetched by the TMA unit (CwTile) beat the
@@ -230,6 +231,7 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
     std::memcpy(c->kp.keys.nonce, q.prg_key, 8);
   }
   std::memcpy(c->kp.keys.hash_key, q.hash_key, 16);
+  std::memcpy(c->kp.keys.hash_iv, q.hash_iv, 64);
   c->kp.ga.vmask = vmask;
   c->kp.ga.mod[0] = uint32_t(q.mod_lo);
   c->kp.ga.mod[1] = uint32_t(q.mod_lo >> 32);
@@ -268,6 +270,7 @@ int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, cons
   if (int rc = check_common(c)) return rc;
   if (!s0s || !alphas || !cws) return FSSB200_EINVAL;
   const int scheme = c->p.scheme;
+  if (scheme == FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;  // fssb200_vdpf_gen
   if (scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
   if (scheme != FSSB200_SCHEME_GROTTO && !betas) return FSSB200_EINVAL;
   if (!aligned16(s0s) || !aligned16(cws) || !aligned16(betas) || !aligned16(ocws)) return FSSB200_EALIGN;
@@ -280,6 +283,7 @@ int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, cons
   DeviceGuard g(c->p.device);
   if (g.err != cudaSuccess) return int(g.err);
   GenArgs a;
+  std::memset(&a, 0, sizeof(a));
   a.s0s = static_cast<const blk *>(s0s);
   a.alphas = static_cast<const uint8_t *>(alphas);
   a.betas = scheme == FSSB200_SCHEME_GROTTO ? nullptr : static_cast<const blk *>(betas);
@@ -298,12 +302,17 @@ int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, cons
 // ---- point eval ---------------------------------------------------------------------------------------------------
 static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const void *seeds, const void *cws,
     const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream, bool level_major, const void *cw_s,
-    const void *cw_v, const void *extra, const void *out_cw) {
+    const void *cw_v, const void *extra, const void *out_cw, const void *vdpf_cs = nullptr, void *vdpf_pis = nullptr) {
   fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
   if (int rc = check_common(c)) return rc;
   const int scheme = c->p.scheme;
   if (scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;  // Grotto: EvalAll / Preprocess+Eval only
   if (want_scheme >= 0 && want_scheme != scheme) return FSSB200_ESCHEME;
+  if (scheme == FSSB200_SCHEME_VDPF) {  // only through fssb200_vdpf_eval
+    if (want_scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+    if (!vdpf_cs || !vdpf_pis || !ocws) return FSSB200_EINVAL;
+    if (!aligned16(vdpf_cs) || !aligned16(vdpf_pis)) return FSSB200_EALIGN;
+  }
   if (party != 0 && party != 1) return FSSB200_EINVAL;
   if (!seeds || !xs || !ys) return FSSB200_EINVAL;
   if (scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
@@ -311,7 +320,7 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
     if (!cw_s) return FSSB200_EINVAL;
     if (scheme == FSSB200_SCHEME_DCF && (!cw_v || !out_cw)) return FSSB200_EINVAL;
     if (scheme == FSSB200_SCHEME_DPF && (!extra || !out_cw)) return FSSB200_EINVAL;
-    if (scheme == FSSB200_SCHEME_HALFTREE && !extra) return FSSB200_EINVAL;
+    if ((scheme == FSSB200_SCHEME_HALFTREE || scheme == FSSB200_SCHEME_VDPF) && !extra) return FSSB200_EINVAL;
     if (!aligned16(cw_s) || !aligned16(cw_v) || !aligned16(out_cw)) return FSSB200_EALIGN;
   } else {
     if (!cws) return FSSB200_EINVAL;
@@ -336,6 +345,8 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   a.cw_v = static_cast<const blk *>(cw_v);
   a.extra = static_cast<const uint32_t *>(extra);
   a.out_cw = static_cast<const blk *>(out_cw);
+  a.cs = static_cast<const blk *>(vdpf_cs);
+  a.pis = static_cast<blk *>(vdpf_pis);
   a.nkeys = nkeys;
   a.in_bits = c->p.in_bits;
   a.in_bytes = c->p.in_bytes;
@@ -483,6 +494,98 @@ int fssb200_eval_all(const fssb200_ctx *cc, int party, const void *seeds, const 
   }
 }
 
+// ---- VDPF ---------------------------------------------------------------------------------------------------------
+int fssb200_vdpf_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, const void *betas, void *cws,
+    void *cs, void *ocws, void *status, size_t nkeys, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!s0s || !alphas || !betas || !cws || !cs || !ocws || !status) return FSSB200_EINVAL;
+  if (!aligned16(s0s) || !aligned16(cws) || !aligned16(betas) || !aligned16(ocws) || !aligned16(cs)) return FSSB200_EALIGN;
+  if (reinterpret_cast<uintptr_t>(alphas) % c->p.in_bytes || reinterpret_cast<uintptr_t>(status) % 4) return FSSB200_EALIGN;
+  if (nkeys == 0) return 0;
+  gen_launch_fn fn = get_gen_launcher(FSSB200_SCHEME_VDPF, c->gk, c->p.prg);
+  if (!fn) return FSSB200_EGROUP;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  GenArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.s0s = static_cast<const blk *>(s0s);
+  a.alphas = static_cast<const uint8_t *>(alphas);
+  a.betas = static_cast<const blk *>(betas);
+  a.cws = static_cast<uint8_t *>(cws);
+  a.ocws = static_cast<blk *>(ocws);
+  a.cs = static_cast<blk *>(cs);
+  a.status = static_cast<int32_t *>(status);
+  a.nkeys = nkeys;
+  a.in_bits = c->p.in_bits;
+  a.in_bytes = c->p.in_bytes;
+  a.pred = c->p.pred;
+  a.vmask = c->vmask;
+  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream));
+  c->launches++;
+  return int(fn(c->kp, a, cfg));
+}
+
+int fssb200_vdpf_eval(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *cs,
+    const void *ocws, const void *xs, void *ys, void *pis, size_t nkeys, void *stream) {
+  return eval_impl(c, FSSB200_SCHEME_VDPF, party, seeds, cws, ocws, xs, ys, nkeys, stream, false, nullptr, nullptr,
+      nullptr, nullptr, cs, pis);
+}
+
+int fssb200_vdpf_eval_levelmajor(const fssb200_ctx *c, int party, const void *seeds, const void *cw_s,
+    const void *extra, const void *cs, const void *ocws, const void *xs, void *ys, void *pis, size_t nkeys,
+    void *stream) {
+  return eval_impl(c, FSSB200_SCHEME_VDPF, party, seeds, nullptr, ocws, xs, ys, nkeys, stream, true, cw_s, nullptr,
+      extra, nullptr, cs, pis);
+}
+
+int fssb200_vdpf_prove(const fssb200_ctx *cc, const void *pi_tildes, const void *cs, size_t m, void *pis,
+    size_t nkeys, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!cs || !pis || (m && !pi_tildes)) return FSSB200_EINVAL;
+  if (!aligned16(pi_tildes) || !aligned16(cs) || !aligned16(pis)) return FSSB200_EALIGN;
+  if (nkeys == 0) return 0;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  c->launches++;
+  return int(launch_vdpf_prove(c->kp, static_cast<const blk *>(pi_tildes), static_cast<const blk *>(cs), m,
+      static_cast<blk *>(pis), nkeys, static_cast<cudaStream_t>(stream)));
+}
+
+int fssb200_vdpf_eval_all(const fssb200_ctx *cc, int party, const void *seeds, const void *cws, const void *cs,
+    const void *ocws, void *ys, void *pis, size_t nkeys, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!cs || !ocws || !pis) return FSSB200_EINVAL;
+  if (!aligned16(cs) || !aligned16(ocws) || !aligned16(pis)) return FSSB200_EALIGN;
+  if (c->p.in_bits > 32) return FSSB200_EDOMAIN;
+  // tree: packed (s | t) leaves into ys; then leaf conversion + sequential proof chain, one warp per key
+  if (int rc = evalall_impl(c, 4, party, seeds, cws, nullptr, ys, nkeys, 0, 0, stream)) return rc;
+  if (nkeys == 0) return 0;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  c->launches++;
+  return int(launch_vdpf_finish(c->kp, c->gk, party, c->p.in_bits, static_cast<const blk *>(cs),
+      static_cast<const blk *>(ocws), static_cast<blk *>(ys), static_cast<blk *>(pis), nkeys,
+      static_cast<cudaStream_t>(stream)));
+}
+
+int fssb200_hash(const fssb200_ctx *cc, int which, const void *msgs, void *out, size_t n, void *stream) {
+  fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
+  if (int rc = check_common(c)) return rc;
+  if ((which != 0 && which != 1) || !msgs || !out) return FSSB200_EINVAL;
+  if (!aligned16(msgs) || !aligned16(out)) return FSSB200_EALIGN;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  c->launches++;
+  return int(launch_hash(c->kp, which, static_cast<const blk *>(msgs), static_cast<blk *>(out), n,
+      static_cast<cudaStream_t>(stream)));
+}
+
 int fssb200_grotto_expand(const fssb200_ctx *cc, int party, const void *seeds, const void *cws, void *t,
     size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count, void *stream) {
   fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
@@ -557,7 +660,7 @@ int fssb200_ctx_reserve_host(fssb200_ctx *c, size_t max_keys_per_chunk) {
   HostArena &a = c->arena;
   // per key: seeds(2 for gen) + cws + ocw + x/alpha(16) + beta + y; evalall output is staged in the
   // same buffers (>= 64 MiB per set)
-  size_t per_key = 32 + size_t(c->ncw) * 32 + 16 + 16 + 16 + 16;
+  size_t per_key = 32 + size_t(c->ncw) * 32 + 16 + 16 + 16 + 16 + 64 + 64 + 16;  // + VDPF cs, pis, status
   size_t bytes = per_key * max_keys_per_chunk;
   if (bytes < (size_t(64) << 20)) bytes = size_t(64) << 20;
   bytes = (bytes + 255) & ~size_t(255);
@@ -577,7 +680,7 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
     const void *xs, void *ys, size_t nkeys) {
   if (int rc = check_common(c)) return rc;
   if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
-  if (c->p.scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  if (c->p.scheme == FSSB200_SCHEME_GROTTO || c->p.scheme == FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
   if (!seeds || !cws || !xs || !ys) return FSSB200_EINVAL;
   if (c->p.scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
   DeviceGuard g(c->p.device);
@@ -603,6 +706,90 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
     rc = fssb200_eval(c, party, d_seeds, d_cws, ocws ? d_ocws : nullptr, d_xs, d_ys, k, s);
     if (rc) break;
     CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(a.stream[i]);
+    if (!rc && e != cudaSuccess) rc = int(e);
+  }
+  return rc;
+}
+
+int fssb200_vdpf_gen_host(fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *cs,
+    void *ocws, void *status, size_t nkeys) {
+  if (int rc = check_common(c)) return rc;
+  if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!s0s || !alphas || !betas || !cws || !cs || !ocws || !status) return FSSB200_EINVAL;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  const size_t ck = a.chunk_keys, cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = nkeys - k0 < ck ? nkeys - k0 : ck;
+    const int b = int(chunk & 1);
+    cudaStream_t s = a.stream[b];
+    // the arena holds >= 96 + ncw*32 bytes per key (fssb200_ctx_reserve_host); VDPF needs 32 + 16 + 16 + cwb + 64 + 16 + 4
+    uint8_t *d_s0s = a.dev[b];
+    uint8_t *d_al = d_s0s + align_up(k * 32, 256);
+    uint8_t *d_be = d_al + align_up(k * 16, 256);
+    uint8_t *d_cws = d_be + align_up(k * 16, 256);
+    uint8_t *d_cs = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_ocws = d_cs + align_up(k * 64, 256);
+    uint8_t *d_st = d_ocws + align_up(k * 16, 256);
+    if (size_t(d_st + k * 4 - a.dev[b]) > a.bytes_per_set) return FSSB200_ENOARENA;
+    CUDA_TRY(cudaMemcpyAsync(d_s0s, static_cast<const uint8_t *>(s0s) + k0 * 32, k * 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_al, static_cast<const uint8_t *>(alphas) + k0 * ib, k * ib, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_be, static_cast<const uint8_t *>(betas) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(d_ocws, 0, k * 16, s));  // Gen leaves ocw untouched when it returns 1
+    rc = fssb200_vdpf_gen(c, d_s0s, d_al, d_be, d_cws, d_cs, d_ocws, d_st, k, s);
+    if (rc) break;
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(cws) + k0 * cwb, d_cws, k * cwb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(cs) + k0 * 64, d_cs, k * 64, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ocws) + k0 * 16, d_ocws, k * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(status) + k0 * 4, d_st, k * 4, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(a.stream[i]);
+    if (!rc && e != cudaSuccess) rc = int(e);
+  }
+  return rc;
+}
+
+int fssb200_vdpf_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *cs,
+    const void *ocws, const void *xs, void *ys, void *pis, size_t nkeys) {
+  if (int rc = check_common(c)) return rc;
+  if (!c->arena.chunk_keys) return FSSB200_ENOARENA;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!seeds || !cws || !cs || !ocws || !xs || !ys || !pis) return FSSB200_EINVAL;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  HostArena &a = c->arena;
+  const size_t ck = a.chunk_keys, cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = nkeys - k0 < ck ? nkeys - k0 : ck;
+    const int b = int(chunk & 1);
+    cudaStream_t s = a.stream[b];
+    uint8_t *d_seeds = a.dev[b];
+    uint8_t *d_cws = d_seeds + align_up(k * 16, 256);
+    uint8_t *d_cs = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_ocws = d_cs + align_up(k * 64, 256);
+    uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_ys = d_xs + align_up(k * 16, 256);
+    uint8_t *d_pis = d_ys + align_up(k * 16, 256);
+    if (size_t(d_pis + k * 64 - a.dev[b]) > a.bytes_per_set) return FSSB200_ENOARENA;
+    CUDA_TRY(cudaMemcpyAsync(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_cs, static_cast<const uint8_t *>(cs) + k0 * 64, k * 64, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, cudaMemcpyHostToDevice, s));
+    rc = fssb200_vdpf_eval(c, party, d_seeds, d_cws, d_cs, d_ocws, d_xs, d_ys, d_pis, k, s);
+    if (rc) break;
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(pis) + k0 * 64, d_pis, k * 64, cudaMemcpyDeviceToHost, s));
   }
   for (int i = 0; i < 2; ++i) {
     cudaError_t e = cudaStreamSynchronize(a.stream[i]);
@@ -771,10 +958,12 @@ point_launch_fn get_point_launcher(int scheme, int gk, int prg, int mode) {
     if (scheme == FSSB200_SCHEME_DPF) return point_launcher_aes_dpf(gk, mode);
     if (scheme == FSSB200_SCHEME_DCF) return point_launcher_aes_dcf(gk, mode);
     if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_aes_ht(gk, mode);
+    if (scheme == FSSB200_SCHEME_VDPF) return point_launcher_aes_vdpf(gk, mode);
   } else {
     if (scheme == FSSB200_SCHEME_DPF) return point_launcher_chacha_dpf(gk, mode);
     if (scheme == FSSB200_SCHEME_DCF) return point_launcher_chacha_dcf(gk, mode);
     if (scheme == FSSB200_SCHEME_HALFTREE) return point_launcher_chacha_ht(gk, mode);
+    if (scheme == FSSB200_SCHEME_VDPF) return point_launcher_chacha_vdpf(gk, mode);
   }
   return nullptr;
 }
@@ -783,10 +972,12 @@ gen_launch_fn get_gen_launcher(int scheme, int gk, int prg) {
     if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_aes_dpf(gk);
     if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_aes_dcf(gk);
     if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_aes_ht(gk);
+    if (scheme == FSSB200_SCHEME_VDPF) return gen_launcher_aes_vdpf(gk);
   } else {
     if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_chacha_dpf(gk);
     if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_chacha_dcf(gk);
     if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_chacha_ht(gk);
+    if (scheme == FSSB200_SCHEME_VDPF) return gen_launcher_chacha_vdpf(gk);
   }
   return nullptr;
 }
@@ -796,11 +987,13 @@ evalall_launch_fn get_evalall_launcher(int mode, int gk, int prg) {
     if (mode == 1) return evalall_launcher_aes_ht(gk);
     if (mode == 2) return evalall_launcher_aes_grotto(gk);
     if (mode == 3) return evalall_launcher_aes_dcf(gk);
+    if (mode == 4) return evalall_launcher_aes_vdpf(gk);
   } else {
     if (mode == 0) return evalall_launcher_chacha_dpf(gk);
     if (mode == 1) return evalall_launcher_chacha_ht(gk);
     if (mode == 2) return evalall_launcher_chacha_grotto(gk);
     if (mode == 3) return evalall_launcher_chacha_dcf(gk);
+    if (mode == 4) return evalall_launcher_chacha_vdpf(gk);
   }
   return nullptr;
 }

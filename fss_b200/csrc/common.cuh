@@ -55,6 +55,7 @@ struct PrgKeys {
   uint32_t rkd[2][44];  // rk[2p] ^ rk[2p+1]: per-thread key selection is rk[2p] ^ (mask & rkd[p])
   uint32_t nonce[2];    // ChaCha nonce words (prg/chacha.cuh:108-110)
   uint32_t hash_key[4]; // HalfTreeDpf::hash_key (half_tree_dpf.cuh:44)
+  uint32_t hash_iv[2][8]; // VDPF: IVs of the XorHash (0) / Hash (1) Blake3 plugins (hash/blake3.cuh:131)
 };
 
 struct GroupMod {
@@ -93,6 +94,8 @@ struct PointArgs {
   int in_bytes;
   int party;
   uint32_t vmask;         // value mask for <= 32-bit groups
+  const blk *cs;          // VDPF: [nkeys][4] correction seeds (vdpf.cuh:153-157)
+  blk *pis;               // VDPF: [nkeys][4] corrected per-point hashes out
   // CUtensorMap of the key-major Cw array as a 2-D byte tensor [nkeys][ncw*32], box 32 keys x 64 B,
   // SWIZZLE_64B (point modes 4 / 5: correction words fetched by the TMA unit); opaque here
   alignas(64) uint8_t tmap[128];
@@ -103,7 +106,9 @@ struct GenArgs {
   const uint8_t *alphas;  // In[nkeys]
   const blk *betas;       // [nkeys] or nullptr
   uint8_t *cws;           // key-major out
-  blk *ocws;              // [nkeys] out (Half-Tree)
+  blk *ocws;              // [nkeys] out (Half-Tree, VDPF)
+  blk *cs;                // VDPF: [nkeys][4] out
+  int32_t *status;        // VDPF: [nkeys] out, Gen's return value (vdpf.cuh:160)
   uint64_t nkeys;
   int in_bits;
   int in_bytes;

@@ -25,11 +25,12 @@ inline bool grp_kind_instantiated(int gk) {
       gk == kGrpU64Mod || gk == kGrpU128Mod;
 }
 
-// scheme in {DPF, DCF, HALFTREE}; returns nullptr when not instantiated.
+// scheme in {DPF, DCF, HALFTREE, VDPF}; returns nullptr when not instantiated.
 // mode: see PointMode in kernels.cuh (0/1 staged key-major, 2 level-major, 3 direct key-major)
 point_launch_fn get_point_launcher(int scheme, int gk, int prg, int mode);
 gen_launch_fn get_gen_launcher(int scheme, int gk, int prg);
-// mode 0 = DPF leaves, 1 = Half-Tree leaves, 2 = Grotto leaf bits (gk ignored), 3 = DCF leaves
+// mode 0 = DPF leaves, 1 = Half-Tree leaves, 2 = Grotto leaf bits (gk ignored), 3 = DCF leaves,
+// 4 = VDPF packed leaves (gk ignored)
 evalall_launch_fn get_evalall_launcher(int mode, int gk, int prg);
 prg_launch_fn get_prg_launcher(int prg, int mul);
 
@@ -37,12 +38,14 @@ prg_launch_fn get_prg_launcher(int prg, int mul);
   point_launch_fn point_launcher_##PRGNAME##_##SCHNAME(int gk, int mode);
 #define FSS_DECL_GEN(PRGNAME, SCHNAME) gen_launch_fn gen_launcher_##PRGNAME##_##SCHNAME(int gk);
 #define FSS_DECL_EVALALL(PRGNAME, MODENAME) evalall_launch_fn evalall_launcher_##PRGNAME##_##MODENAME(int gk);
-FSS_DECL_POINT(aes, dpf) FSS_DECL_POINT(aes, dcf) FSS_DECL_POINT(aes, ht)
-FSS_DECL_POINT(chacha, dpf) FSS_DECL_POINT(chacha, dcf) FSS_DECL_POINT(chacha, ht)
-FSS_DECL_GEN(aes, dpf) FSS_DECL_GEN(aes, dcf) FSS_DECL_GEN(aes, ht)
-FSS_DECL_GEN(chacha, dpf) FSS_DECL_GEN(chacha, dcf) FSS_DECL_GEN(chacha, ht)
+FSS_DECL_POINT(aes, dpf) FSS_DECL_POINT(aes, dcf) FSS_DECL_POINT(aes, ht) FSS_DECL_POINT(aes, vdpf)
+FSS_DECL_POINT(chacha, dpf) FSS_DECL_POINT(chacha, dcf) FSS_DECL_POINT(chacha, ht) FSS_DECL_POINT(chacha, vdpf)
+FSS_DECL_GEN(aes, dpf) FSS_DECL_GEN(aes, dcf) FSS_DECL_GEN(aes, ht) FSS_DECL_GEN(aes, vdpf)
+FSS_DECL_GEN(chacha, dpf) FSS_DECL_GEN(chacha, dcf) FSS_DECL_GEN(chacha, ht) FSS_DECL_GEN(chacha, vdpf)
 FSS_DECL_EVALALL(aes, dpf) FSS_DECL_EVALALL(aes, ht) FSS_DECL_EVALALL(aes, grotto) FSS_DECL_EVALALL(aes, dcf)
+FSS_DECL_EVALALL(aes, vdpf)
 FSS_DECL_EVALALL(chacha, dpf) FSS_DECL_EVALALL(chacha, ht) FSS_DECL_EVALALL(chacha, grotto) FSS_DECL_EVALALL(chacha, dcf)
+FSS_DECL_EVALALL(chacha, vdpf)
 prg_launch_fn prg_launcher_aes(int mul);
 prg_launch_fn prg_launcher_chacha(int mul);
 

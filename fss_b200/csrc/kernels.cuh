@@ -258,8 +258,18 @@ struct PointMode {
 
 template <int SCHEME, int G, int PRG, class Cw>
 FSS_D blk point_eval_one(const KParams &P, const typename Prg<PRG>::ctx_t &pc, const PointArgs &A, blk s0,
-    const InVal &x, const Cw &cw, uint64_t k) {
+    const InVal &x, const Cw &cw, uint64_t k, bool valid) {
   const int n = A.in_bits;
+  if (SCHEME == FSSB200_SCHEME_VDPF) {
+    blk pi[4];
+    const blk y = vdpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k),
+        A.cs + 4 * k, pi);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st_blk(A.pis + 4 * k + j, pi[j]);
+    }
+    return y;
+  }
   if (SCHEME == FSSB200_SCHEME_DPF) return dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
   if (SCHEME == FSSB200_SCHEME_DCF) return dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
   return ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
@@ -272,7 +282,7 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
   SmemPlan sp = smem_plan<PRG>();
   const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
   const int n = A.in_bits;
-  const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE) ? n : n + 1;
+  const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE || SCHEME == FSSB200_SCHEME_VDPF) ? n : n + 1;
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   uint32_t slab = 0, mbar = 0;
   if (PM::kStaged) {
@@ -310,7 +320,7 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       const uint64_t left = A.nkeys - tile * 32;
       cw.nvalid = left < 32 ? int(left) : 32;
       cw.lane = lane;
-      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
       __syncwarp();
     } else if (PM::kTma) {
       CwTile cw;
@@ -324,13 +334,13 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       cw.next_row0 = tile + tile_stride < ntiles ? int((tile + tile_stride) * 32) : -1;
       cw.nchunks = (ncw + 1) >> 1;
       cw.seq = &tma_seq;
-      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
     } else if (MODE == 2) {
       const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, kk};
-      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
     } else {
       const CwKeyMajor cw{A.cws + kk * uint64_t(ncw) * 32u};
-      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk);
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
     }
     if (valid) st_blk(A.ys + k, y);
   }
@@ -343,14 +353,16 @@ gen_kernel(const __grid_constant__ KParams P, const __grid_constant__ GenArgs A)
   SmemPlan sp = smem_plan<PRG>();
   const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
   const int n = A.in_bits;
-  const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE) ? n : n + 1;
+  const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE || SCHEME == FSSB200_SCHEME_VDPF) ? n : n + 1;
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < A.nkeys; k += stride) {
     const blk s0 = ld_blk(A.s0s + 2 * k), s1 = ld_blk(A.s0s + 2 * k + 1);
     const InVal a = load_in(A.alphas + k * uint64_t(A.in_bytes), A.in_bytes);
     const blk beta = A.betas ? ld_blk(A.betas + k) : zero_blk();
     uint8_t *cws = A.cws + k * uint64_t(ncw) * 32u;
-    if (SCHEME == FSSB200_SCHEME_DPF) {
+    if (SCHEME == FSSB200_SCHEME_VDPF) {
+      A.status[k] = vdpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws, A.cs + 4 * k, A.ocws + k);
+    } else if (SCHEME == FSSB200_SCHEME_DPF) {
       dpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws);
     } else if (SCHEME == FSSB200_SCHEME_DCF) {
       dcf_gen_body<G, PRG>(P.keys, P.ga, pc, n, A.pred, s0, s1, a, beta, cws);
@@ -386,7 +398,9 @@ prg_kernel(const __grid_constant__ KParams P, const blk *seeds, blk *out, uint64
 //            accesses), ONE copy of the node-expansion code; the bottom step turns a node into two
 //            adjacent leaves and writes them with a single 256-bit store.
 // Every node is expanded exactly once (2 PRG blocks per DPF node, 1 per Half-Tree node).
-// MODE: 0 = DPF leaves (16 B), 1 = Half-Tree leaves (16 B), 2 = Grotto leaf control bits (1 B).
+// MODE: 0 = DPF leaves (16 B), 1 = Half-Tree leaves (16 B), 2 = Grotto leaf control bits (1 B),
+//       4 = VDPF: packed (s | t) leaves, n correction words and no output CW (vdpf.cuh:345-401); the leaf
+//           conversion and the proof chain run in vdpf_finish_kernel.
 template <int MODE, int G, int PRG>
 __global__ void __launch_bounds__(kEvalAllThreads, 1)
 evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAllArgs A) {
@@ -395,7 +409,7 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
   const int n = A.in_bits;
   const int tid = threadIdx.x;
   const bool half = (MODE == 1);
-  const int ncw = half ? n : n + 1;
+  const int ncw = (half || MODE == 4) ? n : n + 1;
   const int dfs = A.dfs_bits, bt = A.breadth_bits;
   const int du = n - A.unit_bits;
   // scratch: per-level correction words {cwl, cwr}, two breadth buffers, the DFS stack
@@ -477,6 +491,8 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
               const blk ocw = lds_blk(s_cw + 32u * n);
               stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, dpf_leaf<G>(P.ga, uint32_t(A.party), l, ocw),
                   dpf_leaf<G>(P.ga, uint32_t(A.party), r, ocw));
+            } else if (MODE == 4) {
+              stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, l, r);
             } else {
               // Grotto: leaf control bits, one byte per leaf (grotto_dcf.cuh:190-194)
               uint8_t *o = static_cast<uint8_t *>(A.ys) + out0 + 2 * done;  // any alignment (parity trees)

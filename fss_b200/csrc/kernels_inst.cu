@@ -3,7 +3,7 @@
 // kernels_inst.cu -- explicit kernel instantiations + launchers.  Compiled once per
 //   -DFSS_INST_KIND={1 point, 2 gen, 3 evalall, 4 prg}
 //   -DFSS_INST_PRG={0 aes, 1 chacha}
-//   -DFSS_INST_SCHEME={0 dpf, 1 dcf, 2 halftree, 3 grotto}   (ignored for kind 4)
+//   -DFSS_INST_SCHEME={0 dpf, 1 dcf, 2 halftree, 3 grotto, 4 vdpf}   (ignored for kind 4)
 // (see fss_b200/csrc/Makefile) so the ~160 instantiations build in parallel.
 #include "dispatch.h"
 
@@ -33,8 +33,10 @@ constexpr int kInstPrg = kPrgChaCha;
 #define SCHNAME dcf
 #elif FSS_INST_SCHEME == 2
 #define SCHNAME ht
-#else
+#elif FSS_INST_SCHEME == 3
 #define SCHNAME grotto
+#else
+#define SCHNAME vdpf
 #endif
 
 #define CAT3_(a, b, c) a##b##_##c
@@ -85,6 +87,11 @@ static cudaError_t evalall_launch_grotto(const KParams &P, const EvalAllArgs &A,
   return launch_kernel(evalall_kernel<2, kGrpBytes, kInstPrg>, c, P, A);
 }
 evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int) { return &evalall_launch_grotto; }
+#elif FSS_INST_SCHEME == 4
+static cudaError_t evalall_launch_vdpf(const KParams &P, const EvalAllArgs &A, const LaunchCfg &c) {
+  return launch_kernel(evalall_kernel<4, kGrpBytes, kInstPrg>, c, P, A);
+}
+evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int) { return &evalall_launch_vdpf; }
 #elif FSS_INST_SCHEME == 1
 template <int G>
 static cudaError_t evalall_launch_dcf(const KParams &P, const EvalAllArgs &A, const LaunchCfg &c) {

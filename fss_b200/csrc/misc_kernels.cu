@@ -29,7 +29,7 @@ __global__ void relayout_kernel(int scheme, int n, int ncw, const uint8_t *__res
     const uint32_t bits = __ballot_sync(0xffffffffu, flag);
     if (lane == 0 && scheme != FSSB200_SCHEME_DCF) extra[uint64_t(base >> 5) * nkeys + k] = bits;
   }
-  if (lane == 0 && scheme != FSSB200_SCHEME_HALFTREE && out_cw) {
+  if (lane == 0 && scheme != FSSB200_SCHEME_HALFTREE && scheme != FSSB200_SCHEME_VDPF && out_cw) {
     const uint4 s = __ldg(kc + 2 * n), v = __ldg(kc + 2 * n + 1);
     reinterpret_cast<uint4 *>(out_cw)[k] = scheme == FSSB200_SCHEME_DCF ? v : s;
   }

@@ -12,6 +12,7 @@
 // Everything here is FSS_HD: the same code runs per CUDA thread and, in tests/host_emul, per key
 // on the CPU.
 #pragma once
+#include "blake3.cuh"
 #include "group.cuh"
 #include "prg.cuh"
 
@@ -142,6 +143,114 @@ FSS_HD void dpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
   v = GR::cneg(ga, v, t1);                                      // :156-157
   st_blk(cws + 32 * n, GR::into(ga, v));
   st_blk(cws + 32 * n + 16, zero_blk());
+}
+
+// ---- VDPF (vdpf.cuh) -------------------------------------------------------------------------------------
+FSS_HD blk pack_in(const InVal &x) { return make_blk(x.w[0], x.w[1], x.w[2], x.w[3]); }  // util.cuh:46-63 Pack<In>
+
+// Output share and corrected per-point hash of a packed leaf (s | t) at input x: vdpf.cuh:224-242, :318-331.
+template <int G>
+FSS_HD blk vdpf_leaf(const PrgKeys &K, const GroupArgs &ga, uint32_t party, blk st, const InVal &x, blk ocw,
+    const blk *cs, blk pi[4]) {
+  typedef Grp<G> GR;
+  const uint32_t tm = 0u - lsb(st);
+  const blk s = clamp(st);
+  typename GR::V y = GR::from(ga, s);
+  y = GR::add_masked(ga, y, tm, GR::from(ga, ocw));
+  y = GR::cneg(ga, y, party);
+  b3_xor_hash(K.hash_iv[0], pack_in(x), s, pi);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pi[j] = xor_masked(pi[j], tm, ld_blk(cs + j));
+  return GR::into(ga, y);
+}
+
+// Vdpf::Eval, vdpf.cuh:191-243: the DPF walk over n correction words (no entry n), then the leaf above.
+template <int G, int PRG, class Cw>
+FSS_HD blk vdpf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
+    uint32_t party, blk s0, const InVal &x, const Cw &cw, blk ocw, const blk *cs, blk pi[4]) {
+  blk st = clamp(s0);
+  st.w |= party;
+  cw.begin_level(0);
+  blk cs_cw = cw.s(0);
+  uint32_t cf = cw.flag(0);
+  cw.done_level(0);
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    blk cs_next = cs_cw;
+    uint32_t cf_next = 0;
+    if (i + 1 < n) {
+      cw.begin_level(i + 1);
+      cs_next = cw.s(i + 1);
+      cf_next = cw.flag(i + 1);
+      cw.done_level(i + 1);
+    }
+    const uint32_t xb = in_bit(x, n - 1 - i);
+    const uint32_t tm = 0u - lsb(st);
+    blk c[1];
+    Prg<PRG>::template gen_child<1>(K, pc, clamp(st), xb, c);
+    blk cwp = cs_cw;
+    cwp.w = (cs_cw.w & ~1u) | (xb ? cf : (cs_cw.w & 1u));
+    st = xor_masked(c[0], tm, cwp);
+    cs_cw = cs_next;
+    cf = cf_next;
+  }
+  return vdpf_leaf<G>(K, ga, party, st, x, ocw, cs, pi);
+}
+
+// Vdpf::Gen, vdpf.cuh:97-177.  Returns Gen's status (1: t0 == t1, ocw not written).
+template <int G, int PRG>
+FSS_HD int vdpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n, blk s0,
+    blk s1, const InVal &a, blk beta, uint8_t *cws, blk *cs, blk *ocw) {
+  typedef Grp<G> GR;
+  s0 = clamp(s0);
+  s1 = clamp(s1);
+  uint32_t t0 = 0, t1 = 1;
+  beta = clamp(beta);
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {   // the walk of Dpf::Gen (dpf_gen_body)
+    blk g0[2], g1[2];
+    Prg<PRG>::template gen<2>(K, pc, s0, g0);
+    Prg<PRG>::template gen<2>(K, pc, s1, g1);
+    const uint32_t ab = in_bit(a, n - 1 - i);
+    const uint32_t am = 0u - ab;
+    const blk lose0 = xor_masked(g0[1], am, g0[0] ^ g0[1]);
+    const blk lose1 = xor_masked(g1[1], am, g1[0] ^ g1[1]);
+    const blk keep0 = xor_masked(g0[0], am, g0[0] ^ g0[1]);
+    const blk keep1 = xor_masked(g1[0], am, g1[0] ^ g1[1]);
+    blk s_cw = clamp(lose0 ^ lose1);
+    const uint32_t tl_cw = (lsb(g0[0]) ^ lsb(g1[0]) ^ ab ^ 1u) & 1u;
+    const uint32_t tr_cw = (lsb(g0[1]) ^ lsb(g1[1]) ^ ab) & 1u;
+    const uint32_t tk_cw = ab ? tr_cw : tl_cw;
+    const blk ns0 = xor_masked(clamp(keep0), 0u - t0, s_cw);
+    const blk ns1 = xor_masked(clamp(keep1), 0u - t1, s_cw);
+    t0 = lsb(keep0) ^ (t0 & tk_cw);
+    t1 = lsb(keep1) ^ (t1 & tk_cw);
+    s0 = ns0;
+    s1 = ns1;
+    s_cw.w |= tl_cw;
+    st_blk(cws + 32 * i, s_cw);
+    st_blk(cws + 32 * i + 16, make_blk(tr_cw, 0, 0, 0));       // vdpf.cuh:147-149
+  }
+  blk p0[4], p1[4];                                             // :153-157
+  b3_xor_hash(K.hash_iv[0], pack_in(a), s0, p0);
+  b3_xor_hash(K.hash_iv[0], pack_in(a), s1, p1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_blk(cs + j, p0[j] ^ p1[j]);
+  if (t0 == t1) return 1;                                       // :160
+  typename GR::V v = GR::add(ga, GR::add(ga, GR::from(ga, beta), GR::neg(ga, GR::from(ga, s0))), GR::from(ga, s1));
+  v = GR::cneg(ga, v, t1);
+  st_blk(ocw, GR::into(ga, v));
+  return 0;
+}
+
+// One step of Vdpf::Prove (vdpf.cuh:257-263) / the EvalAll accumulation (:336-340).
+FSS_HD void vdpf_accumulate(const PrgKeys &K, blk pi[4], const blk pt[4]) {
+  blk in[4], h[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) in[j] = pi[j] ^ pt[j];
+  b3_hash(K.hash_iv[1], in, h);
+  pi[0] = pi[0] ^ h[0];
+  pi[1] = pi[1] ^ h[1];
 }
 
 // ---- DCF ------------------------------------------------------------------------------------------------

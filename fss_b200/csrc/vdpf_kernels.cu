@@ -1,0 +1,117 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// vdpf_kernels.cu -- VDPF helper kernels (vdpf.cuh): the point / gen walks live in kernels.cuh
+// (point_kernel / gen_kernel with SCHEME = VDPF); here are the pieces around them.
+#include "vdpf_kernels.cuh"
+
+namespace fssb200 {
+
+// ---- VDPF helpers -------------------------------------------------------------------------------------------------
+// Hash known-answer kernel: which = 0 XorHash ((a, b) -> 64 B), 1 Hash (64 B -> 32 B).
+__global__ void __launch_bounds__(256) hash_kernel(const __grid_constant__ KParams P, int which, const blk *msgs,
+    blk *out, uint64_t n) {
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (which == 0) {
+    blk o[4];
+    b3_xor_hash(P.keys.hash_iv[0], ld_blk(msgs + 2 * i), ld_blk(msgs + 2 * i + 1), o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_blk(out + 4 * i + j, o[j]);
+  } else {
+    blk m[4], o[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = ld_blk(msgs + 4 * i + j);
+    b3_hash(P.keys.hash_iv[1], m, o);
+    st_blk(out + 2 * i, o[0]);
+    st_blk(out + 2 * i + 1, o[1]);
+  }
+}
+
+// Vdpf::Prove (vdpf.cuh:254-264) for a batch: thread k walks key k's m hashes in order.
+__global__ void __launch_bounds__(128) vdpf_prove_kernel(const __grid_constant__ KParams P, const blk *pts,
+    const blk *cs, uint64_t m, blk *pis, uint64_t nkeys) {
+  const uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= nkeys) return;
+  blk pi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pi[j] = ld_blk(cs + 4 * k + j);
+  for (uint64_t i = 0; i < m; ++i) {
+    blk pt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pt[j] = ld_blk(pts + 4 * (k * m + i) + j);
+    vdpf_accumulate(P.keys, pi, pt);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_blk(pis + 4 * k + j, pi[j]);
+}
+
+// Second half of Vdpf::EvalAll (vdpf.cuh:313-341): ys holds the packed (s | t) leaves written by
+// evalall_kernel<4>.  One warp per key: 32 leaves at a time the lanes convert their leaf to the output share
+// and compute its corrected hash in parallel (two compressions); the accumulation H'(pi ^ pi_tilde) is
+// sequential in x by definition, so the warp then replays the 32 hashes in order through shuffles, every lane
+// carrying the same proof.
+template <int G>
+__global__ void __launch_bounds__(128) vdpf_finish_kernel(const __grid_constant__ KParams P, int party, int in_bits,
+    const blk *cs, const blk *ocws, blk *ys, blk *pis, uint64_t nkeys) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t k = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (k >= nkeys) return;
+  const uint64_t N = uint64_t(1) << in_bits;
+  const blk ocw = ld_blk(ocws + k);
+  blk pi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pi[j] = ld_blk(cs + 4 * k + j);
+  for (uint64_t base = 0; base < N; base += 32) {
+    const uint64_t x = base + lane;
+    const bool have = x < N;
+    blk pt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pt[j] = zero_blk();
+    if (have) {
+      InVal xv;
+      xv.w[0] = uint32_t(x); xv.w[1] = uint32_t(x >> 32); xv.w[2] = 0; xv.w[3] = 0;
+      const blk y = vdpf_leaf<G>(P.keys, P.ga, uint32_t(party), ys[k * N + x], xv, ocw, cs + 4 * k, pt);
+      st_blk(ys + k * N + x, y);
+    }
+    const uint32_t cnt = N - base < 32 ? uint32_t(N - base) : 32u;
+    for (uint32_t src = 0; src < cnt; ++src) {
+      blk q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        q[j] = make_blk(__shfl_sync(0xffffffffu, pt[j].x, src), __shfl_sync(0xffffffffu, pt[j].y, src),
+            __shfl_sync(0xffffffffu, pt[j].z, src), __shfl_sync(0xffffffffu, pt[j].w, src));
+      vdpf_accumulate(P.keys, pi, q);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_blk(pis + 4 * k + j, pi[j]);
+  }
+}
+
+cudaError_t launch_hash(const KParams &P, int which, const blk *msgs, blk *out, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  hash_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(P, which, msgs, out, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_vdpf_prove(const KParams &P, const blk *pts, const blk *cs, uint64_t m, blk *pis, uint64_t nkeys,
+    cudaStream_t stream) {
+  if (nkeys == 0) return cudaSuccess;
+  vdpf_prove_kernel<<<unsigned((nkeys + 127) / 128), 128, 0, stream>>>(P, pts, cs, m, pis, nkeys);
+  return cudaGetLastError();
+}
+cudaError_t launch_vdpf_finish(const KParams &P, int gk, int party, int in_bits, const blk *cs, const blk *ocws, blk *ys,
+    blk *pis, uint64_t nkeys, cudaStream_t stream) {
+  if (nkeys == 0) return cudaSuccess;
+  const unsigned grid = unsigned((nkeys * 32 + 127) / 128);
+  switch (gk) {
+#define X(GK) \
+  case GK: vdpf_finish_kernel<GK><<<grid, 128, 0, stream>>>(P, party, in_bits, cs, ocws, ys, pis, nkeys); break;
+    X(kGrpBytes) X(kGrpU32) X(kGrpU64) X(kGrpU127) X(kGrpU32Mod) X(kGrpU64Mod) X(kGrpU128Mod)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fssb200

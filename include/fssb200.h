@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FSSB200_VERSION 100 /* 0.1.0 */
+#define FSSB200_VERSION 101 /* 0.1.1: fssb200_params grew hash_iv (VDPF) */
 
 /* ---- enums --------------------------------------------------------------- */
 
@@ -54,7 +54,9 @@ enum {
   FSSB200_SCHEME_DPF = 0,      /* fss::Dpf          dpf.cuh:61-304            */
   FSSB200_SCHEME_DCF = 1,      /* fss::Dcf          dcf.cuh:74-386            */
   FSSB200_SCHEME_HALFTREE = 2, /* fss::HalfTreeDpf  half_tree_dpf.cuh:39-355  */
-  FSSB200_SCHEME_GROTTO = 3    /* fss::GrottoDcf    grotto_dcf.cuh:45-239     */
+  FSSB200_SCHEME_GROTTO = 3,   /* fss::GrottoDcf    grotto_dcf.cuh:45-239     */
+  FSSB200_SCHEME_VDPF = 4      /* fss::Vdpf         vdpf.cuh:63-403 (XorHash = Hash = fss::hash::Blake3);
+                                  only the fssb200_vdpf_* entry points apply          */
 };
 
 /* Output group (the `Group` template parameter, group.cuh:39-45). */
@@ -104,6 +106,8 @@ enum {
  *   hash_key  : HalfTreeDpf::hash_key         (half_tree_dpf.cuh:44)
  *   pred      : DcfPred                       (dcf.cuh:58-61)
  *   device    : CUDA device ordinal the context's kernels run on.
+ *   hash_iv   : VDPF only: the 32-byte IVs of the two fss::hash::Blake3 plugins
+ *               (hash/blake3.cuh:131): [0] = XorHash `H` (vdpf.cuh:55), [1] = Hash `H'` (:56).
  */
 typedef struct fssb200_params {
   int32_t scheme;
@@ -118,6 +122,7 @@ typedef struct fssb200_params {
   uint8_t hash_key[16];
   int32_t device;
   int32_t reserved;
+  uint8_t hash_iv[2][32];
 } fssb200_params;
 
 typedef struct fssb200_ctx fssb200_ctx;
@@ -133,7 +138,7 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out);
 /* Replaces `Aes128Mmo::FreeCtxs` (prg/aes128_mmo.cuh:66-70). */
 void fssb200_ctx_destroy(fssb200_ctx *ctx);
 int fssb200_ctx_params(const fssb200_ctx *ctx, fssb200_params *out);
-/* Number of 32-byte Cw entries per key: n+1 (DPF, DCF, Grotto), n (Half-Tree). */
+/* Number of 32-byte Cw entries per key: n+1 (DPF, DCF, Grotto), n (Half-Tree, VDPF). */
 int fssb200_ctx_ncw(const fssb200_ctx *ctx);
 
 /* ---- batched key generation (device pointers) ------------------------------
@@ -209,6 +214,46 @@ int fssb200_grotto_preprocess(const fssb200_ctx *ctx, int party, const void *see
 int fssb200_grotto_eval(const fssb200_ctx *ctx, const void *pt, const void *xs, void *ys,
                         size_t nkeys, void *stream);
 
+/* ---- VDPF (verifiable DPF) -----------------------------
+ * Context scheme FSSB200_SCHEME_VDPF.  Key of party i = cws (n entries of Dpf-style
+ * 32-byte Cw, vdpf.cuh:77-80) + cs (4 x int4 correction seed) + ocw + s0s[i].
+ *   fssb200_vdpf_gen      replaces `Vdpf::Gen` vdpf.cuh:97-177 (and VdpfGenKernel,
+ *                         src/bench_gpu.cu:173-186).  status[k] = Gen's return value:
+ *                         1 = t0 == t1 at the end, the caller resamples the seeds (:169);
+ *                         cws / cs of such a key are still written, ocw is not.
+ *   fssb200_vdpf_eval     replaces `Vdpf::Eval` vdpf.cuh:191-243 and
+ *                         `fss::gpu::VdpfEvalPointGpu` point_eval_gpu.cuh:514-527:
+ *                         ys[k] = y share, pis[k] = corrected per-point hash (4 x int4).
+ *   fssb200_vdpf_prove    replaces `Vdpf::Prove` vdpf.cuh:254-264 for a batch of keys:
+ *                         key k accumulates its m hashes pi_tildes[k][0..m) in order.
+ *   fssb200_vdpf_eval_all replaces `Vdpf::EvalAll` vdpf.cuh:294-342 (the reference has no
+ *                         GPU version): ys[k][x] for the whole domain and the accumulated
+ *                         proof pis[k].  The proof chain is sequential in x by definition
+ *                         (:336-340), one warp walks it per key.
+ * Verify (vdpf.cuh:271-276) is a 64-byte comparison of two proofs; no entry point.
+ *   cws : Cw[nkeys][n]      cs : int4[nkeys][4]      ocws : int4[nkeys]
+ *   pis / pi_tildes : int4[nkeys][4] / int4[nkeys][m][4]      status : int32[nkeys]
+ */
+int fssb200_vdpf_gen(const fssb200_ctx *ctx, const void *s0s, const void *alphas, const void *betas,
+                     void *cws, void *cs, void *ocws, void *status, size_t nkeys, void *stream);
+int fssb200_vdpf_eval(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                      const void *cs, const void *ocws, const void *xs, void *ys, void *pis,
+                      size_t nkeys, void *stream);
+/* fssb200_vdpf_eval on the level-major arrays of fssb200_relayout (cw_s[n][nkeys], extra); replaces
+ * `fss::gpu::VdpfRelayoutGpu` + `VdpfEvalPointGpu` point_eval_gpu.cuh:390-397,514-527. */
+int fssb200_vdpf_eval_levelmajor(const fssb200_ctx *ctx, int party, const void *seeds, const void *cw_s,
+                                 const void *extra, const void *cs, const void *ocws, const void *xs,
+                                 void *ys, void *pis, size_t nkeys, void *stream);
+int fssb200_vdpf_prove(const fssb200_ctx *ctx, const void *pi_tildes, const void *cs, size_t m,
+                       void *pis, size_t nkeys, void *stream);
+int fssb200_vdpf_eval_all(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                          const void *cs, const void *ocws, void *ys, void *pis, size_t nkeys,
+                          void *stream);
+/* Hash known-answer hook (hash/blake3.cuh:143-171): which = 0: XorHash, msgs = (a, b) pairs of
+ * int4 (32 B) -> 64 B each; which = 1: Hash, msgs = 64 B -> 32 B each.  Device pointers. */
+int fssb200_hash(const fssb200_ctx *ctx, int which, const void *msgs, void *out, size_t n,
+                 void *stream);
+
 /* ---- level-major layout (optional pre-pass) ----------------------------------
  * Replaces `fss::gpu::{Dpf,Dcf,HalfTreeDpf}RelayoutGpu` point_eval_gpu.cuh:324-381:
  * key-major Cw[nkeys][ncw] -> the compact level-major layout the reference's point
@@ -248,6 +293,12 @@ int fssb200_gen_host(fssb200_ctx *ctx, const void *s0s, const void *alphas, cons
  * key format: 16 B + 1 bit per level instead of the 32-byte Cw): chunks of
  * keys are gathered from the [level][key] arrays with strided copies.  Same NULL rules as
  * fssb200_eval_levelmajor. */
+/* VDPF with host arrays (same chunked pipeline). */
+int fssb200_vdpf_gen_host(fssb200_ctx *ctx, const void *s0s, const void *alphas, const void *betas,
+                          void *cws, void *cs, void *ocws, void *status, size_t nkeys);
+int fssb200_vdpf_eval_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                           const void *cs, const void *ocws, const void *xs, void *ys, void *pis,
+                           size_t nkeys);
 int fssb200_eval_levelmajor_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cw_s,
                                  const void *cw_v, const void *extra, const void *out_cw,
                                  const void *ocws, const void *xs, void *ys, size_t nkeys);

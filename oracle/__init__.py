@@ -24,7 +24,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SCHEME = {"dpf": 0, "dcf": 1, "halftree": 2, "grotto": 3}
+SCHEME = {"dpf": 0, "dcf": 1, "halftree": 2, "grotto": 3, "vdpf": 4}
 GROUP = {"bytes": 0, "u8": 1, "u16": 2, "u32": 3, "u64": 4, "u128": 5}
 PRG = {"aes128_mmo": 0, "chacha": 1, "aes128_mmo_raw": 2}
 PRED = {"lt": 0, "gt": 1}
@@ -35,6 +35,12 @@ AES_KEYS = bytes(range(1, 17)) + bytes(range(16, 0, -1)) + bytes(
 CHACHA_NONCE = np.array([0x12345678, 0x9ABCDEF0], dtype=np.uint32).tobytes()
 HASH_KEY_SAMPLE = np.array([0x12345678, 0x9ABCDEF0, 0x13572468, 0x2468ACE0], dtype=np.uint32).tobytes()
 HASH_KEY_BENCH = np.array([0x12345678, 0x9ABCDEF0, 0x0FEDCBA9, 0x87654321], dtype=np.uint32).tobytes()
+# VDPF: IVs of the XorHash / Hash Blake3 plugins -- the constants of the reference's tests
+# (src/vdpf_test.cu:33-42, samples/vdpf_cpu.cu) for XorHash, a second pattern for Hash
+HASH_IVS = (np.array([0x11111111, 0x22222222, 0x33333333, 0x44444444, 0x55555555, 0x66666666, 0x77777777, 0x88888888],
+                     dtype=np.uint32).tobytes()
+            + np.array([0x99999999, 0xAAAAAAAA, 0xBBBBBBBB, 0xCCCCCCCC, 0xDDDDDDDD, 0xEEEEEEEE, 0xFFFFFFFF, 0x01234567],
+                       dtype=np.uint32).tobytes())
 
 
 class CParams(C.Structure):
@@ -42,7 +48,7 @@ class CParams(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("in_bits", C.c_int32), ("in_bytes", C.c_int32), ("group", C.c_int32),
                 ("mod_lo", C.c_uint64), ("mod_hi", C.c_uint64), ("prg", C.c_int32), ("pred", C.c_int32),
                 ("prg_key", C.c_uint8 * 64), ("hash_key", C.c_uint8 * 16), ("device", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("hash_iv", C.c_uint8 * 64)]
 
 
 class CRefParams(C.Structure):
@@ -70,6 +76,7 @@ class Params:
     prg_key: bytes = b""
     hash_key: bytes = HASH_KEY_SAMPLE
     in_bytes: int = 0
+    hash_iv: bytes = HASH_IVS
 
     def __post_init__(self):
         if not self.in_bytes:
@@ -81,11 +88,11 @@ class Params:
 
     @property
     def ncw(self) -> int:
-        return self.in_bits if self.scheme == "halftree" else self.in_bits + 1
+        return self.in_bits if self.scheme in ("halftree", "vdpf") else self.in_bits + 1
 
     @property
     def mul(self) -> int:
-        return {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2}[self.scheme]
+        return {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2, "vdpf": 2}[self.scheme]
 
     def c(self) -> CParams:
         p = CParams()
@@ -97,6 +104,7 @@ class Params:
             p.prg_key[i] = key[i]
         for i in range(16):
             p.hash_key[i] = self.hash_key[i]
+        C.memmove(p.hash_iv, bytes(self.hash_iv), 64)
         return p
 
 
@@ -228,6 +236,65 @@ class Orc(_Base):
         assert rc == 0, rc
         return cw_s, cw_v, extra, out_cw
 
+    # ---- VDPF (vdpf.cuh) ---------------------------------------------------------------------------------
+    def hash(self, p: Params, which: int, msgs) -> np.ndarray:
+        """which 0: XorHash over (a, b) pairs [K,2,4] -> [K,4,4]; 1: Hash over [K,4,4] -> [K,2,4]."""
+        msgs = _u32(msgs, (-1, 2, 4) if which == 0 else (-1, 4, 4))
+        out = np.zeros((len(msgs), 4 if which == 0 else 2, 4), dtype=np.uint32)
+        cp = p.c()
+        rc = self.lib.orc_hash(C.byref(cp), which, C.c_size_t(len(msgs)), _vp(msgs), _vp(out))
+        assert rc == 0, rc
+        return out
+
+    def vdpf_gen(self, p: Params, s0s, alphas, betas, threads: int = 1):
+        """-> cws[K,n,8], cs[K,4,4], ocws[K,4], status[K] (1 = resample the seeds; ocw not written)."""
+        s0s = _u32(s0s, (-1, 2, 4))
+        k = len(s0s)
+        al, be = pack_ints(alphas, p.in_bytes), _u32(betas, (k, 4))
+        cws, cs = np.zeros((k, p.ncw, 8), dtype=np.uint32), np.zeros((k, 4, 4), dtype=np.uint32)
+        ocws, status = np.zeros((k, 4), dtype=np.uint32), np.zeros(k, dtype=np.int32)
+        cp = p.c()
+        rc = self.lib.orc_vdpf_gen(C.byref(cp), C.c_size_t(k), _vp(s0s), _vp(al), _vp(be), _vp(cws), _vp(cs),
+                                   _vp(ocws), _vp(status), threads)
+        assert rc == 0, rc
+        return cws, cs, ocws, status
+
+    def vdpf_eval(self, p: Params, party: int, seeds, cws, cs, ocws, xs, threads: int = 1):
+        """-> ys[K,4], pi_tildes[K,4,4]."""
+        seeds = _u32(seeds, (-1, 4))
+        k = len(seeds)
+        cws, cs, ocws = _u32(cws, (k, p.ncw, 8)), _u32(cs, (k, 4, 4)), _u32(ocws, (k, 4))
+        xb = pack_ints(xs, p.in_bytes)
+        ys, pis = np.zeros((k, 4), dtype=np.uint32), np.zeros((k, 4, 4), dtype=np.uint32)
+        cp = p.c()
+        rc = self.lib.orc_vdpf_eval(C.byref(cp), party, C.c_size_t(k), _vp(seeds), _vp(cws), _vp(cs), _vp(ocws),
+                                    _vp(xb), _vp(ys), _vp(pis), threads)
+        assert rc == 0, rc
+        return ys, pis
+
+    def vdpf_prove(self, p: Params, pi_tildes, cs) -> np.ndarray:
+        """pi_tildes[K,m,4,4], cs[K,4,4] -> pi[K,4,4]."""
+        cs = _u32(cs, (-1, 4, 4))
+        k = len(cs)
+        pts = _u32(pi_tildes).reshape(k, -1, 4, 4)
+        pis = np.zeros((k, 4, 4), dtype=np.uint32)
+        cp = p.c()
+        rc = self.lib.orc_vdpf_prove(C.byref(cp), C.c_size_t(k), C.c_size_t(pts.shape[1]), _vp(pts), _vp(cs), _vp(pis))
+        assert rc == 0, rc
+        return pis
+
+    def vdpf_evalall(self, p: Params, party: int, seeds, cws, cs, ocws, threads: int = 1):
+        """-> ys[K,2^n,4], pi[K,4,4]."""
+        seeds = _u32(seeds, (-1, 4))
+        k = len(seeds)
+        cws, cs, ocws = _u32(cws, (k, p.ncw, 8)), _u32(cs, (k, 4, 4)), _u32(ocws, (k, 4))
+        ys, pis = np.zeros((k, 1 << p.in_bits, 4), dtype=np.uint32), np.zeros((k, 4, 4), dtype=np.uint32)
+        cp = p.c()
+        rc = self.lib.orc_vdpf_evalall(C.byref(cp), party, C.c_size_t(k), _vp(seeds), _vp(cws), _vp(cs), _vp(ocws),
+                                       _vp(ys), _vp(pis), threads)
+        assert rc == 0, rc
+        return ys, pis
+
     def group_add(self, p: Params, a, b) -> np.ndarray:
         a, b = _u32(a, (-1, 4)), _u32(b, (-1, 4))
         out = np.zeros_like(a)
@@ -349,6 +416,70 @@ class Ref(_Base):
         rc = self.lib.ref_grotto_lookup(C.byref(s), C.byref(rp), C.c_size_t(k), _vp(pt), _vp(xb), _vp(ys))
         assert rc == 0, f"reference instantiation missing for {p}"
         return ys
+
+
+    # ---- VDPF (oracle/ref_vdpf.cpp) -------------------------------------------------------------------------
+    @staticmethod
+    def _ivs(p: Params):
+        return (C.c_uint8 * 64).from_buffer_copy(bytes(p.hash_iv))
+
+    def vdpf_supported(self, p: Params) -> bool:
+        s = self._sel(p)
+        return bool(self.lib.ref_vdpf_supported(C.byref(s)))
+
+    def hash(self, p: Params, which: int, msgs) -> np.ndarray:
+        msgs = _u32(msgs, (-1, 2, 4) if which == 0 else (-1, 4, 4))
+        out = np.zeros((len(msgs), 4 if which == 0 else 2, 4), dtype=np.uint32)
+        iv = (C.c_uint8 * 32).from_buffer_copy(bytes(p.hash_iv)[32 * which:32 * which + 32])
+        rc = self.lib.ref_blake3(iv, which, C.c_size_t(len(msgs)), _vp(msgs), _vp(out))
+        assert rc == 0, rc
+        return out
+
+    def vdpf_gen(self, p: Params, s0s, alphas, betas, threads: int = 1):
+        s0s = _u32(s0s, (-1, 2, 4))
+        k = len(s0s)
+        al, be = pack_ints(alphas, p.in_bytes), _u32(betas, (k, 4))
+        cws, cs = np.zeros((k, p.ncw, 8), dtype=np.uint32), np.zeros((k, 4, 4), dtype=np.uint32)
+        ocws, status = np.zeros((k, 4), dtype=np.uint32), np.zeros(k, dtype=np.int32)
+        s, rp = self._sel(p), self._rp(p)
+        rc = self.lib.ref_vdpf_gen(C.byref(s), C.byref(rp), self._ivs(p), C.c_size_t(k), _vp(s0s), _vp(al), _vp(be),
+                                   _vp(cws), _vp(cs), _vp(ocws), _vp(status), threads)
+        assert rc == 0, f"reference VDPF instantiation missing for {p}"
+        return cws, cs, ocws, status
+
+    def vdpf_eval(self, p: Params, party: int, seeds, cws, cs, ocws, xs, threads: int = 1):
+        seeds = _u32(seeds, (-1, 4))
+        k = len(seeds)
+        cws, cs, ocws = _u32(cws, (k, p.ncw, 8)), _u32(cs, (k, 4, 4)), _u32(ocws, (k, 4))
+        xb = pack_ints(xs, p.in_bytes)
+        ys, pis = np.zeros((k, 4), dtype=np.uint32), np.zeros((k, 4, 4), dtype=np.uint32)
+        s, rp = self._sel(p), self._rp(p)
+        rc = self.lib.ref_vdpf_eval(C.byref(s), C.byref(rp), self._ivs(p), party, C.c_size_t(k), _vp(seeds), _vp(cws),
+                                    _vp(cs), _vp(ocws), _vp(xb), _vp(ys), _vp(pis), threads)
+        assert rc == 0, f"reference VDPF instantiation missing for {p}"
+        return ys, pis
+
+    def vdpf_prove(self, p: Params, pi_tildes, cs) -> np.ndarray:
+        cs = _u32(cs, (-1, 4, 4))
+        k = len(cs)
+        pts = _u32(pi_tildes).reshape(k, -1, 4, 4)
+        pis = np.zeros((k, 4, 4), dtype=np.uint32)
+        s, rp = self._sel(p), self._rp(p)
+        rc = self.lib.ref_vdpf_prove(C.byref(s), C.byref(rp), self._ivs(p), C.c_size_t(k), C.c_size_t(pts.shape[1]),
+                                     _vp(pts), _vp(cs), _vp(pis))
+        assert rc == 0, f"reference VDPF instantiation missing for {p}"
+        return pis
+
+    def vdpf_evalall(self, p: Params, party: int, seeds, cws, cs, ocws, threads: int = 1):
+        seeds = _u32(seeds, (-1, 4))
+        k = len(seeds)
+        cws, cs, ocws = _u32(cws, (k, p.ncw, 8)), _u32(cs, (k, 4, 4)), _u32(ocws, (k, 4))
+        ys, pis = np.zeros((k, 1 << p.in_bits, 4), dtype=np.uint32), np.zeros((k, 4, 4), dtype=np.uint32)
+        s, rp = self._sel(p), self._rp(p)
+        rc = self.lib.ref_vdpf_evalall(C.byref(s), C.byref(rp), self._ivs(p), party, C.c_size_t(k), _vp(seeds),
+                                       _vp(cws), _vp(cs), _vp(ocws), _vp(ys), _vp(pis), threads)
+        assert rc == 0, f"reference VDPF instantiation missing for {p}"
+        return ys, pis
 
 
 def synth_inputs(p: Params, nkeys: int, seed: int = 42, alpha_hit_every: int = 16):

@@ -117,7 +117,7 @@ static int ctx_init(octx *c, const fssb200_params *p) {
   sbox_init();
   memset(c, 0, sizeof(*c));
   c->p = *p;
-  if (p->scheme < 0 || p->scheme > 3) return FSSB200_EINVAL;
+  if (p->scheme < 0 || p->scheme > 4) return FSSB200_EINVAL;
   if (p->in_bytes != 1 && p->in_bytes != 2 && p->in_bytes != 4 && p->in_bytes != 8 && p->in_bytes != 16)
     return FSSB200_EINVAL;
   if (p->in_bits < 1 || p->in_bits > 8 * p->in_bytes) return FSSB200_EDOMAIN;
@@ -486,7 +486,9 @@ static void ht_tree(const walk *w, blk node, int i, uint64_t l, uint64_t r) {
 }
 
 /* ---- exported batch API -------------------------------------------------------------------------- */
-static int ncw_of(const fssb200_params *p) { return p->scheme == FSSB200_SCHEME_HALFTREE ? p->in_bits : p->in_bits + 1; }
+static int ncw_of(const fssb200_params *p) {
+  return (p->scheme == FSSB200_SCHEME_HALFTREE || p->scheme == FSSB200_SCHEME_VDPF) ? p->in_bits : p->in_bits + 1;
+}
 int orc_ncw(const fssb200_params *p) { return p ? ncw_of(p) : FSSB200_EINVAL; }
 
 int orc_prg_gen(const fssb200_params *p, int mul, size_t n, const void *seeds, void *out) {
@@ -673,6 +675,216 @@ int orc_group_add(const fssb200_params *p, size_t n, const void *a, const void *
     /* From() asserts a clamped input (bytes.cuh:33, uint.cuh:50) */
     blk x = ((const blk *)a)[i], y = ((const blk *)b)[i];
     ((blk *)out)[i] = g_into(&c, g_add(&c, g_from(&c, x), g_from(&c, y)));
+  }
+  return 0;
+}
+
+/* ---- BLAKE3 keyed compression: hash/blake3.cuh ------------------------------------------------- */
+static uint32_t rotr32(uint32_t v, int n) { return (v >> n) | (v << (32 - n)); }
+static void b3_g(uint32_t *v, int a, int b, int c, int d, uint32_t x, uint32_t y) { /* :33-42 */
+  v[a] = v[a] + v[b] + x; v[d] = rotr32(v[d] ^ v[a], 16);
+  v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 12);
+  v[a] = v[a] + v[b] + y; v[d] = rotr32(v[d] ^ v[a], 8);
+  v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 7);
+}
+/* h: 8 words (the plugin's IV), msg: 16 words, counter = 0; out: 16 words.  :99-124 */
+static void b3_compress(const uint32_t h[8], const uint32_t msg[16], uint32_t block_len, uint32_t flags,
+    uint32_t out[16]) {
+  static const uint32_t iv0[4] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au};  /* :75-80 */
+  static const int perm[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};   /* :53 */
+  uint32_t v[16], m[16], t[16];
+  for (int i = 0; i < 8; ++i) v[i] = h[i];
+  for (int i = 0; i < 4; ++i) v[8 + i] = iv0[i];
+  v[12] = 0; v[13] = 0; v[14] = block_len; v[15] = flags;                              /* :104 */
+  memcpy(m, msg, sizeof(m));
+  for (int r = 0; r < 7; ++r) {                                                       /* :109-114 */
+    b3_g(v, 0, 4, 8, 12, m[0], m[1]);   b3_g(v, 1, 5, 9, 13, m[2], m[3]);               /* :63-67 */
+    b3_g(v, 2, 6, 10, 14, m[4], m[5]);  b3_g(v, 3, 7, 11, 15, m[6], m[7]);
+    b3_g(v, 0, 5, 10, 15, m[8], m[9]);  b3_g(v, 1, 6, 11, 12, m[10], m[11]);            /* :68-72 */
+    b3_g(v, 2, 7, 8, 13, m[12], m[13]); b3_g(v, 3, 4, 9, 14, m[14], m[15]);
+    if (r < 6) { for (int i = 0; i < 16; ++i) t[i] = m[perm[i]]; memcpy(m, t, sizeof(m)); }
+  }
+  for (int i = 0; i < 8; ++i) { out[i] = v[i] ^ v[8 + i]; out[8 + i] = v[8 + i] ^ h[i]; } /* :117-121 */
+}
+#define B3_FLAGS (1u | 2u | 8u | 16u) /* CHUNK_START | CHUNK_END | ROOT | KEYED_HASH, :82-85,144 */
+/* Blake3::Hash(span<int4,4>) :143-147: 64 B -> first 32 B of the compression output */
+static void b3_hash(const uint8_t iv[32], const blk msg[4], blk out[2]) {
+  uint32_t h[8], o[16];
+  memcpy(h, iv, 32);
+  b3_compress(h, (const uint32_t *)msg, 64, B3_FLAGS, o);
+  memcpy(out, o, 32);
+}
+/* Blake3::Hash(tuple<int4,int4>) :158-170: two 32-byte-block compressions, a's lsb 0 / 1 */
+static void b3_xor_hash(const uint8_t iv[32], blk a, blk b, blk out[4]) {
+  uint32_t h[8], o[16];
+  blk padded[4];
+  memcpy(h, iv, 32);
+  padded[0] = set_lsb(a, 0); padded[1] = b; padded[2] = bzero(); padded[3] = bzero();
+  b3_compress(h, (const uint32_t *)padded, 32, B3_FLAGS, o);
+  memcpy(&out[0], o, 32);
+  padded[0] = set_lsb(a, 1);
+  b3_compress(h, (const uint32_t *)padded, 32, B3_FLAGS, o);
+  memcpy(&out[2], o, 32);
+}
+int orc_hash(const fssb200_params *p, int which, size_t n, const void *msgs, void *out) {
+  if (!p || !msgs || !out) return FSSB200_EINVAL;
+  for (size_t i = 0; i < n; ++i) {
+    if (which == 0) {
+      const blk *m = (const blk *)msgs + 2 * i;
+      b3_xor_hash(p->hash_iv[0], m[0], m[1], (blk *)out + 4 * i);
+    } else {
+      b3_hash(p->hash_iv[1], (const blk *)msgs + 4 * i, (blk *)out + 2 * i);
+    }
+  }
+  return 0;
+}
+
+/* ---- VDPF: vdpf.cuh -------------------------------------------------------------------------------- */
+static blk pack_in(const octx *c, u128 x) { /* util.cuh:46-63 Pack<In> */
+  blk b = bzero();
+  const int nb = c->p.in_bytes;
+  b.w[0] = (uint32_t)x;
+  if (nb > 4) b.w[1] = (uint32_t)(x >> 32);
+  if (nb > 8) { b.w[2] = (uint32_t)(x >> 64); b.w[3] = (uint32_t)(x >> 96); }
+  return b;
+}
+/* Vdpf::Gen :97-177.  Returns 1 when t0 == t1 (the caller resamples), ocw is then left untouched. */
+static int vdpf_gen(const octx *c, cw32 *cws, blk cs[4], blk *ocw, const blk s0s[2], u128 a, blk b_buf) {
+  const int n = c->p.in_bits;
+  blk s0 = set_lsb(s0s[0], 0), s1 = set_lsb(s0s[1], 0);
+  int t0 = 0, t1 = 1;
+  b_buf = set_lsb(b_buf, 0);
+  for (int i = 0; i < n; ++i) {                                   /* same walk as Dpf::Gen */
+    blk g0[4], g1[4];
+    prg_gen(c, 2, s0, g0);
+    prg_gen(c, 2, s1, g1);
+    int t0l = get_lsb(g0[0]), t0r = get_lsb(g0[1]), t1l = get_lsb(g1[0]), t1r = get_lsb(g1[1]);
+    blk s0l = set_lsb(g0[0], 0), s0r = set_lsb(g0[1], 0), s1l = set_lsb(g1[0], 0), s1r = set_lsb(g1[1], 0);
+    int a_bit = in_bit(a, n, i);
+    blk s_cw = a_bit ? bxor(s0l, s1l) : bxor(s0r, s1r);
+    int tl_cw = t0l ^ t1l ^ a_bit ^ 1, tr_cw = t0r ^ t1r ^ a_bit;
+    if (!a_bit) {
+      s0 = bxor(s0l, bsel(t0, s_cw)); s1 = bxor(s1l, bsel(t1, s_cw));
+      t0 = t0l ^ (t0 & tl_cw); t1 = t1l ^ (t1 & tl_cw);
+    } else {
+      s0 = bxor(s0r, bsel(t0, s_cw)); s1 = bxor(s1r, bsel(t1, s_cw));
+      t0 = t0r ^ (t0 & tr_cw); t1 = t1r ^ (t1 & tr_cw);
+    }
+    cws[i].s = set_lsb(s_cw, tl_cw);
+    cws[i].v = bzero(); cws[i].v.w[0] = (uint32_t)tr_cw;          /* :147-149 */
+  }
+  blk a_buf = pack_in(c, a), p0[4], p1[4];                         /* :153-157 */
+  b3_xor_hash(c->p.hash_iv[0], a_buf, s0, p0);
+  b3_xor_hash(c->p.hash_iv[0], a_buf, s1, p1);
+  for (int j = 0; j < 4; ++j) cs[j] = bxor(p0[j], p1[j]);
+  if (t0 == t1) return 1;                                          /* :160 */
+  u128 v = g_add(c, g_add(c, g_from(c, b_buf), g_neg(c, g_from(c, s0))), g_from(c, s1));
+  if (t1) v = g_neg(c, v);
+  *ocw = g_into(c, v);
+  return 0;
+}
+/* y share and corrected per-point hash of one packed leaf (s | t) at input x: :224-242, :318-331 */
+static void vdpf_leaf(const octx *c, int b, blk st, const blk cs[4], blk ocw, u128 x, blk *y, blk pi_tilde[4]) {
+  int t = get_lsb(st);
+  blk s = set_lsb(st, 0);
+  u128 g = g_from(c, s);
+  if (t) g = g_add(c, g, g_from(c, ocw));
+  if (b) g = g_neg(c, g);
+  *y = g_into(c, g);
+  b3_xor_hash(c->p.hash_iv[0], pack_in(c, x), s, pi_tilde);
+  if (t) for (int j = 0; j < 4; ++j) pi_tilde[j] = bxor(pi_tilde[j], cs[j]);
+}
+static void vdpf_eval(const octx *c, int b, blk s0, const cw32 *cws, const blk cs[4], blk ocw, u128 x, blk *y,
+    blk pi_tilde[4]) { /* :191-243 */
+  const int n = c->p.in_bits;
+  blk st = set_lsb(s0, b);
+  for (int i = 0; i < n; ++i) {
+    blk l, r;
+    dpf_expand(c, st, &cws[i], &l, &r);
+    st = in_bit(x, n, i) ? r : l;
+  }
+  vdpf_leaf(c, b, st, cs, ocw, x, y, pi_tilde);
+}
+/* one step of Vdpf::Prove :257-263 / EvalAll :336-340 */
+static void vdpf_accumulate(const octx *c, blk pi[4], const blk pi_tilde[4]) {
+  blk in[4], h[2];
+  for (int j = 0; j < 4; ++j) in[j] = bxor(pi[j], pi_tilde[j]);
+  b3_hash(c->p.hash_iv[1], in, h);
+  pi[0] = bxor(pi[0], h[0]);
+  pi[1] = bxor(pi[1], h[1]);
+}
+static void vdpf_tree(const octx *c, blk st, const cw32 *cws, blk *leaves, int i, uint64_t l, uint64_t r) { /* :345-401 */
+  if (i == c->p.in_bits) { leaves[l] = st; return; }
+  blk a, b;
+  dpf_expand(c, st, &cws[i], &a, &b);
+  const uint64_t mid = (l + r) / 2;
+  vdpf_tree(c, a, cws, leaves, i + 1, l, mid);
+  vdpf_tree(c, b, cws, leaves, i + 1, mid, r);
+}
+
+int orc_vdpf_gen(const fssb200_params *p, size_t nkeys, const void *s0s, const void *alphas, const void *betas,
+    void *cws, void *cs, void *ocws, void *status, int threads) {
+  octx c;
+  int rc = ctx_init(&c, p);
+  if (rc) return rc;
+  if (p->scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  const int n = p->in_bits;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+  for (size_t k = 0; k < nkeys; ++k) {
+    const u128 a = load_in((const uint8_t *)alphas + k * (size_t)p->in_bytes, p->in_bytes);
+    ((int32_t *)status)[k] = vdpf_gen(&c, (cw32 *)cws + k * (size_t)n, (blk *)cs + 4 * k, (blk *)ocws + k,
+        (const blk *)s0s + 2 * k, a, ((const blk *)betas)[k]);
+  }
+  return 0;
+}
+int orc_vdpf_eval(const fssb200_params *p, int party, size_t nkeys, const void *seeds, const void *cws,
+    const void *cs, const void *ocws, const void *xs, void *ys, void *pis, int threads) {
+  octx c;
+  int rc = ctx_init(&c, p);
+  if (rc) return rc;
+  if (p->scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  const int n = p->in_bits;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+  for (size_t k = 0; k < nkeys; ++k) {
+    const u128 x = load_in((const uint8_t *)xs + k * (size_t)p->in_bytes, p->in_bytes);
+    vdpf_eval(&c, party, ((const blk *)seeds)[k], (const cw32 *)cws + k * (size_t)n, (const blk *)cs + 4 * k,
+        ((const blk *)ocws)[k], x, (blk *)ys + k, (blk *)pis + 4 * k);
+  }
+  return 0;
+}
+int orc_vdpf_prove(const fssb200_params *p, size_t nkeys, size_t m, const void *pi_tildes, const void *cs,
+    void *pis) {
+  octx c;
+  int rc = ctx_init(&c, p);
+  if (rc) return rc;
+  for (size_t k = 0; k < nkeys; ++k) {
+    blk *pi = (blk *)pis + 4 * k;
+    memcpy(pi, (const blk *)cs + 4 * k, 64);                        /* :256 */
+    for (size_t i = 0; i < m; ++i) vdpf_accumulate(&c, pi, (const blk *)pi_tildes + 4 * (k * m + i));
+  }
+  return 0;
+}
+int orc_vdpf_evalall(const fssb200_params *p, int party, size_t nkeys, const void *seeds, const void *cws,
+    const void *cs, const void *ocws, void *ys, void *pis, int threads) {
+  octx c;
+  int rc = ctx_init(&c, p);
+  if (rc) return rc;
+  if (p->scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  const int n = p->in_bits;
+  if (n > 30) return FSSB200_EDOMAIN;
+  const uint64_t N = (uint64_t)1 << n;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 1)
+  for (size_t k = 0; k < nkeys; ++k) {
+    blk *out = (blk *)ys + k * N, *pi = (blk *)pis + 4 * k;
+    const blk *kcs = (const blk *)cs + 4 * k;
+    vdpf_tree(&c, set_lsb(((const blk *)seeds)[k], party), (const cw32 *)cws + k * (size_t)n, out, 0, 0, N); /* :311 */
+    memcpy(pi, kcs, 64);                                            /* :314 */
+    for (uint64_t j = 0; j < N; ++j) {                              /* :318-341 */
+      blk y, pt[4];
+      vdpf_leaf(&c, party, out[j], kcs, ((const blk *)ocws)[k], (u128)j, &y, pt);
+      out[j] = y;
+      vdpf_accumulate(&c, pi, pt);
+    }
   }
   return 0;
 }

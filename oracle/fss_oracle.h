@@ -49,6 +49,18 @@ int orc_relayout(const fssb200_params *p, size_t nkeys, const void *cws, void *c
 /* Group helper for reconstruction checks: out[i] = From(a[i]) + From(b[i]) -> Into. */
 int orc_group_add(const fssb200_params *p, size_t n, const void *a, const void *b, void *out);
 
+/* VDPF (vdpf.cuh) with XorHash = Hash = fss::hash::Blake3 (hash/blake3.cuh); see the fssb200_vdpf_* entry
+ * points in include/fssb200.h for the array shapes.  which: 0 = XorHash (32 B -> 64 B), 1 = Hash (64 B -> 32 B). */
+int orc_hash(const fssb200_params *p, int which, size_t n, const void *msgs, void *out);
+int orc_vdpf_gen(const fssb200_params *p, size_t nkeys, const void *s0s, const void *alphas,
+                 const void *betas, void *cws, void *cs, void *ocws, void *status, int threads);
+int orc_vdpf_eval(const fssb200_params *p, int party, size_t nkeys, const void *seeds, const void *cws,
+                  const void *cs, const void *ocws, const void *xs, void *ys, void *pis, int threads);
+int orc_vdpf_prove(const fssb200_params *p, size_t nkeys, size_t m, const void *pi_tildes,
+                   const void *cs, void *pis);
+int orc_vdpf_evalall(const fssb200_params *p, int party, size_t nkeys, const void *seeds,
+                     const void *cws, const void *cs, const void *ocws, void *ys, void *pis, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,7 @@ static void make_ctx(const fssb200_params &p, EmuCtx &c) {
   c.in_bytes = p.in_bytes;
   c.prg = p.prg;
   c.pred = p.pred;
-  c.ncw = p.scheme == FSSB200_SCHEME_HALFTREE ? p.in_bits : p.in_bits + 1;
+  c.ncw = (p.scheme == FSSB200_SCHEME_HALFTREE || p.scheme == FSSB200_SCHEME_VDPF) ? p.in_bits : p.in_bits + 1;
   fssb200_params q = p;
   if (q.scheme == FSSB200_SCHEME_GROTTO) { q.group = FSSB200_GROUP_BYTES; q.mod_lo = q.mod_hi = 0; }
   c.gk = group_kind(q, &c.ga.vmask);
@@ -73,6 +73,7 @@ static void make_ctx(const fssb200_params &p, EmuCtx &c) {
     std::memcpy(c.keys.nonce, q.prg_key, 8);
   }
   std::memcpy(c.keys.hash_key, q.hash_key, 16);
+  std::memcpy(c.keys.hash_iv, q.hash_iv, 64);
   c.ga.mod[0] = uint32_t(q.mod_lo); c.ga.mod[1] = uint32_t(q.mod_lo >> 32);
   c.ga.mod[2] = uint32_t(q.mod_hi); c.ga.mod[3] = uint32_t(q.mod_hi >> 32);
 }
@@ -90,6 +91,7 @@ struct Bufs {
   const blk *s0s; const blk *betas; uint8_t *cws_out; blk *ocws_out;
   uint8_t *all_out; uint64_t leaf_begin, leaf_count;
   uint64_t nkeys; int party; bool level_major;
+  const blk *cs; blk *pis; blk *cs_out; int32_t *status;   // VDPF
 };
 
 template <int G, int PRG>
@@ -127,6 +129,32 @@ static void gen_t(const EmuCtx &c, const Bufs &b) {
       dcf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, c.pred, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, cws);
     else
       ht_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, cws, &b.ocws_out[k]);
+  }
+}
+
+template <int G, int PRG>
+static void vdpf_eval_t(const EmuCtx &c, const Bufs &b) {
+  for (uint64_t k = 0; k < b.nkeys; ++k) {
+    const auto pc = lane_ctx<PRG>(k);
+    const InVal x = load_in(b.xs + k * c.in_bytes, c.in_bytes);
+    if (b.level_major) {
+      const CwLevelMajor cw{b.cw_s, nullptr, b.extra, nullptr, b.nkeys, k};
+      b.ys[k] = vdpf_eval_body<G, PRG>(c.keys, c.ga, pc, c.n, b.party, b.seeds[k], x, cw, b.ocws[k], b.cs + 4 * k,
+          b.pis + 4 * k);
+    } else {
+      const CwKeyMajor cw{b.cws + k * uint64_t(c.ncw) * 32};
+      b.ys[k] = vdpf_eval_body<G, PRG>(c.keys, c.ga, pc, c.n, b.party, b.seeds[k], x, cw, b.ocws[k], b.cs + 4 * k,
+          b.pis + 4 * k);
+    }
+  }
+}
+template <int G, int PRG>
+static void vdpf_gen_t(const EmuCtx &c, const Bufs &b) {
+  for (uint64_t k = 0; k < b.nkeys; ++k) {
+    const auto pc = lane_ctx<PRG>(k);
+    const InVal a = load_in(b.xs + k * c.in_bytes, c.in_bytes);
+    b.status[k] = vdpf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, b.betas[k],
+        b.cws_out + k * uint64_t(c.ncw) * 32, b.cs_out + 4 * k, b.ocws_out + k);
   }
 }
 
@@ -275,6 +303,70 @@ int emul_evalall(const fssb200_params *p, int party, size_t nkeys, const void *s
   b.leaf_begin = leaf_begin;
   b.leaf_count = leaf_count ? leaf_count : ((uint64_t(1) << p->in_bits) - leaf_begin);
   DISPATCH(evalall_t, c, b);
+  return 0;
+}
+
+int emul_hash(const fssb200_params *p, int which, size_t n, const void *msgs, void *out) {
+  EmuCtx c;
+  make_ctx(*p, c);
+  const blk *m = static_cast<const blk *>(msgs);
+  blk *o = static_cast<blk *>(out);
+  for (size_t i = 0; i < n; ++i) {
+    if (which == 0) b3_xor_hash(c.keys.hash_iv[0], m[2 * i], m[2 * i + 1], o + 4 * i);
+    else b3_hash(c.keys.hash_iv[1], m + 4 * i, o + 2 * i);
+  }
+  return 0;
+}
+
+int emul_vdpf_gen(const fssb200_params *p, size_t nkeys, const void *s0s, const void *alphas, const void *betas,
+    void *cws, void *cs, void *ocws, void *status) {
+  EmuCtx c;
+  make_ctx(*p, c);
+  Bufs b{};
+  b.nkeys = nkeys;
+  b.s0s = static_cast<const blk *>(s0s);
+  b.xs = static_cast<const uint8_t *>(alphas);
+  b.betas = static_cast<const blk *>(betas);
+  b.cws_out = static_cast<uint8_t *>(cws);
+  b.cs_out = static_cast<blk *>(cs);
+  b.ocws_out = static_cast<blk *>(ocws);
+  b.status = static_cast<int32_t *>(status);
+  DISPATCH(vdpf_gen_t, c, b);
+  return 0;
+}
+
+int emul_vdpf_eval(const fssb200_params *p, int party, size_t nkeys, const void *seeds, const void *cws,
+    const void *cs, const void *ocws, const void *xs, void *ys, void *pis, int level_major, const void *cw_s,
+    const void *extra) {
+  EmuCtx c;
+  make_ctx(*p, c);
+  Bufs b{};
+  b.nkeys = nkeys;
+  b.party = party;
+  b.seeds = static_cast<const blk *>(seeds);
+  b.cws = static_cast<const uint8_t *>(cws);
+  b.cs = static_cast<const blk *>(cs);
+  b.ocws = static_cast<const blk *>(ocws);
+  b.xs = static_cast<const uint8_t *>(xs);
+  b.ys = static_cast<blk *>(ys);
+  b.pis = static_cast<blk *>(pis);
+  b.level_major = level_major != 0;
+  b.cw_s = static_cast<const blk *>(cw_s);
+  b.extra = static_cast<const uint32_t *>(extra);
+  DISPATCH(vdpf_eval_t, c, b);
+  return 0;
+}
+
+int emul_vdpf_prove(const fssb200_params *p, size_t nkeys, size_t m, const void *pi_tildes, const void *cs, void *pis) {
+  EmuCtx c;
+  make_ctx(*p, c);
+  const blk *pt = static_cast<const blk *>(pi_tildes);
+  for (size_t k = 0; k < nkeys; ++k) {
+    blk pi[4];
+    std::memcpy(pi, static_cast<const blk *>(cs) + 4 * k, 64);
+    for (size_t i = 0; i < m; ++i) vdpf_accumulate(c.keys, pi, pt + 4 * (k * m + i));
+    std::memcpy(static_cast<blk *>(pis) + 4 * k, pi, 64);
+  }
   return 0;
 }
 

@@ -23,7 +23,8 @@ CSRC = os.path.join(os.path.dirname(HERE), "fss_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("common.cuh", "aes.cuh", "prg.cuh", "group.cuh", "schemes.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("common.cuh", "aes.cuh", "blake3.cuh", "prg.cuh", "group.cuh",
+                                                          "schemes.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", "-w", "-I/usr/local/cuda/include",
                         SRC, "-o", LIB], check=True)
