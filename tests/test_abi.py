@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r"\bT (fssb200_[a-z0-9_]+)", out.stdout))
     assert set(names) <= exported, sorted(set(names) - exported)
     assert set(names) == set(_lib.SYMBOLS), "python binding table out of sync with the header"
-    assert _lib.lib.fssb200_version() == 100
+    hdr = open(os.path.join(ROOT, "include", "fssb200.h")).read()
+    assert _lib.lib.fssb200_version() == int(re.search(r"#define FSSB200_VERSION (\d+)", hdr).group(1))
 
 
 def test_library_is_sm100a_only():
