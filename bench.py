@@ -411,7 +411,51 @@ def run_own_arm(args) -> None:
             "int_roofline_frac": (leaves * OPS_PER_LEAF_C4 / (msk4 * 1e-3) / 1e12 / int_peak) if int_peak else None,
             "lsu_roofline_frac": (leaves * 2 * LOOKUPS_PER_AES / (msk4 * 1e-3) / 1e12 / lds_peak) if lds_peak else None,
             "hbm_write_gbs": leaves * 16 / (msk4 * 1e-3) / 1e9}
+        # C4 as BASELINE configs[3] words it: "subtrees sharded" -- every rank expands ITS leaf range of every key
+        # (8 keys per GPU in the job, so the per-GPU work stays 32 GiB of leaves: weak scaling), no collective
+        if world > 1:
+            from fss_b200.sharding import leaf_shard
+            kk = k4 * world
+            s0s, alphas, betas, xs, cws = make_keys(c4, kk, torch.Generator(device=dev).manual_seed(4242))  # same keys on every rank
+            seeds0 = s0s[:, 0].contiguous()
+            lb, lc = leaf_shard(n4, c4.granule(), rank, world)
+            outv = out.view(-1)[: kk * lc * 4].view(kk, lc, 4)
+            ms4s, _ = timed(lambda: c4.eval_all(0, seeds0, cws, leaf_begin=lb, leaf_count=lc, out=outv), max(2, x_steps // 2), 2)
+            extra["dpf_evalall_subtree_sharded"] = {
+                "value": kk * (1 << n4) / (ms4s * 1e-3), "unit": "leaves/s", "ms_per_step": ms4s, "in_bits": n4,
+                "keys_total": kk, "leaf_range_per_gpu": [int(lb), int(lc)], "output_gib_per_gpu": kk * lc * 16 / 2 ** 30}
+            del outv
         del out, cws
+        torch.cuda.empty_cache()
+        # the reference's primary GPU PRG (ChaCha<2>, 20 rounds) on the C2 shape: bound = integer issue rate
+        k6 = min(args.keys, 1 << 21)
+        c6 = fss_b200.Context("dpf", 32, "bytes", prg="chacha")
+        s0s, alphas, betas, xs, cws = make_keys(c6, k6, gen)
+        seeds0 = s0s[:, 0].contiguous()
+        ys = torch.empty((k6, 4), dtype=torch.int32, device=dev)
+        ms6, msk6 = timed(lambda: c6.eval(0, seeds0, cws, xs, out=ys), x_steps, x_warm)
+        mixed = peaks.get("lop3_imad_mixed")
+        extra["dpf_n32_chacha"] = {
+            "value": world * k6 / (ms6 * 1e-3), "unit": "evals/s", "ms_per_step": ms6, "keys_per_gpu": k6,
+            "issue_roofline_frac": (k6 * 32 * (976 + 12) / (msk6 * 1e-3) / mixed) if mixed else None,
+            "note": "976 integer instructions per ChaCha20 block (SURVEY.md section 8d) against the measured mixed "
+                    "LOP3+IMAD issue rate (ALU + FMA pipes)"}
+        del s0s, betas, cws, ys, seeds0
+        torch.cuda.empty_cache()
+        # VDPF: DPF walk + Blake3 proof tail, n=32, 2^20 keys
+        k7 = min(args.keys, 1 << 20)
+        c7 = fss_b200.Context("vdpf", 32, "bytes", prg="aes128_mmo")
+        s0s = rand_i32((k7, 2, 4), gen)
+        betas = rand_i32((k7, 4), gen)
+        s0s[:, :, 3] &= ~1
+        betas[:, 3] &= ~1
+        alphas, xs = rand_i32((k7,), gen), rand_i32((k7,), gen)
+        vcws, vcs, vocws, _status = c7.vdpf_gen(s0s, alphas, betas)
+        seeds0 = s0s[:, 0].contiguous()
+        ms7, _ = timed(lambda: c7.vdpf_eval(0, seeds0, vcws, vcs, vocws, xs), x_steps, x_warm)
+        extra["vdpf_n32_aes"] = {"value": world * k7 / (ms7 * 1e-3), "unit": "evals/s", "ms_per_step": ms7,
+                                 "keys_per_gpu": k7}
+        del s0s, betas, vcws, vcs, vocws, seeds0
         torch.cuda.empty_cache()
         sampler.stop()
 

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Small invocation of every kernel family, checked against the oracle -- the workload that
+tools/gpu_sanitize.sh runs under compute-sanitizer (memcheck / racecheck / synccheck / initcheck).
+Sizes are ragged on purpose (tiles of 32 keys, 768-thread CTAs, TMA boxes that run off the tensor)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fss_b200  # noqa: E402
+from oracle import Orc, Params, synth_inputs  # noqa: E402
+
+dev = torch.device("cuda:0")
+orc = Orc()
+only = set(sys.argv[1:])
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+
+
+def same(name, got, want):
+    got = got.cpu().numpy().view(want.dtype).reshape(want.shape)
+    assert np.array_equal(got, want), name
+    print("ok", name, flush=True)
+
+
+for scheme, n, group, prg, nkeys in (("dpf", 32, "bytes", "aes128_mmo", 1000), ("dpf", 17, "u64", "chacha", 333),
+                                     ("dcf", 64, "u128", "aes128_mmo", 777), ("dcf", 9, "u32", "chacha", 100),
+                                     ("halftree", 32, "bytes", "aes128_mmo", 901), ("halftree", 5, "bytes", "chacha", 65)):
+    tag = f"{scheme}-{n}-{group}-{prg}"
+    if only and "point" not in only:
+        break
+    p = Params(scheme=scheme, in_bits=n, group=group, prg=prg)
+    s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=n)
+    ctx = fss_b200.Context(scheme, n, group, p.mod, prg, p.pred, p.prg_key, p.hash_key, p.in_bytes)
+    r = ctx.gen(t(s0s), alphas, t(betas))
+    cws, ocws = r if scheme == "halftree" else (r, None)
+    cw_np = cws.cpu().numpy().view(np.uint32)
+    oc_np = None if ocws is None else ocws.cpu().numpy().view(np.uint32)
+    for party in (0, 1):
+        ys = ctx.eval(party, t(s0s[:, party]), cws, xs, ocws=ocws)
+        w = orc.eval(p, party, s0s[:, party], cw_np, xs, oc_np)
+        same(f"eval {tag} party {party}", ys, w)
+    lay = ctx.relayout(cws)
+    ys2 = ctx.eval_levelmajor(0, t(s0s[:, 0]), lay, xs, ocws=ocws)
+    same(f"levelmajor {tag}", ys2, orc.eval(p, 0, s0s[:, 0], cw_np, xs, oc_np))
+
+if not only or "evalall" in only:
+    for scheme, n, group, prg, nkeys in (("dpf", 18, "bytes", "aes128_mmo", 2), ("dpf", 11, "u64", "chacha", 3),
+                                         ("halftree", 18, "bytes", "aes128_mmo", 2), ("dcf", 17, "u128", "aes128_mmo", 1),
+                                         ("grotto", 18, "bytes", "aes128_mmo", 2)):
+        tag = f"{scheme}-{n}-{group}-{prg}"
+        p = Params(scheme=scheme, in_bits=n, group=group, prg=prg)
+        s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=100 + n)
+        ctx = fss_b200.Context(scheme, n, group, p.mod, prg, p.pred, p.prg_key, p.hash_key, p.in_bytes)
+        r = ctx.gen(t(s0s), alphas, None if scheme == "grotto" else t(betas))
+        cws, ocws = r if scheme == "halftree" else (r, None)
+        cw_np = cws.cpu().numpy().view(np.uint32)
+        oc_np = None if ocws is None else ocws.cpu().numpy().view(np.uint32)
+        ya = ctx.eval_all(1, t(s0s[:, 1]), cws, ocws=ocws)
+        w = orc.evalall(p, 1, s0s[:, 1], cw_np, oc_np)
+        same(f"eval_all {tag}", ya, w)
+        if scheme == "grotto":
+            pt = ctx.grotto_preprocess(0, t(s0s[:, 0]), cws)
+            yl = ctx.grotto_lookup(pt, xs)
+            w0 = orc.evalall(p, 0, s0s[:, 0], cw_np)
+            same(f"grotto lookup {tag}", yl, np.array([w0[k][int(x)] for k, x in enumerate(xs)], dtype=np.uint8))
+
+if not only or "vdpf" in only:
+    ctx = fss_b200.Context("vdpf", 16, "bytes", prg="aes128_mmo")
+    g = torch.Generator(device=dev).manual_seed(5)
+    nk = 500
+    s0s = torch.randint(-2 ** 31, 2 ** 31, (nk, 2, 4), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    betas = torch.randint(-2 ** 31, 2 ** 31, (nk, 4), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    s0s[:, :, 3] &= ~1
+    betas[:, 3] &= ~1
+    alphas = torch.randint(0, 1 << 16, (nk,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    cws, cs, ocws, status = ctx.vdpf_gen(s0s, alphas, betas)
+    ok = status == 0
+    y0, p0 = ctx.vdpf_eval(0, s0s[:, 0].contiguous(), cws, cs, ocws, alphas)
+    y1, p1 = ctx.vdpf_eval(1, s0s[:, 1].contiguous(), cws, cs, ocws, alphas)
+    assert torch.equal((y0 ^ y1)[ok], betas[ok]) and torch.equal(p0[ok], p1[ok])
+    ya0, pa0 = ctx.vdpf_eval_all(0, s0s[:4, 0].contiguous(), cws[:4], cs[:4], ocws[:4])
+    ya1, pa1 = ctx.vdpf_eval_all(1, s0s[:4, 1].contiguous(), cws[:4], cs[:4], ocws[:4])
+    assert torch.equal(pa0, pa1)
+    print("ok vdpf", flush=True)
+
+if not only or "host" in only:
+    p = Params(scheme="dpf", in_bits=32)
+    s0s, alphas, betas, xs = synth_inputs(p, 3000, seed=9)
+    ctx = fss_b200.Context("dpf", 32, "bytes", prg="aes128_mmo")
+    ctx.reserve_host(1024)
+    hs = torch.from_numpy(s0s.view(np.int32)).pin_memory()
+    cws = ctx.gen(hs, alphas, torch.from_numpy(betas.view(np.int32)).pin_memory())
+    ys = ctx.eval(0, hs[:, 0].contiguous().pin_memory(), cws.pin_memory(), xs)
+    same("eval_host", ys, orc.eval(p, 0, s0s[:, 0], cws.numpy().view(np.uint32), xs))
+torch.cuda.synchronize()
+print("ALL OK")
