@@ -32,6 +32,7 @@ struct fssb200_ctx {
   int max_smem_optin;
   uint32_t vmask;
   int point_mode;   // PointMode of the key-major point kernels (kernels.cuh); FSSB200_POINT_MODE overrides
+  int gen_mode;     // gen kernels: 1 = Cw tiles written by the TMA unit (CwTileOut), 0 = direct stores; FSSB200_GEN_MODE
   std::atomic<uint64_t> launches{0};
   HostArena arena;
 };
@@ -137,6 +138,21 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
   return cfg;
 }
 
+// Gen kernels: geometry of point_cfg; out_mode 1 adds one CwTileOut pair of tiles per warp to the ChaCha CTAs
+// (the AES CTAs always own the full dynamic shared memory).
+LaunchCfg gen_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int out_mode) {
+  LaunchCfg cfg = point_cfg(c, n, s);
+  if (c->p.prg != FSSB200_PRG_AES128_MMO && out_mode) cfg.smem = 8 * CwTileOut::kWarpBytes + 512 + 32;
+  return cfg;
+}
+// Fills a.tmap and returns the output mode the launch will use (TMA coordinates are 32-bit).
+int gen_out_mode(const fssb200_ctx *c, GenArgs &a, int *rc) {
+  *rc = 0;
+  if (!c->gen_mode || (a.nkeys >> 31)) return 0;
+  *rc = make_cw_tensor_map(a.tmap, a.cws, a.nkeys, c->ncw);
+  return 1;
+}
+
 struct EvalAllPlan {
   int unit_bits, breadth_bits, dfs_bits;
 };
@@ -220,6 +236,8 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
     const int m = std::atoi(e);
     if (m == 0 || m == 1 || m == 3 || m == 4 || m == 5) c->point_mode = m;
   }
+  c->gen_mode = 1;
+  if (const char *e = std::getenv("FSSB200_GEN_MODE")) c->gen_mode = std::atoi(e) ? 1 : 0;  // A/B measurement knob
   std::memset(&c->kp, 0, sizeof(c->kp));
   if (q.prg == FSSB200_PRG_AES128_MMO) {
     for (int i = 0; i < 4; ++i) aes128_expand_le(q.prg_key + 16 * i, c->kp.keys.rk[i]);
@@ -278,8 +296,7 @@ int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, cons
   if (nkeys == 0) return 0;
   // Grotto keys are DPF keys over Bytes with beta = 0 (grotto_dcf.cuh:63-67)
   const int kscheme = scheme == FSSB200_SCHEME_GROTTO ? FSSB200_SCHEME_DPF : scheme;
-  gen_launch_fn fn = get_gen_launcher(kscheme, c->gk, c->p.prg);
-  if (!fn) return FSSB200_EGROUP;
+  if (!grp_kind_instantiated(c->gk)) return FSSB200_EGROUP;
   DeviceGuard g(c->p.device);
   if (g.err != cudaSuccess) return int(g.err);
   GenArgs a;
@@ -294,7 +311,12 @@ int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, cons
   a.in_bytes = c->p.in_bytes;
   a.pred = c->p.pred;
   a.vmask = c->vmask;
-  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream));
+  int rc = 0;
+  const int out_mode = gen_out_mode(c, a, &rc);
+  if (rc) return rc;
+  gen_launch_fn fn = get_gen_launcher(kscheme, c->gk, c->p.prg, out_mode);
+  if (!fn) return FSSB200_EGROUP;
+  const LaunchCfg cfg = gen_cfg(c, nkeys, static_cast<cudaStream_t>(stream), out_mode);
   c->launches++;
   return int(fn(c->kp, a, cfg));
 }
@@ -413,7 +435,7 @@ uint64_t fssb200_eval_all_granule(const fssb200_ctx *c) {
 }
 
 static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, const void *cws, const void *ocws,
-    void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count, void *stream) {
+    void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count, void *stream, uint64_t ys_stride = 0) {
   if (party != 0 && party != 1) return FSSB200_EINVAL;
   if (!seeds || !cws || !ys) return FSSB200_EINVAL;
   if (mode == 1 && !ocws) return FSSB200_EINVAL;
@@ -442,6 +464,7 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
   a.nkeys = nkeys;
   a.leaf_begin = leaf_begin;
   a.leaf_count = leaf_count;
+  a.ys_stride = ys_stride ? ys_stride : leaf_count;
   a.in_bits = n;
   a.party = party;
   a.unit_bits = pl.unit_bits;
@@ -462,7 +485,8 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
     cfg.grid = dim3(unsigned(units < cap ? units : cap));
     // cw copies + two breadth buffers + DFS stack (+ slack for alignment)
     cfg.smem = size_t(c->ncw + 1) * 48 + 2 * threads * node_bytes +
-        size_t(pl.dfs_bits > 1 ? pl.dfs_bits - 1 : 1) * threads * node_bytes + 64;
+        size_t(pl.dfs_bits > 1 ? pl.dfs_bits - 1 : 1) * threads * node_bytes + 64 +
+        (mode == 2 && pl.dfs_bits >= 5 ? (size_t(threads) * 4) << (pl.dfs_bits - 5) : 0);  // Grotto: packed leaf bits
   }
   c->launches++;
   return int(fn(c->kp, a, cfg));
@@ -504,8 +528,7 @@ int fssb200_vdpf_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas,
   if (!aligned16(s0s) || !aligned16(cws) || !aligned16(betas) || !aligned16(ocws) || !aligned16(cs)) return FSSB200_EALIGN;
   if (reinterpret_cast<uintptr_t>(alphas) % c->p.in_bytes || reinterpret_cast<uintptr_t>(status) % 4) return FSSB200_EALIGN;
   if (nkeys == 0) return 0;
-  gen_launch_fn fn = get_gen_launcher(FSSB200_SCHEME_VDPF, c->gk, c->p.prg);
-  if (!fn) return FSSB200_EGROUP;
+  if (!grp_kind_instantiated(c->gk)) return FSSB200_EGROUP;
   DeviceGuard g(c->p.device);
   if (g.err != cudaSuccess) return int(g.err);
   GenArgs a;
@@ -522,7 +545,12 @@ int fssb200_vdpf_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas,
   a.in_bytes = c->p.in_bytes;
   a.pred = c->p.pred;
   a.vmask = c->vmask;
-  const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream));
+  int rc = 0;
+  const int out_mode = gen_out_mode(c, a, &rc);
+  if (rc) return rc;
+  gen_launch_fn fn = get_gen_launcher(FSSB200_SCHEME_VDPF, c->gk, c->p.prg, out_mode);
+  if (!fn) return FSSB200_EGROUP;
+  const LaunchCfg cfg = gen_cfg(c, nkeys, static_cast<cudaStream_t>(stream), out_mode);
   c->launches++;
   return int(fn(c->kp, a, cfg));
 }
@@ -603,19 +631,20 @@ int fssb200_grotto_preprocess(const fssb200_ctx *cc, int party, const void *seed
   const int n = c->p.in_bits;
   if (n > 31) return FSSB200_EDOMAIN;
   const uint64_t N = uint64_t(1) << n;
-  // leaf bits of key k go to pt[k*(2N-1) + N-1 ...] (grotto_dcf.cuh:98), then the internal nodes
-  // are filled level by level, bottom-up (grotto_dcf.cuh:100-103)
-  for (size_t k = 0; k < nkeys; ++k) {
-    uint8_t *tree = static_cast<uint8_t *>(pt) + k * (2 * N - 1);
-    int rc = evalall_impl(c, 2, party, static_cast<const blk *>(seeds) + k,
-        static_cast<const uint8_t *>(cws) + k * size_t(c->ncw) * 32, nullptr, tree + (N - 1), 1, 0, N, stream);
-    if (rc) return rc;
-    DeviceGuard g(c->p.device);
-    for (int lvl = n - 1; lvl >= 0; --lvl) {
-      c->launches++;
-      cudaError_t e = launch_parity_level(tree, lvl, static_cast<cudaStream_t>(stream));
-      if (e != cudaSuccess) return int(e);
-    }
+  // leaf bits of key k go to pt[k*(2N-1) + N-1 ...] (grotto_dcf.cuh:98): one expansion launch for all keys,
+  // rows 2N-1 bytes apart; then the internal nodes bottom-up (grotto_dcf.cuh:100-103), kParityLevels tree
+  // levels per launch
+  if (int rc = evalall_impl(c, 2, party, seeds, cws, nullptr, static_cast<uint8_t *>(pt) + (N - 1), nkeys, 0, N, stream,
+          2 * N - 1))
+    return rc;
+  if (nkeys == 0) return 0;
+  DeviceGuard g(c->p.device);
+  if (g.err != cudaSuccess) return int(g.err);
+  for (int bottom = n; bottom > 0; bottom -= kParityLevels) {
+    c->launches++;
+    cudaError_t e = launch_parity_levels(static_cast<uint8_t *>(pt), 2 * N - 1, nkeys, bottom,
+        static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return int(e);
   }
   return 0;
 }
@@ -967,17 +996,17 @@ point_launch_fn get_point_launcher(int scheme, int gk, int prg, int mode) {
   }
   return nullptr;
 }
-gen_launch_fn get_gen_launcher(int scheme, int gk, int prg) {
+gen_launch_fn get_gen_launcher(int scheme, int gk, int prg, int out_mode) {
   if (prg == kPrgAes) {
-    if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_aes_dpf(gk);
-    if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_aes_dcf(gk);
-    if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_aes_ht(gk);
-    if (scheme == FSSB200_SCHEME_VDPF) return gen_launcher_aes_vdpf(gk);
+    if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_aes_dpf(gk, out_mode);
+    if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_aes_dcf(gk, out_mode);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_aes_ht(gk, out_mode);
+    if (scheme == FSSB200_SCHEME_VDPF) return gen_launcher_aes_vdpf(gk, out_mode);
   } else {
-    if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_chacha_dpf(gk);
-    if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_chacha_dcf(gk);
-    if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_chacha_ht(gk);
-    if (scheme == FSSB200_SCHEME_VDPF) return gen_launcher_chacha_vdpf(gk);
+    if (scheme == FSSB200_SCHEME_DPF) return gen_launcher_chacha_dpf(gk, out_mode);
+    if (scheme == FSSB200_SCHEME_DCF) return gen_launcher_chacha_dcf(gk, out_mode);
+    if (scheme == FSSB200_SCHEME_HALFTREE) return gen_launcher_chacha_ht(gk, out_mode);
+    if (scheme == FSSB200_SCHEME_VDPF) return gen_launcher_chacha_vdpf(gk, out_mode);
   }
   return nullptr;
 }

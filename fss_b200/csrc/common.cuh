@@ -114,6 +114,8 @@ struct GenArgs {
   int in_bytes;
   int pred;
   uint32_t vmask;
+  // CUtensorMap of the key-major output array (as PointArgs::tmap): gen kernels with OUT = 1 write through it
+  alignas(64) uint8_t tmap[128];
 };
 
 struct EvalAllArgs {
@@ -124,6 +126,7 @@ struct EvalAllArgs {
   uint64_t nkeys;
   uint64_t leaf_begin;
   uint64_t leaf_count;
+  uint64_t ys_stride;     // elements between the outputs of consecutive keys (leaf_count, or 2N-1 inside a parity tree)
   int in_bits;
   int party;
   int unit_bits;          // log2(leaves per CTA work unit)

@@ -28,7 +28,8 @@ inline bool grp_kind_instantiated(int gk) {
 // scheme in {DPF, DCF, HALFTREE, VDPF}; returns nullptr when not instantiated.
 // mode: see PointMode in kernels.cuh (0/1 staged key-major, 2 level-major, 3 direct key-major)
 point_launch_fn get_point_launcher(int scheme, int gk, int prg, int mode);
-gen_launch_fn get_gen_launcher(int scheme, int gk, int prg);
+// out_mode: 0 = direct key-major stores, 1 = tiles written by the TMA unit (CwTileOut)
+gen_launch_fn get_gen_launcher(int scheme, int gk, int prg, int out_mode);
 // mode 0 = DPF leaves, 1 = Half-Tree leaves, 2 = Grotto leaf bits (gk ignored), 3 = DCF leaves,
 // 4 = VDPF packed leaves (gk ignored)
 evalall_launch_fn get_evalall_launcher(int mode, int gk, int prg);
@@ -36,7 +37,7 @@ prg_launch_fn get_prg_launcher(int prg, int mul);
 
 #define FSS_DECL_POINT(PRGNAME, SCHNAME) \
   point_launch_fn point_launcher_##PRGNAME##_##SCHNAME(int gk, int mode);
-#define FSS_DECL_GEN(PRGNAME, SCHNAME) gen_launch_fn gen_launcher_##PRGNAME##_##SCHNAME(int gk);
+#define FSS_DECL_GEN(PRGNAME, SCHNAME) gen_launch_fn gen_launcher_##PRGNAME##_##SCHNAME(int gk, int out_mode);
 #define FSS_DECL_EVALALL(PRGNAME, MODENAME) evalall_launch_fn evalall_launcher_##PRGNAME##_##MODENAME(int gk);
 FSS_DECL_POINT(aes, dpf) FSS_DECL_POINT(aes, dcf) FSS_DECL_POINT(aes, ht) FSS_DECL_POINT(aes, vdpf)
 FSS_DECL_POINT(chacha, dpf) FSS_DECL_POINT(chacha, dcf) FSS_DECL_POINT(chacha, ht) FSS_DECL_POINT(chacha, vdpf)

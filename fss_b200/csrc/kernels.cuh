@@ -346,32 +346,104 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
   }
 }
 
+// ---- correction words written by the TMA unit (gen kernels, OUT = 1) -------------------------------------------------------
+// The first gen kernels stored each 32-byte entry straight into the key-major array: two STG.128 per level whose 32
+// lanes hit 32 different rows (stride ncw*32 B), i.e. ~64 LSU wavefronts per warp and level next to the 320 (Half-Tree)
+// .. 1280 (DCF) wavefronts of the level's AES lookups -- the same data pipe.  Here a warp parks two levels of its 32
+// keys in a 2 KB shared-memory tile (same swizzled layout as CwTile: conflict-free lane-per-key 128-bit stores) and lane
+// 0 hands the tile to the TMA unit (`cp.async.bulk.tensor.2d.global.shared::cta`); rows / levels outside the tensor
+// are clipped by the hardware.  Double-buffered: a buffer is rewritten only after the store issued from it two
+// chunks earlier has read it (`cp.async.bulk.wait_group.read 1`).
+struct CwTileOut {
+  static constexpr uint32_t kBuf = 2048u;
+  static constexpr uint32_t kWarpBytes = 2u * kBuf;
+  uint32_t buf;        // the warp's two tiles (512-byte aligned)
+  const void *tmap;
+  uint32_t lane, rowoff, sw;
+  int row0;            // first key of the warp's tile
+  int ncw;
+  uint32_t *seq;       // chunks this warp has stored so far (kernel lifetime; buffer = seq & 1)
+
+  FSS_D void put(int i, blk s, blk v) const {
+    const uint32_t q = *seq, h = uint32_t(i) & 1u;
+    const uint32_t tile = buf + (q & 1u) * kBuf;
+    if (h == 0) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+    }
+    sts_blk(tile + rowoff + (((h * 2u) ^ sw) << 4), s);
+    sts_blk(tile + rowoff + (((h * 2u + 1u) ^ sw) << 4), v);
+    if (h == 1 || i == ncw - 1) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap),
+                     "r"((i >> 1) * 64), "r"(row0), "r"(tile)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      *seq = q + 1u;
+    }
+  }
+  static FSS_D void drain(uint32_t lane) {  // before the CTA's shared memory goes away
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+};
+
 // ---- batched key generation --------------------------------------------------------------------------------------
-template <int SCHEME, int G, int PRG>
+// One key per thread, both parties in lock-step; warps own tiles of 32 consecutive keys.
+// OUT: 0 = direct key-major stores (first version, FSSB200_GEN_MODE=0), 1 = TMA-written tiles (CwTileOut).
+template <int SCHEME, int G, int PRG, class Out>
+FSS_D void gen_one(const KParams &P, const typename Prg<PRG>::ctx_t &pc, const GenArgs &A, uint64_t k, bool valid,
+    const Out &out) {
+  const int n = A.in_bits;
+  const blk s0 = ld_blk(A.s0s + 2 * k), s1 = ld_blk(A.s0s + 2 * k + 1);
+  const InVal a = load_in(A.alphas + k * uint64_t(A.in_bytes), A.in_bytes);
+  const blk beta = A.betas ? ld_blk(A.betas + k) : zero_blk();
+  if (SCHEME == FSSB200_SCHEME_VDPF) {
+    const int st = vdpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, out, A.cs + 4 * k, A.ocws + k, valid);
+    if (valid) A.status[k] = st;
+  } else if (SCHEME == FSSB200_SCHEME_DPF) {
+    dpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, out);
+  } else if (SCHEME == FSSB200_SCHEME_DCF) {
+    dcf_gen_body<G, PRG>(P.keys, P.ga, pc, n, A.pred, s0, s1, a, beta, out);
+  } else {
+    blk ocw;
+    ht_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, out, &ocw);
+    if (valid) st_blk(A.ocws + k, ocw);
+  }
+}
+
+template <int SCHEME, int G, int PRG, int OUT>
 __global__ void __launch_bounds__(kPointThreads, 1)
 gen_kernel(const __grid_constant__ KParams P, const __grid_constant__ GenArgs A) {
   SmemPlan sp = smem_plan<PRG>();
   const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
   const int n = A.in_bits;
   const int ncw = (SCHEME == FSSB200_SCHEME_HALFTREE || SCHEME == FSSB200_SCHEME_VDPF) ? n : n + 1;
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < A.nkeys; k += stride) {
-    const blk s0 = ld_blk(A.s0s + 2 * k), s1 = ld_blk(A.s0s + 2 * k + 1);
-    const InVal a = load_in(A.alphas + k * uint64_t(A.in_bytes), A.in_bytes);
-    const blk beta = A.betas ? ld_blk(A.betas + k) : zero_blk();
-    uint8_t *cws = A.cws + k * uint64_t(ncw) * 32u;
-    if (SCHEME == FSSB200_SCHEME_VDPF) {
-      A.status[k] = vdpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws, A.cs + 4 * k, A.ocws + k);
-    } else if (SCHEME == FSSB200_SCHEME_DPF) {
-      dpf_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws);
-    } else if (SCHEME == FSSB200_SCHEME_DCF) {
-      dcf_gen_body<G, PRG>(P.keys, P.ga, pc, n, A.pred, s0, s1, a, beta, cws);
-    } else {
-      blk ocw;
-      ht_gen_body<G, PRG>(P.keys, P.ga, pc, n, s0, s1, a, beta, cws, &ocw);
-      st_blk(A.ocws + k, ocw);
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint32_t slab = 0, seq = 0;
+  if (OUT == 1) {
+    for (uint32_t w = 0; w < nwarps; ++w) {  // same allocation sequence in every thread
+      const uint32_t a = sp.alloc(CwTileOut::kWarpBytes, false, 512u);
+      if (w == wid) slab = a;
     }
   }
+  const uint64_t ntiles = (A.nkeys + 31) >> 5;
+  for (uint64_t tile = uint64_t(blockIdx.x) * nwarps + wid; tile < ntiles; tile += uint64_t(gridDim.x) * nwarps) {
+    const uint64_t k = tile * 32 + lane;
+    const bool valid = k < A.nkeys;
+    if (OUT == 1) {
+      // idle lanes of a ragged tile shadow the last key; their tile rows lie outside the tensor and are clipped
+      const CwTileOut out{slab, A.tmap, lane, lane * 64u, (lane >> 1) & 3u, int(tile * 32), ncw, &seq};
+      gen_one<SCHEME, G, PRG>(P, pc, A, valid ? k : A.nkeys - 1, valid, out);
+    } else if (valid) {
+      const CwOutKeyMajor out{A.cws + k * uint64_t(ncw) * 32u};
+      gen_one<SCHEME, G, PRG>(P, pc, A, k, true, out);
+    }
+  }
+  if (OUT == 1) CwTileOut::drain(lane);
 }
 
 // ---- PRG known-answer kernel ------------------------------------------------------------------------------------------
@@ -386,6 +458,47 @@ prg_kernel(const __grid_constant__ KParams P, const blk *seeds, blk *out, uint64
     Prg<PRG>::template gen<MUL>(P.keys, pc, ld_blk(seeds + i), o);
 #pragma unroll
     for (int j = 0; j < MUL; ++j) st_blk(out + i * MUL + j, o[j]);
+  }
+}
+
+// ---- Grotto leaf bits: bit-packed in shared memory, written as coalesced bytes ------------------------------------------
+// A thread's 2^dfs leaf control bits are packed into 2^(dfs-5) words (`[word][thread]`, conflict-free writes) and the
+// CTA then writes the unit's 2^unit_bits output bytes together: 16 bytes per lane and store, consecutive lanes on
+// consecutive 16-byte pieces (the per-thread byte stores of the first version put 32 two-byte fragments into 32
+// different sectors per instruction).  The destination may have any alignment (leaf row of a heap-ordered parity
+// tree, grotto_dcf.cuh:98): unaligned head / tail bytes go out as single bytes.
+FSS_D uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+FSS_D void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// bits 0..3 of b -> bytes 0..3 of the result (0 / 1 each)
+FSS_D uint32_t spread4(uint32_t b) { return ((b & 15u) * 0x00204081u) & 0x01010101u; }
+// word W of the unit's bit string: thread W >> (dfs-5), word W & (2^(dfs-5) - 1)
+FSS_D uint32_t bits_word_addr(uint32_t s_bits, uint32_t W, int dfs) {
+  const uint32_t wpt_bits = uint32_t(dfs - 5);
+  return s_bits + (((W & ((1u << wpt_bits) - 1u)) * kEvalAllThreads + (W >> wpt_bits)) << 2);
+}
+FSS_D void write_leaf_bits(uint8_t *dst, uint32_t s_bits, int unit_bits, int dfs, uint32_t tid) {
+  const uint32_t total = 1u << unit_bits, nwords = total >> 5;
+  uint32_t head = uint32_t(-reinterpret_cast<uintptr_t>(dst)) & 15u;
+  if (head > total) head = total;
+  const uint32_t nvec = (total - head) >> 4;
+  for (uint32_t v = tid; v < nvec; v += kEvalAllThreads) {
+    const uint32_t p = head + (v << 4), W = p >> 5;
+    const uint32_t lo = lds_u32(bits_word_addr(s_bits, W, dfs));
+    const uint32_t hi = (W + 1u < nwords) ? lds_u32(bits_word_addr(s_bits, W + 1u, dfs)) : 0u;
+    const uint32_t b = __funnelshift_r(lo, hi, p & 31u);
+    uint4 o;
+    o.x = spread4(b); o.y = spread4(b >> 4); o.z = spread4(b >> 8); o.w = spread4(b >> 12);
+    *reinterpret_cast<uint4 *>(dst + p) = o;
+  }
+  const uint32_t tail0 = head + (nvec << 4);
+  const uint32_t nscalar = head + (total - tail0);  // < 32
+  if (tid < nscalar) {
+    const uint32_t p = tid < head ? tid : tail0 + (tid - head);
+    dst[p] = uint8_t((lds_u32(bits_word_addr(s_bits, p >> 5, dfs)) >> (p & 31u)) & 1u);
   }
 }
 
@@ -416,6 +529,9 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
   const uint32_t s_cw = sp.alloc(uint32_t(ncw + 1) * 32u, true);
   const uint32_t s_bfs = sp.alloc(2u * kEvalAllThreads * 16u, true);
   const uint32_t s_stk = sp.alloc(uint32_t(dfs > 1 ? dfs - 1 : 1) * kEvalAllThreads * 16u, false);
+  // Grotto, dfs >= 5 (n >= 14, every thread active): the unit's leaf bits, packed (write_leaf_bits)
+  const bool packed = MODE == 2 && dfs >= 5;
+  const uint32_t s_bits = packed ? sp.alloc((kEvalAllThreads * 4u) << (dfs - 5), true) : 0u;
 
   const uint64_t upk = A.leaf_count >> A.unit_bits;  // units per key
   const uint64_t total = A.nkeys * upk;
@@ -470,9 +586,10 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
     if (tid < (1 << bt)) {
       blk cur = lds_blk(s_bfs + uint32_t(bt & 1) * (kEvalAllThreads * 16u) + 16u * tid);
       const int lvl0 = du + bt;  // tree level of `cur`
-      const uint64_t out0 = key * A.leaf_count + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
+      const uint64_t out0 = key * A.ys_stride + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
       const uint32_t pairs = 1u << (dfs - 1);
       uint32_t done = 0;  // leaf pairs emitted
+      uint32_t acc = 0;   // Grotto: leaf bits of the current 32-leaf word
       int d = 0;
       while (true) {
         const int lvl = lvl0 + d;
@@ -495,9 +612,17 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
               stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, l, r);
             } else {
               // Grotto: leaf control bits, one byte per leaf (grotto_dcf.cuh:190-194)
-              uint8_t *o = static_cast<uint8_t *>(A.ys) + out0 + 2 * done;  // any alignment (parity trees)
-              o[0] = uint8_t(lsb(l));
-              o[1] = uint8_t(lsb(r));
+              if (packed) {
+                acc |= (lsb(l) | (lsb(r) << 1)) << ((2u * done) & 31u);
+                if ((done & 15u) == 15u) {
+                  sts_u32(s_bits + (((done >> 4) * kEvalAllThreads + uint32_t(tid)) << 2), acc);
+                  acc = 0;
+                }
+              } else {
+                uint8_t *o = static_cast<uint8_t *>(A.ys) + out0 + 2 * done;  // any alignment (parity trees)
+                o[0] = uint8_t(lsb(l));
+                o[1] = uint8_t(lsb(r));
+              }
             }
           }
           ++done;
@@ -513,6 +638,11 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
           ++d;
         }
       }
+    }
+    if (packed) {
+      __syncthreads();
+      write_leaf_bits(static_cast<uint8_t *>(A.ys) + key * A.ys_stride + (leaf0 - A.leaf_begin), s_bits, A.unit_bits, dfs,
+          uint32_t(tid));
     }
   }
 }
@@ -611,7 +741,7 @@ dcf_evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ Ev
       blk cur = lds_blk(slot);
       V u = smem_load_val<G>(P.ga, slot + 16u);
       const int lvl0 = du + bt;
-      const uint64_t out0 = key * A.leaf_count + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
+      const uint64_t out0 = key * A.ys_stride + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
       const uint32_t pairs = 1u << (dfs - 1);
       const blk out_v = ld_blk(A.cws + key * uint64_t(ncw) * 32u + 32u * n + 16u);  // cws[n].v
       uint32_t done = 0;

@@ -68,14 +68,14 @@ point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, int mode) {
   return nullptr;
 }
 #elif FSS_INST_KIND == 2
-template <int G>
+template <int G, int OUT>
 static cudaError_t gen_launch(const KParams &P, const GenArgs &A, const LaunchCfg &c) {
-  return launch_kernel(gen_kernel<FSS_INST_SCHEME, G, kInstPrg>, c, P, A);
+  return launch_kernel(gen_kernel<FSS_INST_SCHEME, G, kInstPrg, OUT>, c, P, A);
 }
-gen_launch_fn CAT3(gen_launcher_, PRGNAME, SCHNAME)(int gk) {
+gen_launch_fn CAT3(gen_launcher_, PRGNAME, SCHNAME)(int gk, int out_mode) {
   switch (gk) {
 #define X(GK) \
-  case GK: return &gen_launch<GK>;
+  case GK: return out_mode ? &gen_launch<GK, 1> : &gen_launch<GK, 0>;
     FOR_EACH_GK(X)
 #undef X
   }

@@ -8,38 +8,76 @@
 namespace fssb200 {
 
 // ---- relayout (point_eval_gpu.cuh:39-91) ------------------------------------------------------------------
-// One warp per key: lanes read the key's 32-byte Cw entries coalesced (lane l -> level l, l+32, ...)
-// and scatter them to the level-major arrays; the control bits are gathered with a ballot.
-__global__ void relayout_kernel(int scheme, int n, int ncw, const uint8_t *__restrict__ cws, blk *__restrict__ cw_s,
-    blk *__restrict__ cw_v, uint32_t *__restrict__ extra, blk *__restrict__ out_cw, uint64_t nkeys) {
-  const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= nkeys) return;
-  const uint64_t k = warp;
-  const uint4 *kc = reinterpret_cast<const uint4 *>(cws + k * uint64_t(ncw) * 32u);
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    uint32_t flag = 0;
-    if (i < n) {
-      const uint4 s = __ldg(kc + 2 * i), v = __ldg(kc + 2 * i + 1);
-      reinterpret_cast<uint4 *>(cw_s)[uint64_t(i) * nkeys + k] = s;
-      if (scheme == FSSB200_SCHEME_DCF) reinterpret_cast<uint4 *>(cw_v)[uint64_t(i) * nkeys + k] = v;
-      flag = (v.x & 0xffu) != 0;  // Dpf::Cw::tr / HalfTreeDpf::Cw::extra (bool at byte 16)
+// Key-major Cw[nkeys][ncw] -> level-major arrays.  One warp per tile of 32 consecutive keys: the tile is read in
+// chunks of 4 levels -- lane = (key-in-group r, 16-byte piece q), 8 adjacent lanes read the 128 contiguous bytes of
+// one key -- into a padded shared-memory slab, then written level by level with lane = key, so every store
+// instruction covers 512 contiguous bytes of cw_s[level] / cw_v[level] (the first version stored 16 bytes per key
+// per level from different warps: half-sector writes, 2.2 TB/s).  The control bits are packed per key into `extra`.
+constexpr int kRlWarps = 8;
+constexpr int kRlLevels = 4;                                  // levels per chunk
+constexpr uint32_t kRlRow = kRlLevels * 32u + 16u;            // slab row stride per key (bytes): conflict-free both ways
+__global__ void __launch_bounds__(kRlWarps * 32) relayout_kernel(int scheme, int n, int ncw,
+    const uint8_t *__restrict__ cws, blk *__restrict__ cw_s, blk *__restrict__ cw_v, uint32_t *__restrict__ extra,
+    blk *__restrict__ out_cw, uint64_t nkeys) {
+  __shared__ __align__(16) uint8_t slab_all[kRlWarps][32 * kRlRow];
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  uint8_t *slab = slab_all[wid];
+  const uint64_t ntiles = (nkeys + 31) >> 5;
+  const bool dcf = scheme == FSSB200_SCHEME_DCF;
+  const bool has_out = scheme != FSSB200_SCHEME_HALFTREE && scheme != FSSB200_SCHEME_VDPF && out_cw;
+  const uint32_t key_bytes = uint32_t(ncw) * 32u;
+  for (uint64_t tile = uint64_t(blockIdx.x) * kRlWarps + wid; tile < ntiles; tile += uint64_t(gridDim.x) * kRlWarps) {
+    const uint64_t k0 = tile * 32, k = k0 + lane;
+    const uint32_t nvalid = nkeys - k0 < 32 ? uint32_t(nkeys - k0) : 32u;
+    uint32_t bits = 0;
+    for (int base = 0; base < ncw; base += kRlLevels) {
+      const uint32_t chunk_bytes = uint32_t(ncw - base < kRlLevels ? ncw - base : kRlLevels) * 32u;
+      __syncwarp();
+      // load: 2 * kRlLevels lanes per key, 32 / (2 * kRlLevels) keys per step
+      constexpr uint32_t kLpk = 2u * kRlLevels;
+      const uint32_t q = lane % kLpk;
+#pragma unroll 4
+      for (uint32_t r = lane / kLpk; r < 32u; r += 32u / kLpk) {
+        if (r < nvalid && q * 16u < chunk_bytes) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(cws + (k0 + r) * key_bytes + uint32_t(base) * 32u) + q);
+          *reinterpret_cast<uint4 *>(slab + r * kRlRow + q * 16u) = v;
+        }
+      }
+      __syncwarp();
+      if (lane < nvalid) {
+#pragma unroll
+        for (int j = 0; j < kRlLevels; ++j) {
+          const int i = base + j;
+          if (i >= ncw) break;
+          const uint4 s = *reinterpret_cast<const uint4 *>(slab + lane * kRlRow + j * 32);
+          const uint4 v = *reinterpret_cast<const uint4 *>(slab + lane * kRlRow + j * 32 + 16);
+          if (i < n) {
+            reinterpret_cast<uint4 *>(cw_s)[uint64_t(i) * nkeys + k] = s;
+            if (dcf) reinterpret_cast<uint4 *>(cw_v)[uint64_t(i) * nkeys + k] = v;
+            // Dpf::Cw::tr / HalfTreeDpf::Cw::extra (bool at byte 16)
+            bits |= uint32_t((v.x & 0xffu) != 0) << (i & 31);
+            if (!dcf && ((i & 31) == 31 || i == n - 1)) {
+              extra[uint64_t(i >> 5) * nkeys + k] = bits;
+              bits = 0;
+            }
+          } else if (has_out) {  // i == n: output correction word
+            reinterpret_cast<uint4 *>(out_cw)[k] = dcf ? v : s;
+          }
+        }
+      }
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0 && scheme != FSSB200_SCHEME_DCF) extra[uint64_t(base >> 5) * nkeys + k] = bits;
-  }
-  if (lane == 0 && scheme != FSSB200_SCHEME_HALFTREE && scheme != FSSB200_SCHEME_VDPF && out_cw) {
-    const uint4 s = __ldg(kc + 2 * n), v = __ldg(kc + 2 * n + 1);
-    reinterpret_cast<uint4 *>(out_cw)[k] = scheme == FSSB200_SCHEME_DCF ? v : s;
   }
 }
 
 cudaError_t launch_relayout(int scheme, int in_bits, int ncw, const uint8_t *cws, blk *cw_s, blk *cw_v,
     uint32_t *extra, blk *out_cw, uint64_t nkeys, cudaStream_t stream) {
-  const uint64_t threads = nkeys * 32;
-  const unsigned blocks = unsigned((threads + 255) / 256);
-  relayout_kernel<<<blocks, 256, 0, stream>>>(scheme, in_bits, ncw, cws, cw_s, cw_v, extra, out_cw, nkeys);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t ntiles = (nkeys + 31) >> 5;
+  const uint64_t want = (ntiles + kRlWarps - 1) / kRlWarps, cap = uint64_t(sms) * 8;
+  const unsigned blocks = unsigned(want < cap ? (want ? want : 1) : cap);
+  relayout_kernel<<<blocks, kRlWarps * 32, 0, stream>>>(scheme, in_bits, ncw, cws, cw_s, cw_v, extra, out_cw, nkeys);
   return cudaGetLastError();
 }
 
@@ -153,15 +191,42 @@ cudaError_t launch_prefix_xor(uint8_t *ys, uint64_t nkeys, uint64_t len, cudaStr
 }
 
 // ---- Grotto parity tree / lookup ------------------------------------------------------------------------------
-__global__ void parity_level_kernel(uint8_t *tree, uint64_t first, uint64_t count) {
-  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const uint64_t j = first + i;
-  tree[j] = tree[2 * j + 1] ^ tree[2 * j + 2];
+// Heap-ordered tree p[j] = p[2j+1] ^ p[2j+2] (grotto_dcf.cuh:100-103): level l occupies bytes [2^l - 1, 2^(l+1) - 1).
+// One CTA takes 2^kParityLevels consecutive nodes of level `bottom` (coalesced byte loads: rows sit at odd offsets)
+// into shared memory and produces its slice of the kParityLevels levels above, so a tree of depth n costs
+// ceil(n / kParityLevels) launches and each node byte is read from HBM once.  grid.y = keys.
+constexpr int kParityThreads = 256;
+__global__ void __launch_bounds__(kParityThreads) parity_levels_kernel(uint8_t *pt, uint64_t key_stride, int bottom) {
+  __shared__ __align__(4) uint8_t buf[2][1 << kParityLevels];
+  uint8_t *tree = pt + uint64_t(blockIdx.y) * key_stride;
+  const int levels = bottom < kParityLevels ? bottom : kParityLevels;  // levels produced by this launch
+  const uint32_t chunk = 1u << levels;                                  // nodes of level `bottom` per CTA
+  const uint64_t node0 = uint64_t(blockIdx.x) * chunk;
+  const uint8_t *src = tree + ((uint64_t(1) << bottom) - 1) + node0;
+  for (uint32_t i = threadIdx.x; i < chunk; i += kParityThreads) buf[0][i] = src[i];
+  __syncthreads();
+  int cur = 0;
+  for (int l = 1; l <= levels; ++l) {
+    const uint32_t cnt = chunk >> l;
+    uint8_t *dst = tree + ((uint64_t(1) << (bottom - l)) - 1) + (node0 >> l);
+    for (uint32_t j = threadIdx.x; j < cnt; j += kParityThreads) {
+      const uint32_t two = *reinterpret_cast<const uint16_t *>(&buf[cur][2 * j]);
+      const uint8_t v = uint8_t((two ^ (two >> 8)) & 0xffu);
+      buf[cur ^ 1][j] = v;
+      dst[j] = v;
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
 }
-cudaError_t launch_parity_level(uint8_t *tree, int level, cudaStream_t stream) {
-  const uint64_t count = uint64_t(1) << level, first = count - 1;
-  parity_level_kernel<<<unsigned((count + 255) / 256), 256, 0, stream>>>(tree, first, count);
+cudaError_t launch_parity_levels(uint8_t *pt, uint64_t key_stride, uint64_t nkeys, int bottom, cudaStream_t stream) {
+  const int levels = bottom < kParityLevels ? bottom : kParityLevels;
+  const uint64_t ctas = (uint64_t(1) << bottom) >> levels;
+  for (uint64_t k0 = 0; k0 < nkeys; k0 += 65535) {  // grid.y limit
+    const uint64_t kn = nkeys - k0 < 65535 ? nkeys - k0 : 65535;
+    parity_levels_kernel<<<dim3(unsigned(ctas), unsigned(kn), 1), kParityThreads, 0, stream>>>(pt + k0 * key_stride,
+        key_stride, bottom);
+  }
   return cudaGetLastError();
 }
 

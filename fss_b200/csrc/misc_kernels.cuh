@@ -13,9 +13,10 @@ cudaError_t launch_relayout(int scheme, int in_bits, int ncw, const uint8_t *cws
 // In-place inclusive prefix XOR over `len` bytes (values 0/1) for each of nkeys rows
 // (grotto_dcf.cuh:160-162).
 cudaError_t launch_prefix_xor(uint8_t *ys, uint64_t nkeys, uint64_t len, cudaStream_t stream);
-// One level of the heap-ordered parity tree: p[j] = p[2j+1] ^ p[2j+2] for the 2^level nodes of
-// that level (grotto_dcf.cuh:100-103).
-cudaError_t launch_parity_level(uint8_t *tree, int level, cudaStream_t stream);
+// Heap-ordered parity trees p[j] = p[2j+1] ^ p[2j+2] (grotto_dcf.cuh:100-103) of nkeys keys, rows key_stride
+// bytes apart: fills the min(bottom, kParityLevels) levels above level `bottom` (whose 2^bottom nodes are present).
+constexpr int kParityLevels = 13;
+cudaError_t launch_parity_levels(uint8_t *pt, uint64_t key_stride, uint64_t nkeys, int bottom, cudaStream_t stream);
 // GrottoDcf::Eval lookup (grotto_dcf.cuh:116-135), one thread per key.
 cudaError_t launch_grotto_lookup(const uint8_t *pt, const uint8_t *xs, uint8_t *ys, uint64_t nkeys, int in_bits,
     int in_bytes, cudaStream_t stream);

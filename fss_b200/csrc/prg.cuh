@@ -49,6 +49,12 @@ struct Prg<kPrgAes> {
   static FSS_HD blk gen1(const PrgKeys &k, const ctx_t &c, const blk s) {
     return aes128_mmo(c, KeyFixed{k.rk[0]}, s);
   }
+  // output block I alone (every block has its own key): lets a caller consume blocks one at a time
+  static constexpr bool kPerBlock = true;
+  template <int I>
+  static FSS_HD blk block(const PrgKeys &k, const ctx_t &c, const blk s) {
+    return aes128_mmo(c, KeyFixed{k.rk[I]}, s);
+  }
 };
 
 // ---- ChaCha (prg/chacha.cuh) ---------------------------------------------------------------------------
@@ -114,6 +120,9 @@ struct Prg<kPrgChaCha> {
     chacha_gen<1>(k, s, o);
     return o[0];
   }
+  static constexpr bool kPerBlock = false;  // one ChaCha block yields all rows
+  template <int I>
+  static FSS_HD blk block(const PrgKeys &, const ctx_t &, const blk s) { return s; }  // never called
 };
 
 }  // namespace fssb200

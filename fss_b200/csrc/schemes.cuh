@@ -63,6 +63,16 @@ struct CwLevelMajor {
   FSS_HD void done_level(int) const {}
 };
 
+// Gen output: entry i of this key's Cw array = {s, v} (32 B).  Key-major direct stores here; the gen kernel
+// uses CwTileOut (kernels.cuh: tiles written by the TMA unit) with the same interface.
+struct CwOutKeyMajor {
+  uint8_t *base;
+  FSS_HD void put(int i, blk s, blk v) const {
+    st_blk(base + 32 * i, s);
+    st_blk(base + 32 * i + 16, v);
+  }
+};
+
 // ---- DPF ------------------------------------------------------------------------------------------------
 // Leaf conversion, dpf.cuh:207-213 / :255-263.
 template <int G>
@@ -105,9 +115,9 @@ FSS_HD blk dpf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename P
 }
 
 // Dpf::Gen, dpf.cuh:93-159.  Writes Cw[n+1] (32 B each, padding zeroed).
-template <int G, int PRG>
+template <int G, int PRG, class Out>
 FSS_HD void dpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
-    blk s0, blk s1, const InVal &a, blk beta, uint8_t *cws) {
+    blk s0, blk s1, const InVal &a, blk beta, const Out &out) {
   typedef Grp<G> GR;
   s0 = clamp(s0);
   s1 = clamp(s1);
@@ -136,13 +146,11 @@ FSS_HD void dpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
     s0 = ns0;
     s1 = ns1;
     s_cw.w |= tl_cw;
-    st_blk(cws + 32 * i, s_cw);
-    st_blk(cws + 32 * i + 16, make_blk(tr_cw, 0, 0, 0));       // :151-153
+    out.put(i, s_cw, make_blk(tr_cw, 0, 0, 0));                // :151-153
   }
   typename GR::V v = GR::add(ga, GR::add(ga, GR::from(ga, beta), GR::neg(ga, GR::from(ga, s0))), GR::from(ga, s1));
   v = GR::cneg(ga, v, t1);                                      // :156-157
-  st_blk(cws + 32 * n, GR::into(ga, v));
-  st_blk(cws + 32 * n + 16, zero_blk());
+  out.put(n, GR::into(ga, v), zero_blk());
 }
 
 // ---- VDPF (vdpf.cuh) -------------------------------------------------------------------------------------
@@ -198,9 +206,9 @@ FSS_HD blk vdpf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename 
 }
 
 // Vdpf::Gen, vdpf.cuh:97-177.  Returns Gen's status (1: t0 == t1, ocw not written).
-template <int G, int PRG>
+template <int G, int PRG, class Out>
 FSS_HD int vdpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n, blk s0,
-    blk s1, const InVal &a, blk beta, uint8_t *cws, blk *cs, blk *ocw) {
+    blk s1, const InVal &a, blk beta, const Out &out, blk *cs, blk *ocw, bool write = true) {
   typedef Grp<G> GR;
   s0 = clamp(s0);
   s1 = clamp(s1);
@@ -228,18 +236,19 @@ FSS_HD int vdpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
     s0 = ns0;
     s1 = ns1;
     s_cw.w |= tl_cw;
-    st_blk(cws + 32 * i, s_cw);
-    st_blk(cws + 32 * i + 16, make_blk(tr_cw, 0, 0, 0));       // vdpf.cuh:147-149
+    out.put(i, s_cw, make_blk(tr_cw, 0, 0, 0));                // vdpf.cuh:147-149
   }
   blk p0[4], p1[4];                                             // :153-157
   b3_xor_hash(K.hash_iv[0], pack_in(a), s0, p0);
   b3_xor_hash(K.hash_iv[0], pack_in(a), s1, p1);
+  if (write) {  // (idle lanes of a ragged tile shadow the last key and write nothing)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) st_blk(cs + j, p0[j] ^ p1[j]);
+    for (int j = 0; j < 4; ++j) st_blk(cs + j, p0[j] ^ p1[j]);
+  }
   if (t0 == t1) return 1;                                       // :160
   typename GR::V v = GR::add(ga, GR::add(ga, GR::from(ga, beta), GR::neg(ga, GR::from(ga, s0))), GR::from(ga, s1));
   v = GR::cneg(ga, v, t1);
-  st_blk(ocw, GR::into(ga, v));
+  if (write) st_blk(ocw, GR::into(ga, v));
   return 0;
 }
 
@@ -293,12 +302,17 @@ FSS_HD blk dcf_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename P
   return GR::into(ga, GR::cneg(ga, acc, party));
 }
 
-// Dcf::Gen, dcf.cuh:108-194.
-template <int G, int PRG>
+// Dcf::Gen, dcf.cuh:108-194.  Per level the reference needs, of the eight PRG blocks {s_l, v_l, s_r, v_r} x 2 parties,
+// only: the two seeds of the kept side, the XOR of the seeds of the lost side, the control-bit sums, and per side
+// D = v1 - v0 (v_cw = -v + D_lose (+ beta), v += -D_keep + sign * v_cw: dcf.cuh:147-160 regrouped; exact in every
+// supported group since all values are canonical).  With a per-block PRG (AES) the blocks are consumed pair by
+// pair into that reduced state -- the first version held all eight blocks and spilled ~90 registers per level.
+template <int G, int PRG, class Out>
 FSS_HD void dcf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n,
-    int pred, blk s0, blk s1, const InVal &a, blk beta, uint8_t *cws) {
+    int pred, blk s0, blk s1, const InVal &a, blk beta, const Out &out) {
   typedef Grp<G> GR;
   typedef typename GR::V V;
+  typedef Prg<PRG> PG;
   s0 = clamp(s0);
   s1 = clamp(s1);
   uint32_t t0 = 0, t1 = 1;
@@ -306,30 +320,47 @@ FSS_HD void dcf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
   const V vbeta = GR::from(ga, clamp(beta));
 #pragma unroll 1
   for (int i = 0; i < n; ++i) {
-    blk g0[4], g1[4];  // {s_l, v_l, s_r, v_r}  (dcf.cuh:122)
-    Prg<PRG>::template gen<4>(K, pc, s0, g0);
-    Prg<PRG>::template gen<4>(K, pc, s1, g1);
     const uint32_t ab = in_bit(a, n - 1 - i);
-    const blk s0l = g0[0], s0r = g0[2], s1l = g1[0], s1r = g1[2];
-    const V v0l = GR::from(ga, clamp(g0[1])), v0r = GR::from(ga, clamp(g0[3]));
-    const V v1l = GR::from(ga, clamp(g1[1])), v1r = GR::from(ga, clamp(g1[3]));
-    blk s_cw = ab ? clamp(s0l ^ s1l) : clamp(s0r ^ s1r);       // :143-145
-    V v_cw = GR::neg(ga, v);                                    // :147
-    if (!ab) {
-      v_cw = GR::add(ga, GR::add(ga, v_cw, v1r), GR::neg(ga, v0r));
-      if (pred == FSSB200_PRED_GT) v_cw = GR::add(ga, v_cw, vbeta);
+    const uint32_t am = 0u - ab;                                // ab = 1: keep right, lose left
+    blk keep0, keep1, lose_x;                                   // kept seeds (packed with t), s0_lose ^ s1_lose
+    uint32_t tl_sum, tr_sum;                                    // lsb(s0l) ^ lsb(s1l), lsb(s0r) ^ lsb(s1r)
+    V d_l, d_r;                                                 // v1l - v0l, v1r - v0r
+    if (PG::kPerBlock) {
+      blk x0 = PG::template block<0>(K, pc, s0), x1 = PG::template block<0>(K, pc, s1);   // s_l
+      tl_sum = lsb(x0) ^ lsb(x1);
+      keep0 = xor_masked(zero_blk(), ~am, x0);
+      keep1 = xor_masked(zero_blk(), ~am, x1);
+      lose_x = xor_masked(zero_blk(), am, x0 ^ x1);
+      x0 = PG::template block<1>(K, pc, s0); x1 = PG::template block<1>(K, pc, s1);       // v_l
+      d_l = GR::add(ga, GR::from(ga, clamp(x1)), GR::neg(ga, GR::from(ga, clamp(x0))));
+      x0 = PG::template block<2>(K, pc, s0); x1 = PG::template block<2>(K, pc, s1);       // s_r
+      tr_sum = lsb(x0) ^ lsb(x1);
+      keep0 = xor_masked(keep0, am, x0);
+      keep1 = xor_masked(keep1, am, x1);
+      lose_x = xor_masked(lose_x, ~am, x0 ^ x1);
+      x0 = PG::template block<3>(K, pc, s0); x1 = PG::template block<3>(K, pc, s1);       // v_r
+      d_r = GR::add(ga, GR::from(ga, clamp(x1)), GR::neg(ga, GR::from(ga, clamp(x0))));
     } else {
-      v_cw = GR::add(ga, GR::add(ga, v_cw, v1l), GR::neg(ga, v0l));
-      if (pred == FSSB200_PRED_LT) v_cw = GR::add(ga, v_cw, vbeta);
+      blk g0[4], g1[4];  // {s_l, v_l, s_r, v_r}  (dcf.cuh:122)
+      PG::template gen<4>(K, pc, s0, g0);
+      PG::template gen<4>(K, pc, s1, g1);
+      tl_sum = lsb(g0[0]) ^ lsb(g1[0]);
+      tr_sum = lsb(g0[2]) ^ lsb(g1[2]);
+      keep0 = ab ? g0[2] : g0[0];
+      keep1 = ab ? g1[2] : g1[0];
+      lose_x = ab ? (g0[0] ^ g1[0]) : (g0[2] ^ g1[2]);
+      d_l = GR::add(ga, GR::from(ga, clamp(g1[1])), GR::neg(ga, GR::from(ga, clamp(g0[1]))));
+      d_r = GR::add(ga, GR::from(ga, clamp(g1[3])), GR::neg(ga, GR::from(ga, clamp(g0[3]))));
     }
+    blk s_cw = clamp(lose_x);                                   // :143-145
+    const V d_lose = ab ? d_l : d_r, d_keep = ab ? d_r : d_l;
+    V v_cw = GR::add(ga, GR::neg(ga, v), d_lose);               // :147-153
+    if ((ab != 0) == (pred == FSSB200_PRED_LT)) v_cw = GR::add(ga, v_cw, vbeta);
     v_cw = GR::cneg(ga, v_cw, t1);                              // :155
-    if (!ab) v = GR::add(ga, GR::add(ga, v, GR::neg(ga, v1l)), v0l);
-    else v = GR::add(ga, GR::add(ga, v, GR::neg(ga, v1r)), v0r);
-    v = GR::add(ga, v, GR::cneg(ga, v_cw, t1));                 // :159-160
-    const uint32_t tl_cw = (lsb(s0l) ^ lsb(s1l) ^ ab ^ 1u) & 1u;
-    const uint32_t tr_cw = (lsb(s0r) ^ lsb(s1r) ^ ab) & 1u;
+    v = GR::add(ga, GR::add(ga, v, GR::neg(ga, d_keep)), GR::cneg(ga, v_cw, t1));  // :157-160
+    const uint32_t tl_cw = (tl_sum ^ ab ^ 1u) & 1u;
+    const uint32_t tr_cw = (tr_sum ^ ab) & 1u;
     const uint32_t tk_cw = ab ? tr_cw : tl_cw;
-    const blk keep0 = ab ? s0r : s0l, keep1 = ab ? s1r : s1l;
     const blk ns0 = xor_masked(clamp(keep0), 0u - t0, s_cw);
     const blk ns1 = xor_masked(clamp(keep1), 0u - t1, s_cw);
     t0 = lsb(keep0) ^ (t0 & tk_cw);
@@ -339,13 +370,11 @@ FSS_HD void dcf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
     s_cw.w |= tl_cw;
     blk v_buf = GR::into(ga, v_cw);
     v_buf.w = (v_buf.w & ~1u) | tr_cw;                          // :187-189
-    st_blk(cws + 32 * i, s_cw);
-    st_blk(cws + 32 * i + 16, v_buf);
+    out.put(i, s_cw, v_buf);
   }
   V vn = GR::add(ga, GR::add(ga, GR::from(ga, s1), GR::neg(ga, GR::from(ga, s0))), GR::neg(ga, v));
   vn = GR::cneg(ga, vn, t1);                                    // :191-193
-  st_blk(cws + 32 * n, zero_blk());
-  st_blk(cws + 32 * n + 16, GR::into(ga, vn));
+  out.put(n, zero_blk(), GR::into(ga, vn));
 }
 
 // ---- Half-Tree DPF ---------------------------------------------------------------------------------------
@@ -398,9 +427,9 @@ FSS_HD blk ht_eval_body(const PrgKeys &K, const GroupArgs &ga, const typename Pr
   return ht_last<G, PRG>(K, ga, pc, party, node, xn, cs, lcw, ocw);
 }
 // HalfTreeDpf::Gen, half_tree_dpf.cuh:68-175.
-template <int G, int PRG>
+template <int G, int PRG, class Out>
 FSS_HD void ht_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Prg<PRG>::ctx_t &pc, int n, blk s0,
-    blk s1, const InVal &a, blk beta, uint8_t *cws, blk *ocw) {
+    blk s1, const InVal &a, blk beta, const Out &out, blk *ocw) {
   typedef Grp<G> GR;
   beta = clamp(beta);
   blk node0 = clamp(s0), node1 = clamp(s1);
@@ -411,8 +440,7 @@ FSS_HD void ht_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Pr
     const blk h0 = ht_hash<PRG>(K, pc, node0), h1 = ht_hash<PRG>(K, pc, node1);
     const uint32_t am = 0u - in_bit(a, n - 1 - i);
     const blk cw = xor_masked(h0 ^ h1, ~am, delta);              // :83-84
-    st_blk(cws + 32 * i, cw);
-    st_blk(cws + 32 * i + 16, zero_blk());
+    out.put(i, cw, zero_blk());
     const uint32_t t0m = 0u - lsb(node0), t1m = 0u - lsb(node1);
     node0 = xor_masked(xor_masked(h0, am, node0), t0m, cw);
     node1 = xor_masked(xor_masked(h1, am, node1), t1m, cw);
@@ -430,8 +458,7 @@ FSS_HD void ht_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename Pr
   const uint32_t lcw1 = (lsb(h0_1) ^ lsb(h1_1) ^ an) & 1u;        // :133
   blk cwn = hcw;
   cwn.w |= lcw0;
-  st_blk(cws + 32 * (n - 1), cwn);
-  st_blk(cws + 32 * (n - 1) + 16, make_blk(lcw1, 0, 0, 0));       // :139-141
+  out.put(n - 1, cwn, make_blk(lcw1, 0, 0, 0));                   // :139-141
   blk leaf0 = an ? h0_1 : h0_0, leaf1 = an ? h1_1 : h1_0;          // packed high||low
   blk leaf_cw = hcw;
   leaf_cw.w |= an ? lcw1 : lcw0;

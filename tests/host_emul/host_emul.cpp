@@ -124,11 +124,11 @@ static void gen_t(const EmuCtx &c, const Bufs &b) {
     const blk beta = b.betas ? b.betas[k] : zero_blk();
     uint8_t *cws = b.cws_out + k * uint64_t(c.ncw) * 32;
     if (c.scheme == FSSB200_SCHEME_DPF || c.scheme == FSSB200_SCHEME_GROTTO)
-      dpf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, cws);
+      dpf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, CwOutKeyMajor{cws});
     else if (c.scheme == FSSB200_SCHEME_DCF)
-      dcf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, c.pred, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, cws);
+      dcf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, c.pred, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, CwOutKeyMajor{cws});
     else
-      ht_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, cws, &b.ocws_out[k]);
+      ht_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, beta, CwOutKeyMajor{cws}, &b.ocws_out[k]);
   }
 }
 
@@ -154,7 +154,7 @@ static void vdpf_gen_t(const EmuCtx &c, const Bufs &b) {
     const auto pc = lane_ctx<PRG>(k);
     const InVal a = load_in(b.xs + k * c.in_bytes, c.in_bytes);
     b.status[k] = vdpf_gen_body<G, PRG>(c.keys, c.ga, pc, c.n, b.s0s[2 * k], b.s0s[2 * k + 1], a, b.betas[k],
-        b.cws_out + k * uint64_t(c.ncw) * 32, b.cs_out + 4 * k, b.ocws_out + k);
+        CwOutKeyMajor{b.cws_out + k * uint64_t(c.ncw) * 32}, b.cs_out + 4 * k, b.ocws_out + k);
   }
 }
 

@@ -162,6 +162,9 @@ def test_random_batches(dev, orc, scheme, n, group, mod, prg, nkeys):
     ("dpf", 18, "bytes", "aes128_mmo", 3), ("dpf", 10, "u64", "aes128_mmo", 9), ("dpf", 5, "u128", "chacha", 70),
     ("halftree", 18, "u64", "aes128_mmo", 2), ("halftree", 9, "bytes", "chacha", 5), ("halftree", 1, "u32", "aes128_mmo", 4),
     ("grotto", 18, "bytes", "aes128_mmo", 2), ("grotto", 11, "bytes", "chacha", 5), ("dpf", 1, "bytes", "aes128_mmo", 3),
+    # Grotto, bit-packed leaf output (n >= 14) into rows of every alignment (parity trees are 2N-1 bytes apart)
+    ("grotto", 14, "bytes", "aes128_mmo", 5), ("grotto", 15, "bytes", "chacha", 3), ("grotto", 19, "bytes", "aes128_mmo", 3),
+    ("grotto", 13, "bytes", "aes128_mmo", 4), ("grotto", 1, "bytes", "aes128_mmo", 2), ("grotto", 20, "bytes", "chacha", 2),
     ("dpf", 19, "u128", "chacha", 2), ("dcf", 17, "u128", "aes128_mmo", 2), ("dcf", 10, "u64", "chacha", 5),
     ("dcf", 3, "bytes", "aes128_mmo", 9), ("dcf", 12, "u32", "aes128_mmo", 3),
 ])
@@ -187,7 +190,7 @@ def test_evalall_vs_oracle(dev, orc, scheme, n, group, prg, nkeys):
     if scheme == "grotto":
         t = ctx.grotto_expand(1, T(s0s[:, 1], dev), cws)
         assert np.array_equal(N(t, np.uint8), orc.grotto_expand(p, 1, s0s[:, 1], oc, threads=8))
-        if n <= 12:
+        if n <= 20:
             pt = ctx.grotto_preprocess(1, T(s0s[:, 1], dev), cws)
             want = orc.grotto_preprocess(p, 1, s0s[:, 1], oc)
             assert np.array_equal(N(pt, np.uint8), want)

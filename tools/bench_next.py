@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--keys", type=int, default=1 << 22)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_next.json"))
+    ap.add_argument("--sections", default="f1,f2,f3,f4", help="comma-separated subset of f1,f2,f3,f4 (A/B runs)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -85,117 +86,122 @@ def main():
         return s0s, alphas, betas, xs
 
     K = args.keys
+    sections = set(args.sections.split(","))
     # ---- f-1: Gen ---------------------------------------------------------------------------------------------------
-    for name, scheme, n, group, wide, blocks, k in (
-            ("gen_dpf_n32_bytes", "dpf", 32, "bytes", False, 4 * 32, K),
-            ("gen_dcf_n64_u127", "dcf", 64, "u128", True, 8 * 64, K // 2),
-            ("gen_halftree_n32_bytes", "halftree", 32, "bytes", False, 2 * 32 + 2, K)):
-        ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
-        s0s, alphas, betas, xs = seeds_for(k, wide)
-        al = ctx.in_tensor(alphas, dev)
-        ms = timed(lambda: ctx.gen(s0s, al, betas))
-        out_bytes = k * ctx.ncw * 32
-        rows[name] = {"keys": k, "ms": ms, "keys_per_s": k / (ms * 1e-3), "aes_blocks_per_key": blocks,
-                      "aes_blocks_per_s": k * blocks / (ms * 1e-3), "lsu_roofline_frac": lsu(k, blocks, ms),
-                      "hbm_write_gbs": out_bytes / (ms * 1e-3) / 1e9, "hbm_frac": out_bytes / (ms * 1e-3) / 1e9 / hbm_peak}
-        del ctx, s0s, betas
-        torch.cuda.empty_cache()
+    if "f1" in sections:
+        for name, scheme, n, group, wide, blocks, k in (
+                ("gen_dpf_n32_bytes", "dpf", 32, "bytes", False, 4 * 32, K),
+                ("gen_dcf_n64_u127", "dcf", 64, "u128", True, 8 * 64, K // 2),
+                ("gen_halftree_n32_bytes", "halftree", 32, "bytes", False, 2 * 32 + 2, K)):
+            ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
+            s0s, alphas, betas, xs = seeds_for(k, wide)
+            al = ctx.in_tensor(alphas, dev)
+            ms = timed(lambda: ctx.gen(s0s, al, betas))
+            out_bytes = k * ctx.ncw * 32
+            rows[name] = {"keys": k, "ms": ms, "keys_per_s": k / (ms * 1e-3), "aes_blocks_per_key": blocks,
+                          "aes_blocks_per_s": k * blocks / (ms * 1e-3), "lsu_roofline_frac": lsu(k, blocks, ms),
+                          "hbm_write_gbs": out_bytes / (ms * 1e-3) / 1e9, "hbm_frac": out_bytes / (ms * 1e-3) / 1e9 / hbm_peak}
+            del ctx, s0s, betas
+            torch.cuda.empty_cache()
 
     # ---- f-2: relayout + level-major evaluation ---------------------------------------------------------------------------
-    ctx = fss_b200.Context("dpf", 32, "bytes", prg="aes128_mmo")
-    s0s, alphas, betas, xs = seeds_for(K)
-    cws = ctx.gen(s0s, alphas, betas)
-    seeds0 = s0s[:, 0].contiguous()
-    ms = timed(lambda: ctx.relayout(cws))
-    lay = ctx.relayout(cws)
-    rd = cws.numel() * 4
-    wr = sum(t.numel() * 4 for t in lay if t is not None)
-    rows["relayout_dpf_n32"] = {"keys": K, "ms": ms, "read_bytes": rd, "write_bytes": wr,
-                                "note": "includes the torch.empty / torch.zeros of the output arrays (allocator hit)",
-                                "hbm_gbs": (rd + wr) / (ms * 1e-3) / 1e9, "hbm_frac": (rd + wr) / (ms * 1e-3) / 1e9 / hbm_peak}
-    ys = torch.empty((K, 4), dtype=torch.int32, device=dev)
-    ms = timed(lambda: ctx.eval_levelmajor(0, seeds0, lay, xs, out=ys))
-    rows["eval_levelmajor_dpf_n32"] = {"keys": K, "ms": ms, "evals_per_s": K / (ms * 1e-3),
-                                       "lsu_roofline_frac": lsu(K, 32, ms)}
-    ms = timed(lambda: ctx.eval(0, seeds0, cws, xs, out=ys))
-    rows["eval_keymajor_dpf_n32"] = {"keys": K, "ms": ms, "evals_per_s": K / (ms * 1e-3),
-                                     "lsu_roofline_frac": lsu(K, 32, ms)}
-    del cws, lay, ys, s0s, betas, seeds0
-    torch.cuda.empty_cache()
+    if "f2" in sections:
+        ctx = fss_b200.Context("dpf", 32, "bytes", prg="aes128_mmo")
+        s0s, alphas, betas, xs = seeds_for(K)
+        cws = ctx.gen(s0s, alphas, betas)
+        seeds0 = s0s[:, 0].contiguous()
+        ms = timed(lambda: ctx.relayout(cws))
+        lay = ctx.relayout(cws)
+        rd = cws.numel() * 4
+        wr = sum(t.numel() * 4 for t in lay if t is not None)
+        rows["relayout_dpf_n32"] = {"keys": K, "ms": ms, "read_bytes": rd, "write_bytes": wr,
+                                    "note": "includes the torch.empty / torch.zeros of the output arrays (allocator hit)",
+                                    "hbm_gbs": (rd + wr) / (ms * 1e-3) / 1e9, "hbm_frac": (rd + wr) / (ms * 1e-3) / 1e9 / hbm_peak}
+        ys = torch.empty((K, 4), dtype=torch.int32, device=dev)
+        ms = timed(lambda: ctx.eval_levelmajor(0, seeds0, lay, xs, out=ys))
+        rows["eval_levelmajor_dpf_n32"] = {"keys": K, "ms": ms, "evals_per_s": K / (ms * 1e-3),
+                                           "lsu_roofline_frac": lsu(K, 32, ms)}
+        ms = timed(lambda: ctx.eval(0, seeds0, cws, xs, out=ys))
+        rows["eval_keymajor_dpf_n32"] = {"keys": K, "ms": ms, "evals_per_s": K / (ms * 1e-3),
+                                         "lsu_roofline_frac": lsu(K, 32, ms)}
+        del cws, lay, ys, s0s, betas, seeds0
+        torch.cuda.empty_cache()
 
     # ---- f-3: DCF EvalAll, Half-Tree EvalAll, Grotto --------------------------------------------------------------------------
-    for name, scheme, n, group, blocks, k in (
-            ("evalall_dcf_n24_u127", "dcf", 24, "u128", 4.0, 16),
-            ("evalall_dcf_n24_bytes", "dcf", 24, "bytes", 4.0, 16),
-            ("evalall_halftree_n28_bytes", "halftree", 28, "bytes", 1.5, 4),
-            ("evalall_dpf_n28_bytes", "dpf", 28, "bytes", 2.0, 4)):
-        ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
+    if "f3" in sections:
+        for name, scheme, n, group, blocks, k in (
+                ("evalall_dcf_n24_u127", "dcf", 24, "u128", 4.0, 16),
+                ("evalall_dcf_n24_bytes", "dcf", 24, "bytes", 4.0, 16),
+                ("evalall_halftree_n28_bytes", "halftree", 28, "bytes", 1.5, 4),
+                ("evalall_dpf_n28_bytes", "dpf", 28, "bytes", 2.0, 4)):
+            ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
+            s0s, alphas, betas, xs = seeds_for(k)
+            alphas = alphas & ((1 << n) - 1)
+            r = ctx.gen(s0s, alphas, betas)
+            cws, ocws = r if scheme == "halftree" else (r, None)
+            seeds0 = s0s[:, 0].contiguous()
+            out = torch.empty((k, 1 << n, 4), dtype=torch.int32, device=dev)
+            ms = timed(lambda: ctx.eval_all(0, seeds0, cws, ocws, out=out), max(3, args.iters // 2), 2)
+            leaves = k * (1 << n)
+            rows[name] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3), "aes_blocks_per_leaf": blocks,
+                          "lsu_roofline_frac": lsu(leaves, blocks, ms), "hbm_write_gbs": leaves * 16 / (ms * 1e-3) / 1e9}
+            del out, cws, ctx
+            torch.cuda.empty_cache()
+        n, k = 26, 16
+        ctx = fss_b200.Context("grotto", n, prg="aes128_mmo")
         s0s, alphas, betas, xs = seeds_for(k)
         alphas = alphas & ((1 << n) - 1)
-        r = ctx.gen(s0s, alphas, betas)
-        cws, ocws = r if scheme == "halftree" else (r, None)
+        cws = ctx.gen(s0s, alphas)
         seeds0 = s0s[:, 0].contiguous()
-        out = torch.empty((k, 1 << n, 4), dtype=torch.int32, device=dev)
-        ms = timed(lambda: ctx.eval_all(0, seeds0, cws, ocws, out=out), max(3, args.iters // 2), 2)
         leaves = k * (1 << n)
-        rows[name] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3), "aes_blocks_per_leaf": blocks,
-                      "lsu_roofline_frac": lsu(leaves, blocks, ms), "hbm_write_gbs": leaves * 16 / (ms * 1e-3) / 1e9}
-        del out, cws, ctx
+        ms = timed(lambda: ctx.grotto_expand(0, seeds0, cws), 5, 2)
+        rows["grotto_expand_n26"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
+                                     "aes_blocks_per_leaf": 2.0, "lsu_roofline_frac": lsu(leaves, 2.0, ms)}
+        ms = timed(lambda: ctx.eval_all(0, seeds0, cws), 5, 2)
+        rows["grotto_evalall_n26"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
+                                      "note": "leaf-bit expansion + in-place prefix-XOR scan (grotto_dcf.cuh:151-163)",
+                                      "lsu_roofline_frac": lsu(leaves, 2.0, ms)}
+        ms = timed(lambda: ctx.grotto_preprocess(0, seeds0, cws), 5, 2)
+        rows["grotto_preprocess_n26"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
+                                         "note": "expansion + heap-ordered parity tree of 2N-1 bytes (grotto_dcf.cuh:94-104)",
+                                         "lsu_roofline_frac": lsu(leaves, 2.0, ms)}
+        pt = ctx.grotto_preprocess(0, seeds0, cws)
+        q = 1 << 22
+        qx = (rand_i32((k, q // k)) & ((1 << n) - 1))
+        # one lookup call evaluates one x per key row; time a batch of rows by repeating the parity tree rows
+        ms = timed(lambda: ctx.grotto_lookup(pt, qx[:, 0].contiguous()), 5, 2)
+        rows["grotto_lookup_n26"] = {"keys": k, "ms": ms, "note": "GrottoDcf::Eval (tree lookup, grotto_dcf.cuh:116-135), one x per key; "
+                                     "launch-latency bound at this batch size"}
+        del pt, cws, ctx
         torch.cuda.empty_cache()
-    n, k = 26, 16
-    ctx = fss_b200.Context("grotto", n, prg="aes128_mmo")
-    s0s, alphas, betas, xs = seeds_for(k)
-    alphas = alphas & ((1 << n) - 1)
-    cws = ctx.gen(s0s, alphas)
-    seeds0 = s0s[:, 0].contiguous()
-    leaves = k * (1 << n)
-    ms = timed(lambda: ctx.grotto_expand(0, seeds0, cws), 5, 2)
-    rows["grotto_expand_n26"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
-                                 "aes_blocks_per_leaf": 2.0, "lsu_roofline_frac": lsu(leaves, 2.0, ms)}
-    ms = timed(lambda: ctx.eval_all(0, seeds0, cws), 5, 2)
-    rows["grotto_evalall_n26"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
-                                  "note": "leaf-bit expansion + in-place prefix-XOR scan (grotto_dcf.cuh:151-163)",
-                                  "lsu_roofline_frac": lsu(leaves, 2.0, ms)}
-    ms = timed(lambda: ctx.grotto_preprocess(0, seeds0, cws), 5, 2)
-    rows["grotto_preprocess_n26"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
-                                     "note": "expansion + heap-ordered parity tree of 2N-1 bytes (grotto_dcf.cuh:94-104)",
-                                     "lsu_roofline_frac": lsu(leaves, 2.0, ms)}
-    pt = ctx.grotto_preprocess(0, seeds0, cws)
-    q = 1 << 22
-    qx = (rand_i32((k, q // k)) & ((1 << n) - 1))
-    # one lookup call evaluates one x per key row; time a batch of rows by repeating the parity tree rows
-    ms = timed(lambda: ctx.grotto_lookup(pt, qx[:, 0].contiguous()), 5, 2)
-    rows["grotto_lookup_n26"] = {"keys": k, "ms": ms, "note": "GrottoDcf::Eval (tree lookup, grotto_dcf.cuh:116-135), one x per key; "
-                                 "launch-latency bound at this batch size"}
-    del pt, cws, ctx
-    torch.cuda.empty_cache()
 
     # ---- f-4: VDPF ----------------------------------------------------------------------------------------------------------
-    k = min(K, 1 << 21)
-    ctx = fss_b200.Context("vdpf", 32, "bytes", prg="aes128_mmo")
-    s0s, alphas, betas, xs = seeds_for(k)
-    vcws, vcs, vocws, _st = ctx.vdpf_gen(s0s, alphas, betas)
-    seeds0 = s0s[:, 0].contiguous()
-    ms = timed(lambda: ctx.vdpf_eval(0, seeds0, vcws, vcs, vocws, xs))
-    rows["vdpf_eval_n32"] = {"keys": k, "ms": ms, "evals_per_s": k / (ms * 1e-3),
-                             "note": "n AES blocks for the walk + 2 Blake3 compressions for the proof share per evaluation; "
-                                     "the fraction counts the AES lookups only",
-                             "lsu_roofline_frac_aes_only": lsu(k, 32, ms)}
-    ms = timed(lambda: ctx.vdpf_gen(s0s, alphas, betas))
-    rows["vdpf_gen_n32"] = {"keys": k, "ms": ms, "keys_per_s": k / (ms * 1e-3)}
-    del vcws, vcs, vocws, ctx
-    torch.cuda.empty_cache()
-    n, k = 24, 8
-    ctx = fss_b200.Context("vdpf", n, "bytes", prg="aes128_mmo")
-    s0s, alphas, betas, xs = seeds_for(k)
-    alphas = alphas & ((1 << n) - 1)
-    vcws, vcs, vocws, _st = ctx.vdpf_gen(s0s, alphas, betas)
-    seeds0 = s0s[:, 0].contiguous()
-    ms = timed(lambda: ctx.vdpf_eval_all(0, seeds0, vcws, vcs, vocws), 3, 2)
-    leaves = k * (1 << n)
-    rows["vdpf_evalall_n24"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
-                                "note": "tree expansion (2 AES blocks per leaf) + per-leaf Blake3 + the sequential proof chain "
-                                        "(vdpf.cuh:294-342); includes the torch.empty of the outputs"}
+    if "f4" in sections:
+        k = min(K, 1 << 21)
+        ctx = fss_b200.Context("vdpf", 32, "bytes", prg="aes128_mmo")
+        s0s, alphas, betas, xs = seeds_for(k)
+        vcws, vcs, vocws, _st = ctx.vdpf_gen(s0s, alphas, betas)
+        seeds0 = s0s[:, 0].contiguous()
+        ms = timed(lambda: ctx.vdpf_eval(0, seeds0, vcws, vcs, vocws, xs))
+        rows["vdpf_eval_n32"] = {"keys": k, "ms": ms, "evals_per_s": k / (ms * 1e-3),
+                                 "note": "n AES blocks for the walk + 2 Blake3 compressions for the proof share per evaluation; "
+                                         "the fraction counts the AES lookups only",
+                                 "lsu_roofline_frac_aes_only": lsu(k, 32, ms)}
+        ms = timed(lambda: ctx.vdpf_gen(s0s, alphas, betas))
+        rows["vdpf_gen_n32"] = {"keys": k, "ms": ms, "keys_per_s": k / (ms * 1e-3)}
+        del vcws, vcs, vocws, ctx
+        torch.cuda.empty_cache()
+        n, k = 24, 8
+        ctx = fss_b200.Context("vdpf", n, "bytes", prg="aes128_mmo")
+        s0s, alphas, betas, xs = seeds_for(k)
+        alphas = alphas & ((1 << n) - 1)
+        vcws, vcs, vocws, _st = ctx.vdpf_gen(s0s, alphas, betas)
+        seeds0 = s0s[:, 0].contiguous()
+        ms = timed(lambda: ctx.vdpf_eval_all(0, seeds0, vcws, vcs, vocws), 3, 2)
+        leaves = k * (1 << n)
+        rows["vdpf_evalall_n24"] = {"keys": k, "in_bits": n, "ms": ms, "leaves_per_s": leaves / (ms * 1e-3),
+                                    "note": "tree expansion (2 AES blocks per leaf) + per-leaf Blake3 + the sequential proof chain "
+                                            "(vdpf.cuh:294-342); includes the torch.empty of the outputs"}
 
     txt = json.dumps(res)
     print(txt, flush=True)
