@@ -5,6 +5,8 @@
 // microbenchmarks that give the roofline denominators.
 #include "misc_kernels.cuh"
 
+#include <cstring>
+
 namespace fssb200 {
 
 // ---- relayout (point_eval_gpu.cuh:39-91) ------------------------------------------------------------------
@@ -320,8 +322,110 @@ __global__ void __launch_bounds__(1024, 1) microbench_kernel(uint32_t *sink, uin
   if (acc == 0x12345678u) sink[0] = acc;  // keeps the chains alive
 }
 
+
+// ---- lookup-path microbenchmarks: do texture fetches (TEX pipe) or cached global loads add lookup bandwidth on top of
+// the shared-memory pipe?  NLDS conflict-free ld.shared.u32 + NTEX tex1Dfetch<uint32_t> (256-entry table, per-lane
+// data-dependent index) + NLDG ld.global.nc (same table) per iteration, all independent chains.
+template <int NLDS, int NTEX, int NLDG>
+__global__ void __launch_bounds__(1024, 1)
+lookup_mix_kernel(uint32_t *sink, cudaTextureObject_t tex, const uint32_t *__restrict__ gtbl) {
+  __shared__ uint32_t tbl[32 * 64];
+  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) tbl[i] = i * 2654435761u;
+  __syncthreads();
+  constexpr int N = NLDS + NTEX + NLDG;
+  uint32_t a[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = threadIdx.x * 7u + j * 13u;
+  const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(tbl)) + (threadIdx.x & 31u) * 4u;
+#pragma unroll 1
+  for (int it = 0; it < kMbIters; ++it) {
+#pragma unroll
+    for (int j = 0; j < NLDS; ++j) {
+      uint32_t v;
+      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + uint32_t(j) * 128u));
+      a[j] ^= v;
+    }
+#pragma unroll
+    for (int j = 0; j < NTEX; ++j) a[NLDS + j] = tex1Dfetch<uint32_t>(tex, int(a[NLDS + j] & 255u));
+#pragma unroll
+    for (int j = 0; j < NLDG; ++j) a[NLDS + NTEX + j] = __ldg(gtbl + (a[NLDS + NTEX + j] & 255u));
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) acc ^= a[j];
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+template <int NLDS, int NTEX, int NLDG>
+static float time_lookup_mix(dim3 grid, dim3 block, uint32_t *sink, cudaTextureObject_t tex, const uint32_t *gtbl,
+    cudaError_t *err) {
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(t0);
+    lookup_mix_kernel<NLDS, NTEX, NLDG><<<grid, block>>>(sink, tex, gtbl);
+    cudaEventRecord(t1);
+    *err = cudaEventSynchronize(t1);
+    if (*err != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return best;
+}
+
+// kinds 7..12: 7 = TEX only (4), 8 = 8 LDS + 4 TEX, 9 = 8 LDS + 2 TEX, 10 = LDG only (4), 11 = 8 LDS + 2 LDG, 12 = 8 LDS (same harness)
+static int run_lookup_mix(int kind, double *ops_per_s) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint32_t host[256];
+  for (int i = 0; i < 256; ++i) host[i] = (uint32_t(i) * 2654435761u) ^ 0x5bd1e995u;
+  uint32_t *buf = nullptr;  // [0, 1 KiB): sink, [1 KiB, 2 KiB): the table
+  cudaError_t e = cudaMalloc(&buf, 2048);
+  if (e != cudaSuccess) return int(e);
+  uint32_t *gtbl = buf + 256;
+  cudaMemcpy(gtbl, host, 1024, cudaMemcpyHostToDevice);
+  cudaResourceDesc rd;
+  memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeLinear;
+  rd.res.linear.devPtr = gtbl;
+  rd.res.linear.desc = cudaCreateChannelDesc<uint32_t>();
+  rd.res.linear.sizeInBytes = 1024;
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof(td));
+  td.readMode = cudaReadModeElementType;
+  cudaTextureObject_t tex = 0;
+  e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+  if (e != cudaSuccess) {
+    cudaFree(buf);
+    return int(e);
+  }
+  const dim3 grid = dim3(static_cast<unsigned>(sms) * 2, 1, 1), block = dim3(1024, 1, 1);
+  float ms = 0;
+  int n = 0;
+  switch (kind) {
+    case 7: ms = time_lookup_mix<0, 4, 0>(grid, block, buf, tex, gtbl, &e); n = 4; break;
+    case 8: ms = time_lookup_mix<8, 4, 0>(grid, block, buf, tex, gtbl, &e); n = 12; break;
+    case 9: ms = time_lookup_mix<8, 2, 0>(grid, block, buf, tex, gtbl, &e); n = 10; break;
+    case 10: ms = time_lookup_mix<0, 0, 4>(grid, block, buf, tex, gtbl, &e); n = 4; break;
+    case 11: ms = time_lookup_mix<8, 0, 2>(grid, block, buf, tex, gtbl, &e); n = 10; break;
+    default: ms = time_lookup_mix<8, 0, 0>(grid, block, buf, tex, gtbl, &e); n = 8; break;
+  }
+  cudaDestroyTextureObject(tex);
+  cudaFree(buf);
+  if (e != cudaSuccess) return int(e);
+  *ops_per_s = double(grid.x) * block.x * double(kMbIters) * n / (double(ms) * 1e-3);
+  return 0;
+}
+
 int run_microbench(int kind, double *ops_per_s) {
-  if (kind < 0 || kind > 6) return FSSB200_EINVAL;
+  if (kind < 0 || kind > 12) return FSSB200_EINVAL;
+  if (kind >= 7) return run_lookup_mix(kind, ops_per_s);
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
