@@ -484,8 +484,11 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
     const uint64_t cap = uint64_t(c->sm_count) * 2;
     cfg.grid = dim3(unsigned(units < cap ? units : cap));
     // cw copies + two breadth buffers + DFS stack (+ slack for alignment)
-    cfg.smem = size_t(c->ncw + 1) * 48 + 2 * threads * node_bytes +
-        size_t(pl.dfs_bits > 1 ? pl.dfs_bits - 1 : 1) * threads * node_bytes + 64 +
+    // (16-byte leaves: the cooperative bottom stage trades one stack level for frontier tiles: 64 B per thread, half of them in the breadth buffers)
+    const bool coop = mode != 2 && mode != 3 && pl.breadth_bits >= 5 && pl.dfs_bits >= 3;
+    const int nstk = pl.dfs_bits - (coop ? 2 : 1);
+    cfg.smem = size_t(c->ncw + 1) * 48 + 2 * threads * node_bytes + size_t(nstk > 1 ? nstk : 1) * threads * node_bytes + 64 +
+        (coop ? size_t(threads) * 32 + 16 : 0) +
         (mode == 2 && pl.dfs_bits >= 5 ? (size_t(threads) * 4) << (pl.dfs_bits - 5) : 0);  // Grotto: packed leaf bits
   }
   c->launches++;

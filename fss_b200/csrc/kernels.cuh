@@ -528,7 +528,12 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
   // scratch: per-level correction words {cwl, cwr}, two breadth buffers, the DFS stack
   const uint32_t s_cw = sp.alloc(uint32_t(ncw + 1) * 32u, true);
   const uint32_t s_bfs = sp.alloc(2u * kEvalAllThreads * 16u, true);
-  const uint32_t s_stk = sp.alloc(uint32_t(dfs > 1 ? dfs - 1 : 1) * kEvalAllThreads * 16u, false);
+  // leaves of 16 B: cooperative bottom stage (see phase 2) when every warp is full and the thread sub-tree has >= 8 leaves
+  const bool coop = MODE != 2 && bt >= 5 && dfs >= 3;
+  const int nstk = coop ? dfs - 2 : dfs - 1;
+  const uint32_t s_stk = sp.alloc(uint32_t(nstk > 1 ? nstk : 1) * kEvalAllThreads * 16u, false);
+  // frontier tiles of the bottom stage, 2 KB per warp: warps 0..7 reuse s_bfs (dead in phase 2), warps 8..15 get s_fr1
+  const uint32_t s_fr1 = coop ? sp.alloc((kEvalAllThreads / 2) * 64u, true) : 0u;  // 64 B (four nodes) per thread
   // Grotto, dfs >= 5 (n >= 14, every thread active): the unit's leaf bits, packed (write_leaf_bits)
   const bool packed = MODE == 2 && dfs >= 5;
   const uint32_t s_bits = packed ? sp.alloc((kEvalAllThreads * 4u) << (dfs - 5), true) : 0u;
@@ -583,47 +588,113 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
       __syncthreads();
     }
     // ---- phase 2: per-thread depth-first over dfs levels ----
-    if (tid < (1 << bt)) {
-      blk cur = lds_blk(s_bfs + uint32_t(bt & 1) * (kEvalAllThreads * 16u) + 16u * tid);
+    // Only TWO node-expansion sites per instantiation (internal node, bottom node): three copies of the AES pair
+    // (43 KB of SASS) fall out of the 32 KB instruction cache and cost 5 % (measured, profiles/r01_evalall_coop.md).
+    blk cur = {0u, 0u, 0u, 0u};
+    if (tid < (1 << bt)) cur = lds_blk(s_bfs + uint32_t(bt & 1) * (kEvalAllThreads * 16u) + 16u * tid);
+    if (coop) __syncthreads();  // the frontier tiles of warps 0..7 reuse the breadth buffers
+    if (MODE != 2 && tid < (1 << bt)) {
+      // Leaves (16 B).  coop: the depth-first walk stops one level above the bottom nodes and parks them -- four per
+      // thread, i.e. one 8-leaf sub-tree -- in the warp's frontier tile; the warp then turns the 128 parked nodes into
+      // leaves with the lanes re-mapped so that 4 adjacent lanes write one full 128-byte line (8 lines per STG.256
+      // instead of 32; the scattered form cost 34 LSU wavefronts per store, profiles/r01_ncu_full.md).
+      // !coop (tiny domains): every thread turns its own bottom node into two leaves.
       const int lvl0 = du + bt;  // tree level of `cur`
+      const uint32_t lane = uint32_t(tid) & 31u;
+      const uint64_t out0 = key * A.ys_stride + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
+      const int dint = coop ? dfs - 2 : dfs - 1;  // internal nodes live at depths < dint (+ depth dint itself when coop)
+      const uint32_t fr = !coop ? 0u : (tid < kEvalAllThreads / 2 ? s_bfs + (uint32_t(tid) >> 5) * 2048u
+                                                                  : s_fr1 + ((uint32_t(tid) >> 5) - kEvalAllThreads / 64) * 2048u);
+      const uint32_t total = 1u << dint;  // coop: nodes at depth dfs-2 (two bottom nodes each); else bottom nodes
+      uint32_t cnt = 0;
+      int d = 0;
+      while (true) {
+        if (d < dint || coop) {
+          const int lvl = lvl0 + d;
+          blk l, r;
+          if (half) ht_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), l, r);
+          else dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          if (d < dint) {
+            sts_blk(s_stk + (uint32_t(d) * kEvalAllThreads + tid) * 16u, r);  // slot of depth d+1
+            cur = l;
+            ++d;
+            continue;
+          }
+          // coop, d == dfs-2: l, r are bottom nodes 2h, 2h+1 of the thread's current 8-leaf sub-tree -> tile slot
+          // (i, lane), XOR-swizzled so that the lane-major writes and the re-mapped reads are both conflict-free
+          const uint32_t h = cnt & 1u;
+          sts_blk(fr + (((2u * h) << 5) + (lane ^ (4u * h))) * 16u, l);
+          sts_blk(fr + (((2u * h + 1u) << 5) + (lane ^ (4u * h + 2u))) * 16u, r);
+          ++cnt;
+          if (h == 0u) {  // the right sibling at depth dfs-2 is on top of the stack
+            cur = lds_blk(s_stk + (uint32_t(d - 1) * kEvalAllThreads + tid) * 16u);
+            continue;
+          }
+          __syncwarp();
+        }
+        // bottom stage: nodes at tree level n-1 -> two leaves each
+        const uint32_t passes = coop ? 4u : 1u;
+#pragma unroll 1
+        for (uint32_t p = 0; p < passes; ++p) {
+          blk node = cur;
+          uint64_t o = out0 + 2u * cnt;
+          if (coop) {
+            const uint32_t idx = (p << 5) + lane, owner = idx >> 2, sub = idx & 3u;
+            node = lds_blk(fr + ((sub << 5) + (owner ^ (2u * sub))) * 16u);
+            o = out0 + (int64_t(int32_t(owner) - int32_t(lane)) << dfs) + 8u * ((cnt >> 1) - 1u) + 2u * sub;
+          }
+          const int lb = n - 1;
+          if (MODE == 1) {
+            const blk cwl = lds_blk(s_cw + 32u * lb), ex = lds_blk(s_cw + 32u * lb + 16u);
+            const blk ocw = ld_blk(A.ocws + key);
+            const blk y0 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), node, 0u, cwl, cwl.w & 1u, ocw);
+            const blk y1 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), node, 1u, cwl, uint32_t((ex.x & 0xffu) != 0), ocw);
+            stg_blk2(static_cast<blk *>(A.ys) + o, y0, y1);
+          } else {
+            blk l, r;
+            dpf_expand<PRG>(P.keys, pc, node, lds_blk(s_cw + 32u * lb), lds_blk(s_cw + 32u * lb + 16u), l, r);
+            if (MODE == 0) {
+              const blk ocw = lds_blk(s_cw + 32u * n);
+              stg_blk2(static_cast<blk *>(A.ys) + o, dpf_leaf<G>(P.ga, uint32_t(A.party), l, ocw),
+                  dpf_leaf<G>(P.ga, uint32_t(A.party), r, ocw));
+            } else {
+              stg_blk2(static_cast<blk *>(A.ys) + o, l, r);  // MODE 4: packed (s | t) leaves
+            }
+          }
+        }
+        if (coop) __syncwarp();  // the tile is rewritten by the next sub-tree
+        else ++cnt;
+        if (cnt == total) break;
+        // depth of the pending right sibling: cnt counts finished nodes at depth dint
+        d = dint - (__ffs(int(cnt)) - 1);
+        cur = lds_blk(s_stk + (uint32_t(d - 1) * kEvalAllThreads + tid) * 16u);
+      }
+    }
+    if (MODE == 2 && tid < (1 << bt)) {
+      // Grotto: leaf control bits.  Two expansion sites on purpose: at the bottom site only the clamp bits of the two
+      // children are live, so most of the last AES round is dead code there.
+      const int lvl0 = du + bt;
       const uint64_t out0 = key * A.ys_stride + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
       const uint32_t pairs = 1u << (dfs - 1);
       uint32_t done = 0;  // leaf pairs emitted
-      uint32_t acc = 0;   // Grotto: leaf bits of the current 32-leaf word
+      uint32_t acc = 0;   // leaf bits of the current 32-leaf word
       int d = 0;
       while (true) {
         const int lvl = lvl0 + d;
         if (d == dfs - 1) {
-          // bottom: node at tree level n-1 -> leaves 2*done, 2*done+1 of this thread
-          if (MODE == 1) {
-            const blk cwl = lds_blk(s_cw + 32u * lvl), ex = lds_blk(s_cw + 32u * lvl + 16u);
-            const blk ocw = ld_blk(A.ocws + key);
-            const blk y0 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), cur, 0u, cwl, cwl.w & 1u, ocw);
-            const blk y1 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), cur, 1u, cwl, uint32_t((ex.x & 0xffu) != 0), ocw);
-            stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, y0, y1);
-          } else {
-            blk l, r;
-            dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
-            if (MODE == 0) {
-              const blk ocw = lds_blk(s_cw + 32u * n);
-              stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, dpf_leaf<G>(P.ga, uint32_t(A.party), l, ocw),
-                  dpf_leaf<G>(P.ga, uint32_t(A.party), r, ocw));
-            } else if (MODE == 4) {
-              stg_blk2(static_cast<blk *>(A.ys) + out0 + 2 * done, l, r);
-            } else {
-              // Grotto: leaf control bits, one byte per leaf (grotto_dcf.cuh:190-194)
-              if (packed) {
-                acc |= (lsb(l) | (lsb(r) << 1)) << ((2u * done) & 31u);
-                if ((done & 15u) == 15u) {
-                  sts_u32(s_bits + (((done >> 4) * kEvalAllThreads + uint32_t(tid)) << 2), acc);
-                  acc = 0;
-                }
-              } else {
-                uint8_t *o = static_cast<uint8_t *>(A.ys) + out0 + 2 * done;  // any alignment (parity trees)
-                o[0] = uint8_t(lsb(l));
-                o[1] = uint8_t(lsb(r));
-              }
+          blk l, r;
+          dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          // one byte per leaf (grotto_dcf.cuh:190-194)
+          if (packed) {
+            acc |= (lsb(l) | (lsb(r) << 1)) << ((2u * done) & 31u);
+            if ((done & 15u) == 15u) {
+              sts_u32(s_bits + (((done >> 4) * kEvalAllThreads + uint32_t(tid)) << 2), acc);
+              acc = 0;
             }
+          } else {
+            uint8_t *o = static_cast<uint8_t *>(A.ys) + out0 + 2 * done;  // any alignment (parity trees)
+            o[0] = uint8_t(lsb(l));
+            o[1] = uint8_t(lsb(r));
           }
           ++done;
           if (done == pairs) break;
@@ -631,8 +702,7 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
           cur = lds_blk(s_stk + (uint32_t(d - 1) * kEvalAllThreads + tid) * 16u);
         } else {
           blk l, r;
-          if (half) ht_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), l, r);
-          else dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
           sts_blk(s_stk + (uint32_t(d) * kEvalAllThreads + tid) * 16u, r);  // slot of depth d+1
           cur = l;
           ++d;
