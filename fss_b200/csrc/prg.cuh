@@ -55,6 +55,11 @@ struct Prg<kPrgAes> {
   static FSS_HD blk block(const PrgKeys &k, const ctx_t &c, const blk s) {
     return aes128_mmo(c, KeyFixed{k.rk[I]}, s);
   }
+  // output block i, i warp-uniform at run time: lets a caller LOOP over the blocks of a node instead of inlining one
+  // AES copy per block (7 KB of SASS each; the instruction cache holds 32 KB)
+  static FSS_HD blk block_rt(const PrgKeys &k, const ctx_t &c, int i, const blk s) {
+    return aes128_mmo(c, KeyFixed{k.rk[i]}, s);
+  }
 };
 
 // ---- ChaCha (prg/chacha.cuh) ---------------------------------------------------------------------------
@@ -123,6 +128,7 @@ struct Prg<kPrgChaCha> {
   static constexpr bool kPerBlock = false;  // one ChaCha block yields all rows
   template <int I>
   static FSS_HD blk block(const PrgKeys &, const ctx_t &, const blk s) { return s; }  // never called
+  static FSS_HD blk block_rt(const PrgKeys &, const ctx_t &, int, const blk s) { return s; }  // never called
 };
 
 }  // namespace fssb200
