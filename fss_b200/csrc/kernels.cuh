@@ -527,6 +527,7 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
   const int du = n - A.unit_bits;
   // scratch: per-level correction words {cwl, cwr}, two breadth buffers, the DFS stack
   const uint32_t s_cw = sp.alloc(uint32_t(ncw + 1) * 32u, true);
+  const uint32_t s_trm = sp.alloc(16u, true);  // tr_cw bits of levels 0..63 (phase 2 reads cwl only, see below)
   const uint32_t s_bfs = sp.alloc(2u * kEvalAllThreads * 16u, true);
   // leaves of 16 B: cooperative bottom stage (see phase 2) when every warp is full and the thread sub-tree has >= 8 leaves
   const bool coop = MODE != 2 && bt >= 5 && dfs >= 3;
@@ -554,6 +555,11 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
         if (!half) cr.w = (cs.w & ~1u) | uint32_t(__ldg(kc + 32 * i + 16) != 0);
         sts_blk(s_cw + 32u * i, cs);
         sts_blk(s_cw + 32u * i + 16u, half ? ld_blk(kc + 32 * i + 16) : cr);
+      }
+      if (!half && tid < 64) {  // n <= 40: warps 0 and 1 cover every level
+        const uint32_t f = tid < ncw ? uint32_t(__ldg(kc + 32 * tid + 16) != 0) : 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
+        if ((tid & 31) == 0) sts_u32(s_trm + 4u * (uint32_t(tid) >> 5), m);
       }
       __syncthreads();
     }
@@ -606,14 +612,26 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
       const uint32_t fr = !coop ? 0u : (tid < kEvalAllThreads / 2 ? s_bfs + (uint32_t(tid) >> 5) * 2048u
                                                                   : s_fr1 + ((uint32_t(tid) >> 5) - kEvalAllThreads / 64) * 2048u);
       const uint32_t total = 1u << dint;  // coop: nodes at depth dfs-2 (two bottom nodes each); else bottom nodes
+      // bottom-level correction words and the output correction word stay in registers for the whole unit: as
+      // broadcast LDS.128 they cost 4 wavefronts each, 12 per bottom pass next to its 320 table-lookup wavefronts
+      const blk bcw0 = lds_blk(s_cw + 32u * uint32_t(n - 1)), bcw1 = lds_blk(s_cw + 32u * uint32_t(n - 1) + 16u);
+      const uint64_t trm = half ? 0ull : (uint64_t(lds_u32(s_trm + 4u)) << 32) | lds_u32(s_trm);
+      const blk bocw = MODE == 0 ? lds_blk(s_cw + 32u * n) : (MODE == 1 ? ld_blk(A.ocws + key) : blk{0u, 0u, 0u, 0u});
       uint32_t cnt = 0;
       int d = 0;
       while (true) {
         if (d < dint || coop) {
           const int lvl = lvl0 + d;
           blk l, r;
-          if (half) ht_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), l, r);
-          else dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          if (half) {
+            ht_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), l, r);
+          } else {
+            // one broadcast LDS.128 (4 wavefronts) instead of two: cwr = cwl with tr_cw in the clamp bit
+            const blk cwl = lds_blk(s_cw + 32u * lvl);
+            blk cwr = cwl;
+            cwr.w = (cwl.w & ~1u) | (uint32_t(trm >> lvl) & 1u);
+            dpf_expand<PRG>(P.keys, pc, cur, cwl, cwr, l, r);
+          }
           if (d < dint) {
             sts_blk(s_stk + (uint32_t(d) * kEvalAllThreads + tid) * 16u, r);  // slot of depth d+1
             cur = l;
@@ -643,20 +661,16 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
             node = lds_blk(fr + ((sub << 5) + (owner ^ (2u * sub))) * 16u);
             o = out0 + (int64_t(int32_t(owner) - int32_t(lane)) << dfs) + 8u * ((cnt >> 1) - 1u) + 2u * sub;
           }
-          const int lb = n - 1;
           if (MODE == 1) {
-            const blk cwl = lds_blk(s_cw + 32u * lb), ex = lds_blk(s_cw + 32u * lb + 16u);
-            const blk ocw = ld_blk(A.ocws + key);
-            const blk y0 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), node, 0u, cwl, cwl.w & 1u, ocw);
-            const blk y1 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), node, 1u, cwl, uint32_t((ex.x & 0xffu) != 0), ocw);
+            const blk y0 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), node, 0u, bcw0, bcw0.w & 1u, bocw);
+            const blk y1 = ht_last<G, PRG>(P.keys, P.ga, pc, uint32_t(A.party), node, 1u, bcw0, uint32_t((bcw1.x & 0xffu) != 0), bocw);
             stg_blk2(static_cast<blk *>(A.ys) + o, y0, y1);
           } else {
             blk l, r;
-            dpf_expand<PRG>(P.keys, pc, node, lds_blk(s_cw + 32u * lb), lds_blk(s_cw + 32u * lb + 16u), l, r);
+            dpf_expand<PRG>(P.keys, pc, node, bcw0, bcw1, l, r);
             if (MODE == 0) {
-              const blk ocw = lds_blk(s_cw + 32u * n);
-              stg_blk2(static_cast<blk *>(A.ys) + o, dpf_leaf<G>(P.ga, uint32_t(A.party), l, ocw),
-                  dpf_leaf<G>(P.ga, uint32_t(A.party), r, ocw));
+              stg_blk2(static_cast<blk *>(A.ys) + o, dpf_leaf<G>(P.ga, uint32_t(A.party), l, bocw),
+                  dpf_leaf<G>(P.ga, uint32_t(A.party), r, bocw));
             } else {
               stg_blk2(static_cast<blk *>(A.ys) + o, l, r);  // MODE 4: packed (s | t) leaves
             }
@@ -678,12 +692,15 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
       const uint32_t pairs = 1u << (dfs - 1);
       uint32_t done = 0;  // leaf pairs emitted
       uint32_t acc = 0;   // leaf bits of the current 32-leaf word
+      const uint64_t trm = (uint64_t(lds_u32(s_trm + 4u)) << 32) | lds_u32(s_trm);
+      // bottom-level correction words in registers (a broadcast LDS.128 is 4 wavefronts)
+      const blk bcw0 = lds_blk(s_cw + 32u * uint32_t(n - 1)), bcw1 = lds_blk(s_cw + 32u * uint32_t(n - 1) + 16u);
       int d = 0;
       while (true) {
         const int lvl = lvl0 + d;
         if (d == dfs - 1) {
           blk l, r;
-          dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          dpf_expand<PRG>(P.keys, pc, cur, bcw0, bcw1, l, r);
           // one byte per leaf (grotto_dcf.cuh:190-194)
           if (packed) {
             acc |= (lsb(l) | (lsb(r) << 1)) << ((2u * done) & 31u);
@@ -702,7 +719,10 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
           cur = lds_blk(s_stk + (uint32_t(d - 1) * kEvalAllThreads + tid) * 16u);
         } else {
           blk l, r;
-          dpf_expand<PRG>(P.keys, pc, cur, lds_blk(s_cw + 32u * lvl), lds_blk(s_cw + 32u * lvl + 16u), l, r);
+          const blk cwl = lds_blk(s_cw + 32u * lvl);
+          blk cwr = cwl;
+          cwr.w = (cwl.w & ~1u) | (uint32_t(trm >> lvl) & 1u);
+          dpf_expand<PRG>(P.keys, pc, cur, cwl, cwr, l, r);
           sts_blk(s_stk + (uint32_t(d) * kEvalAllThreads + tid) * 16u, r);  // slot of depth d+1
           cur = l;
           ++d;
