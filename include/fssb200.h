@@ -314,8 +314,10 @@ int fssb200_prg_gen(const fssb200_ctx *ctx, const void *seeds, void *out, int mu
 uint64_t fssb200_ctx_launch_count(const fssb200_ctx *ctx);
 /* Integer-pipe / shared-memory issue-rate microbenchmarks used for the roofline
  * denominator.  kind: 0 = LOP3 chain, 1 = IMAD chain, 2 = LOP3+IMAD
- * mixed, 3 = conflict-free LDS.32, 4 = PRMT, 5 = IDP.4A, 6 = PRMT+IDP.4A mixed.  Returns ops (or lookups) per second
- * through *ops_per_s. */
+ * mixed, 3 = conflict-free LDS.32, 4 = PRMT, 5 = IDP.4A, 6 = PRMT+IDP.4A mixed; lookup-path probes (per-lane
+ * data-dependent index into a 256-entry table): 7 = texture fetches, 8 / 9 = 8 LDS + 4 / 2 texture fetches, 10 = cached
+ * read-only global loads, 11 = 8 LDS + 2 global loads, 12 = 8 LDS.  Returns ops (or lookups) per second through
+ * *ops_per_s. */
 int fssb200_microbench(int device, int kind, double *ops_per_s);
 
 #ifdef __cplusplus
