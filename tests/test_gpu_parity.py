@@ -167,6 +167,9 @@ def test_random_batches(dev, orc, scheme, n, group, mod, prg, nkeys):
     ("grotto", 13, "bytes", "aes128_mmo", 4), ("grotto", 1, "bytes", "aes128_mmo", 2), ("grotto", 20, "bytes", "chacha", 2),
     ("dpf", 19, "u128", "chacha", 2), ("dcf", 17, "u128", "aes128_mmo", 2), ("dcf", 10, "u64", "chacha", 5),
     ("dcf", 3, "bytes", "aes128_mmo", 9), ("dcf", 12, "u32", "aes128_mmo", 3),
+    # cooperative bottom stage of the leaf kernels (n >= 12): shortest walks (dfs = 3, 4, 5), both PRGs, every leaf mode
+    ("dpf", 12, "u32", "aes128_mmo", 5), ("halftree", 12, "u64", "chacha", 3), ("halftree", 13, "bytes", "aes128_mmo", 4),
+    ("dpf", 14, "u128", "chacha", 2), ("dpf", 13, "bytes", "aes128_mmo", 150), ("dpf", 11, "u64", "aes128_mmo", 7),
 ])
 def test_evalall_vs_oracle(dev, orc, scheme, n, group, prg, nkeys):
     p = Params(scheme=scheme, in_bits=n, group=group, prg=prg, hash_key=HASH_KEY_BENCH)
