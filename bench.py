@@ -347,11 +347,34 @@ def run_own_arm(args) -> None:
         dt = max_over_ranks((time.perf_counter() - t0) / e_steps)
         if not torch.equal(h_ys, ys.cpu()):
             raise SystemExit("bench: host-buffer path disagrees with the device path")
+        pack_threads = ctx.host_pack_threads(local)
+        cws_bytes = nkeys * ctx.packed_row_bytes(local) if pack_threads else h_cws.numel() * 4
         e2e = {"value": world * nkeys / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e_steps,
-               "h2d_bytes_per_step": h_seeds.numel() * 4 + h_cws.numel() * 4 + h_xs.numel() * 4,
+               "h2d_bytes_per_step": h_seeds.numel() * 4 + cws_bytes + h_xs.numel() * 4,
                "d2h_bytes_per_step": h_ys.numel() * 4,
-               "api": "fssb200_eval_host (pinned host buffers, 2^18-key chunks, 2 streams), wall clock around the "
-                      "blocking call"}
+               "host_pack_threads": pack_threads,
+               "api": "fssb200_eval_host (reference-layout keys in pinned host buffers, 2^18-key chunks, 2 streams), wall "
+                      "clock around the blocking call" + (
+                          f"; {pack_threads} host threads strip the 15 padding bytes of each 32-byte Dpf::Cw into pinned "
+                          "staging while the previous chunk is in flight, so 17 B per level cross PCIe" if pack_threads
+                          else "; keys copied as they are (not enough host cores per rank to pack faster than PCIe)")}
+        if pack_threads:
+            # the same call with packing switched off: the reference layout crosses PCIe as it is
+            os.environ["FSSB200_PACK_THREADS"] = "0"
+            ctx_d = fss_b200.Context("dpf", N_BITS, "bytes", prg="aes128_mmo")
+            ctx_d.reserve_host(1 << 18, local)
+            del os.environ["FSSB200_PACK_THREADS"]
+            for _ in range(2):
+                ctx_d.eval(0, h_seeds, h_cws, h_xs, out=h_ys)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                ctx_d.eval(0, h_seeds, h_cws, h_xs, out=h_ys)
+            torch.cuda.synchronize()
+            dt_d = max_over_ranks((time.perf_counter() - t0) / e_steps)
+            e2e["direct_copy"] = {"value": world * nkeys / dt_d, "unit": UNIT, "ms_per_step": dt_d * 1e3,
+                                  "h2d_bytes_per_step": h_seeds.numel() * 4 + h_cws.numel() * 4 + h_xs.numel() * 4}
+            ctx_d.close()
         # the same keys in the compact level-major layout (fssb200_relayout: 16 B + 1 bit per level instead of the
         # 32-byte Dpf::Cw) through fssb200_eval_levelmajor_host
         lay = ctx.relayout(cws)

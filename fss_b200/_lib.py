@@ -67,6 +67,10 @@ SYMBOLS = {
     "fssb200_eval_all_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _SZ, _U64, _U64]),
     "fssb200_gen_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
     "fssb200_eval_levelmajor_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
+    "fssb200_packed_row_bytes": (_SZ, [_VP]),
+    "fssb200_ctx_host_pack_threads": (_I, [_VP]),
+    "fssb200_pack_rows": (_I, [_VP, _VP, _VP, _SZ]),
+    "fssb200_eval_packed": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_prg_gen": (_I, [_VP, _VP, _VP, _I, _SZ, _VP]),
     "fssb200_ctx_launch_count": (_U64, [_VP]),
     "fssb200_microbench": (_I, [_I, _I, C.POINTER(C.c_double)]),

@@ -196,6 +196,42 @@ class Context:
                     "fssb200_eval_host")
         return ys
 
+    # ---- packed rows (compact key format, include/fssb200.h) ------------------------------------------------------
+    def packed_row_bytes(self, dev: int = 0) -> int:
+        return int(L.lib.fssb200_packed_row_bytes(self.handle(dev)))
+
+    def host_pack_threads(self, dev: int = 0) -> int:
+        """Threads the host entry point packs rows with (0: reference layout copied as it is)."""
+        return int(L.lib.fssb200_ctx_host_pack_threads(self.handle(dev)))
+
+    def pack_rows(self, cws: torch.Tensor, dev: int = 0) -> torch.Tensor:
+        """Reference-layout keys (N, ncw, 8) int32 on the HOST -> packed rows (N, row_bytes) uint8 on the host."""
+        if cws.device.type != "cpu":
+            raise RuntimeError("pack_rows converts host arrays")
+        cws = cws.contiguous()
+        n = cws.shape[0]
+        rb = self.packed_row_bytes(dev)
+        if rb == 0:
+            raise ValueError(f"scheme {self.scheme!r} has no packed key format")
+        rows = torch.empty((n, rb), dtype=torch.uint8)
+        L.check(L.lib.fssb200_pack_rows(self.handle(dev), _ptr(cws), _ptr(rows), n), "fssb200_pack_rows")
+        return rows
+
+    def eval_packed(self, party: int, seeds: torch.Tensor, rows: torch.Tensor, xs: IntLike,
+                    ocws: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        seeds, rows = seeds.contiguous(), rows.contiguous()
+        n = seeds.shape[0]
+        on_gpu, dev = self._dev(seeds)
+        if not on_gpu:
+            raise RuntimeError("eval_packed takes device tensors (the host entry point packs internally)")
+        x = self.in_tensor(xs, seeds.device)
+        ocws = None if ocws is None else ocws.contiguous()
+        ys = out if out is not None else torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_eval_packed(self.handle(dev), party, _ptr(seeds), _ptr(rows), _ptr(ocws), _ptr(x),
+                                              _ptr(ys), n, self._stream(dev)), "fssb200_eval_packed")
+        return ys
+
     # ---- EvalAll (dpf.cuh:232-303, half_tree_dpf.cuh:246-354, grotto_dcf.cuh:151-163) --------------------------
     def eval_all(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, ocws: Optional[torch.Tensor] = None,
                  leaf_begin: int = 0, leaf_count: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:

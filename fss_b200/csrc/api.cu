@@ -4,10 +4,21 @@
 // geometry, host-buffer staging.  There is no CPU evaluation path in this library: every entry
 // point either launches sm_100a kernels or returns an error code.
 #include <atomic>
+#include <condition_variable>
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no libcuda link dependency)
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "dispatch.h"
 #include "misc_kernels.cuh"
@@ -15,11 +26,87 @@
 
 using namespace fssb200;
 
+// Worker threads of the host entry points (row packing).  parallel_for blocks until [0, total) is done; the caller
+// takes blocks too.
+class PackPool {
+ public:
+  explicit PackPool(int nworkers) {
+    for (int i = 0; i < nworkers; ++i) th_.emplace_back([this] { worker(); });
+  }
+  ~PackPool() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+    }
+    cv_start_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  int workers() const { return int(th_.size()); }
+  void parallel_for(size_t total, size_t grain, const std::function<void(size_t, size_t)> &fn) {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      fn_ = &fn;
+      total_ = total;
+      grain_ = grain ? grain : 1;
+      next_.store(0);
+      active_ = int(th_.size());
+      ++gen_;
+    }
+    cv_start_.notify_all();
+    drain(fn);
+    std::unique_lock<std::mutex> l(mu_);
+    cv_done_.wait(l, [this] { return active_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void drain(const std::function<void(size_t, size_t)> &fn) {
+    for (;;) {
+      const size_t b = next_.fetch_add(grain_);
+      if (b >= total_) break;
+      fn(b, b + grain_ < total_ ? b + grain_ : total_);
+    }
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(size_t, size_t)> *fn;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_start_.wait(l, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        fn = fn_;
+      }
+      drain(*fn);
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--active_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_start_, cv_done_;
+  const std::function<void(size_t, size_t)> *fn_ = nullptr;
+  size_t total_ = 0, grain_ = 1;
+  std::atomic<size_t> next_{0};
+  uint64_t gen_ = 0;
+  int active_ = 0;
+  bool stop_ = false;
+};
+
+constexpr int kStageSlots = 3;
 struct HostArena {
   size_t chunk_keys = 0;
   size_t bytes_per_set = 0;
   uint8_t *dev[2] = {nullptr, nullptr};
   cudaStream_t stream[2] = {nullptr, nullptr};
+  // packed host path of fssb200_eval_host (DPF / Half-Tree): pinned staging for the packed rows of a chunk
+  uint8_t *stage[kStageSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr};
+  bool stage_busy[kStageSlots] = {false, false, false};
+  PackPool *pool = nullptr;
 };
 
 struct fssb200_ctx {
@@ -51,7 +138,12 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_rows_tensor_map(uint8_t out[128], const void *rows, size_t nkeys, size_t row_bytes);
 int make_cw_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, int ncw) {
+  return make_rows_tensor_map(out, cws, nkeys, size_t(ncw) * 32u);
+}
+// 2-D byte tensor [nkeys][row_bytes], box 32 rows x 64 B, SWIZZLE_64B (CwTileT / CwTileOut in kernels.cuh)
+int make_rows_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, size_t row_bytes) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -63,8 +155,8 @@ int make_cw_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, int ncw)
   }
   static_assert(sizeof(CUtensorMap) == 128, "PointArgs::tmap size");
   alignas(64) CUtensorMap m;
-  const cuuint64_t gdim[2] = {cuuint64_t(ncw) * 32u, cuuint64_t(nkeys)};
-  const cuuint64_t gstride[1] = {cuuint64_t(ncw) * 32u};
+  const cuuint64_t gdim[2] = {cuuint64_t(row_bytes), cuuint64_t(nkeys)};
+  const cuuint64_t gstride[1] = {cuuint64_t(row_bytes)};
   const cuuint32_t box[2] = {64u, 32u};
   const cuuint32_t estride[2] = {1u, 1u};
   const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(cws), gdim, gstride, box, estride,
@@ -121,7 +213,7 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
   LaunchCfg cfg;
   cfg.stream = s;
   if (c->p.prg == FSSB200_PRG_AES128_MMO) {
-    const unsigned threads = mode == 1 ? 1024u : (mode == 5 ? 768u : unsigned(kPointThreads));
+    const unsigned threads = mode == 1 ? 1024u : (mode >= 5 ? 768u : unsigned(kPointThreads));
     const uint64_t want = (n + threads - 1) / threads;
     cfg.grid = dim3(unsigned(want < uint64_t(c->sm_count) ? (want ? want : 1) : c->sm_count));
     cfg.block = dim3(threads);
@@ -133,7 +225,7 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
     cfg.block = dim3(256);
     // staged correction words: one slab per warp (L = 4, or L = 2 in mode 1)
     cfg.smem = (mode == 0 || mode == 1) ? 8 * (mode == 1 ? CwStagedWarp<2>::kWarpBytes : CwStagedWarp<4>::kWarpBytes) + 32
-        : (mode == 4 || mode == 5) ? 8 * CwTile::kWarpBytes + 8 * 16 + 512 + 32 : 0;
+        : (mode >= 4) ? 8 * CwTile::kWarpBytes + 8 * 16 + 512 + 32 : 0;
   }
   return cfg;
 }
@@ -172,6 +264,53 @@ EvalAllPlan plan_evalall(int n, int thread_bits = kEvalAllThreadBits) {
 
 int check_common(const fssb200_ctx *c) { return c ? 0 : FSSB200_EINVAL; }
 
+}  // namespace
+
+namespace {
+// rows [k0, k1): ncw x {16 B s} + 16 B of flag bits (bit i = byte 16 of entry i != 0, i < 128).
+// STREAM: non-temporal stores for the whole row, flag word included -- a regular store into a line that is still
+// being assembled in a write-combining buffer forces a flush + read-for-ownership and cost 3.5x (measured).
+template <bool STREAM>
+void pack_rows_range_t(const uint8_t *src, uint8_t *dst, size_t k0, size_t k1, int ncw) {
+  const size_t in_row = size_t(ncw) * 32u, out_row = size_t(ncw) * 16u + 16u;
+  const int nflag = ncw < 128 ? ncw : 128;
+  for (size_t k = k0; k < k1; ++k) {
+    const uint8_t *r = src + k * in_row;
+    uint8_t *o = dst + k * out_row;
+    uint64_t f0 = 0, f1 = 0;
+    for (int i = 0; i < nflag && i < 64; ++i) f0 |= uint64_t(r[32 * i + 16] != 0) << i;
+    for (int i = 64; i < nflag; ++i) f1 |= uint64_t(r[32 * i + 16] != 0) << (i - 64);
+#if defined(__SSE2__)
+    for (int i = 0; i < ncw; ++i) {
+      const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(r + 32 * i));
+      if (STREAM) _mm_stream_si128(reinterpret_cast<__m128i *>(o + 16 * i), v);
+      else _mm_storeu_si128(reinterpret_cast<__m128i *>(o + 16 * i), v);
+    }
+    const __m128i fv = _mm_set_epi64x(static_cast<long long>(f1), static_cast<long long>(f0));
+    if (STREAM) _mm_stream_si128(reinterpret_cast<__m128i *>(o + size_t(ncw) * 16u), fv);
+    else _mm_storeu_si128(reinterpret_cast<__m128i *>(o + size_t(ncw) * 16u), fv);
+#else
+    for (int i = 0; i < ncw; ++i) std::memcpy(o + 16 * i, r + 32 * i, 16);
+    const uint64_t f[2] = {f0, f1};
+    std::memcpy(o + size_t(ncw) * 16u, f, 16);
+#endif
+  }
+#if defined(__SSE2__)
+  if (STREAM) _mm_sfence();
+#endif
+}
+void pack_rows_range(const uint8_t *src, uint8_t *dst, size_t k0, size_t k1, int ncw, bool stream_stores) {
+  if (stream_stores) pack_rows_range_t<true>(src, dst, k0, k1, ncw);
+  else pack_rows_range_t<false>(src, dst, k0, k1, ncw);
+}
+int usable_cpus() {
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) return CPU_COUNT(&set);
+#endif
+  const unsigned h = std::thread::hardware_concurrency();
+  return h ? int(h) : 1;
+}
 }  // namespace
 
 extern "C" {
@@ -267,7 +406,12 @@ void fssb200_ctx_destroy(fssb200_ctx *c) {
       if (c->arena.dev[i]) cudaFree(c->arena.dev[i]);
       if (c->arena.stream[i]) cudaStreamDestroy(c->arena.stream[i]);
     }
+    for (int i = 0; i < kStageSlots; ++i) {
+      if (c->arena.stage[i]) cudaFreeHost(c->arena.stage[i]);
+      if (c->arena.stage_ev[i]) cudaEventDestroy(c->arena.stage_ev[i]);
+    }
   }
+  delete c->arena.pool;
   delete c;
 }
 
@@ -324,11 +468,13 @@ int fssb200_gen(const fssb200_ctx *cc, const void *s0s, const void *alphas, cons
 // ---- point eval ---------------------------------------------------------------------------------------------------
 static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const void *seeds, const void *cws,
     const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream, bool level_major, const void *cw_s,
-    const void *cw_v, const void *extra, const void *out_cw, const void *vdpf_cs = nullptr, void *vdpf_pis = nullptr) {
+    const void *cw_v, const void *extra, const void *out_cw, const void *vdpf_cs = nullptr, void *vdpf_pis = nullptr,
+    bool packed = false) {
   fssb200_ctx *c = const_cast<fssb200_ctx *>(cc);
   if (int rc = check_common(c)) return rc;
   const int scheme = c->p.scheme;
   if (scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;  // Grotto: EvalAll / Preprocess+Eval only
+  if (packed && scheme != FSSB200_SCHEME_DPF && scheme != FSSB200_SCHEME_HALFTREE) return FSSB200_ESCHEME;
   if (want_scheme >= 0 && want_scheme != scheme) return FSSB200_ESCHEME;
   if (scheme == FSSB200_SCHEME_VDPF) {  // only through fssb200_vdpf_eval
     if (want_scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
@@ -351,7 +497,7 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   if (!aligned16(seeds) || !aligned16(ys) || !aligned16(ocws)) return FSSB200_EALIGN;
   if (reinterpret_cast<uintptr_t>(xs) % c->p.in_bytes) return FSSB200_EALIGN;
   if (nkeys == 0) return 0;
-  const int mode = level_major ? 2 : c->point_mode;
+  const int mode = level_major ? 2 : (packed ? 6 : c->point_mode);
   point_launch_fn fn = get_point_launcher(scheme, c->gk, c->p.prg, mode);
   if (!fn) return FSSB200_EGROUP;
   DeviceGuard g(c->p.device);
@@ -374,9 +520,10 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   a.in_bytes = c->p.in_bytes;
   a.party = party;
   a.vmask = c->vmask;
-  if (mode == 4 || mode == 5) {
+  if (mode >= 4) {
     if (nkeys >> 31) return FSSB200_EINVAL;  // TMA coordinates are 32-bit
-    if (int rc = make_cw_tensor_map(a.tmap, cws, nkeys, c->ncw)) return rc;
+    if (int rc = make_rows_tensor_map(a.tmap, cws, nkeys, mode == 6 ? size_t(c->ncw) * 16u + 16u : size_t(c->ncw) * 32u))
+      return rc;
   }
   const LaunchCfg cfg = point_cfg(c, nkeys, static_cast<cudaStream_t>(stream), mode);
   c->launches++;
@@ -405,6 +552,40 @@ int fssb200_halftree_eval(const fssb200_ctx *c, int party, const void *seeds, co
 int fssb200_eval_levelmajor(const fssb200_ctx *c, int party, const void *seeds, const void *cw_s, const void *cw_v,
     const void *extra, const void *out_cw, const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream) {
   return eval_impl(c, -1, party, seeds, nullptr, ocws, xs, ys, nkeys, stream, true, cw_s, cw_v, extra, out_cw);
+}
+
+// ---- packed rows (compact key format of the schemes whose Cw is {int4 s; bool flag} + 15 bytes of padding) ---------
+size_t fssb200_packed_row_bytes(const fssb200_ctx *c) {
+  if (!c || (c->p.scheme != FSSB200_SCHEME_DPF && c->p.scheme != FSSB200_SCHEME_HALFTREE)) return 0;
+  return size_t(c->ncw) * 16u + 16u;
+}
+
+
+int fssb200_ctx_host_pack_threads(const fssb200_ctx *c) {
+  return (c && c->arena.pool && c->arena.stage[0]) ? c->arena.pool->workers() + 1 : 0;
+}
+
+int fssb200_pack_rows(const fssb200_ctx *c, const void *cws, void *rows, size_t nkeys) {
+  if (int rc = check_common(c)) return rc;
+  if (!fssb200_packed_row_bytes(c)) return FSSB200_ESCHEME;
+  if (!cws || !rows) return FSSB200_EINVAL;
+  const bool al = aligned16(rows);
+  PackPool *pool = c->arena.pool;
+  const uint8_t *src = static_cast<const uint8_t *>(cws);
+  uint8_t *dst = static_cast<uint8_t *>(rows);
+  const int ncw = c->ncw;
+  if (pool && nkeys >= 4096) {
+    pool->parallel_for(nkeys, 1024, [=](size_t b, size_t e) { pack_rows_range(src, dst, b, e, ncw, al); });
+  } else {
+    pack_rows_range(src, dst, 0, nkeys, ncw, al);
+  }
+  return 0;
+}
+
+int fssb200_eval_packed(const fssb200_ctx *c, int party, const void *seeds, const void *rows, const void *ocws,
+    const void *xs, void *ys, size_t nkeys, void *stream) {
+  return eval_impl(c, -1, party, seeds, rows, ocws, xs, ys, nkeys, stream, false, nullptr, nullptr, nullptr, nullptr,
+      nullptr, nullptr, true);
 }
 
 int fssb200_relayout(const fssb200_ctx *cc, const void *cws, void *cw_s, void *cw_v, void *extra, void *out_cw,
@@ -703,6 +884,35 @@ int fssb200_ctx_reserve_host(fssb200_ctx *c, size_t max_keys_per_chunk) {
   }
   a.chunk_keys = max_keys_per_chunk;
   a.bytes_per_set = bytes;
+  // Packed host path (DPF / Half-Tree): 15 of the 32 bytes of a Cw are padding, and the host-buffer calls are bound
+  // by the PCIe link (profiles/r01_h2d_probe_n1.json).  If this process has enough cores to strip the padding faster
+  // than the link moves it (measured: 11 GB/s per core, 70-100 GB/s on 16 cores), worker threads pack each chunk into
+  // pinned staging while the previous chunk is in flight and half the bytes cross the link: 82 -> 57 ms for 2^22 keys.
+  // Packing trades link bytes for host-memory traffic (9 GB instead of 4.5 GB per 2^22 keys), so it is only used when
+  // this is the only rank on the host (torchrun's LOCAL_WORLD_SIZE): with several GPUs every link already draws its
+  // share of the host memory bandwidth (8 ranks: 173 GB/s aggregate, profiles/bench_r01_session6_n8.json).
+  // FSSB200_PACK_THREADS overrides the thread count (0 = off).
+  for (int i = 0; i < kStageSlots; ++i) {
+    if (a.stage[i]) { cudaFreeHost(a.stage[i]); a.stage[i] = nullptr; }
+    a.stage_busy[i] = false;
+  }
+  delete a.pool;
+  a.pool = nullptr;
+  int threads = usable_cpus();
+  if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+    if (std::atoi(e) > 1) threads = 0;
+  }
+  if (threads > 32) threads = 32;
+  if (const char *e = std::getenv("FSSB200_PACK_THREADS")) threads = std::atoi(e);
+  const size_t row = fssb200_packed_row_bytes(c);
+  if (row && threads >= 6) {
+    for (int i = 0; i < kStageSlots; ++i) {
+      CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&a.stage[i]), row * max_keys_per_chunk, cudaHostAllocDefault));
+      if (!a.stage_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&a.stage_ev[i], cudaEventDisableTiming));
+    }
+    a.pool = new (std::nothrow) PackPool(threads - 1);
+    if (!a.pool) return FSSB200_EINVAL;
+  }
   return 0;
 }
 
@@ -719,6 +929,17 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
   if (g.err != cudaSuccess) return int(g.err);
   HostArena &a = c->arena;
   const size_t ck = a.chunk_keys, cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  const size_t rowb = fssb200_packed_row_bytes(c);
+  const bool can_pack = a.pool && a.stage[0] && rowb && nkeys >= 8192;  // see fssb200_ctx_reserve_host
+  // A/B knob: every `direct_every`-th chunk crosses the link unpacked (0 = pack every chunk, the default).  Measured
+  // (profiles/r01_host_pack.md): mixing does not help -- the packing cores and the DMA reads compete for the same host
+  // memory bandwidth (~160 GB/s on the box), which, not the cores, is what bounds the packed path.
+  static const int direct_every = [] {
+    const char *e = std::getenv("FSSB200_PACK_DIRECT_EVERY");
+    const int v = e ? std::atoi(e) : 0;
+    return v < 0 ? 0 : v;
+  }();
+  size_t pslot = 0;
   int rc = 0;
   size_t chunk = 0;
   for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
@@ -731,11 +952,26 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
     uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
     uint8_t *d_ys = d_xs + align_up(k * 16, 256);
     CUDA_TRY(cudaMemcpyAsync(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, cudaMemcpyHostToDevice, s));
+    const bool packed = can_pack && !(direct_every && chunk % size_t(direct_every) == size_t(direct_every) - 1);
+    if (packed) {
+      // pack this chunk while the copies of the previous ones are in flight
+      const int slot = int(pslot++ % kStageSlots);
+      if (a.stage_busy[slot]) CUDA_TRY(cudaEventSynchronize(a.stage_ev[slot]));
+      const uint8_t *src = static_cast<const uint8_t *>(cws) + k0 * cwb;
+      uint8_t *dst = a.stage[slot];
+      const int ncw = c->ncw;
+      a.pool->parallel_for(k, 512, [=](size_t b, size_t e) { pack_rows_range(src, dst, b, e, ncw, true); });
+      CUDA_TRY(cudaMemcpyAsync(d_cws, dst, k * rowb, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaEventRecord(a.stage_ev[slot], s));
+      a.stage_busy[slot] = true;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, cudaMemcpyHostToDevice, s));
+    }
     if (ocws)
       CUDA_TRY(cudaMemcpyAsync(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, cudaMemcpyHostToDevice, s));
-    rc = fssb200_eval(c, party, d_seeds, d_cws, ocws ? d_ocws : nullptr, d_xs, d_ys, k, s);
+    rc = packed ? fssb200_eval_packed(c, party, d_seeds, d_cws, ocws ? d_ocws : nullptr, d_xs, d_ys, k, s)
+                : fssb200_eval(c, party, d_seeds, d_cws, ocws ? d_ocws : nullptr, d_xs, d_ys, k, s);
     if (rc) break;
     CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, cudaMemcpyDeviceToHost, s));
   }
@@ -743,6 +979,7 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
     cudaError_t e = cudaStreamSynchronize(a.stream[i]);
     if (!rc && e != cudaSuccess) rc = int(e);
   }
+  for (int i = 0; i < kStageSlots; ++i) a.stage_busy[i] = false;
   return rc;
 }
 

@@ -171,9 +171,15 @@ struct CwStagedWarp {
 // current one (also across tiles) is always in flight, so the wait does not stall; SWIZZLE_64B (16-byte chunk index
 // ^= address bits 7..8) makes the lane-per-key 128-bit reads conflict-free without padding; rows / levels outside
 // the tensor are zero-filled by the hardware, so ragged tiles and odd ncw need no predicates.
-struct CwTile {
-  static constexpr uint32_t kBuf = 2048u;          // 32 keys x 2 levels x 32 B
+//
+// PACKED = true (point mode 6, fssb200_eval_packed): the rows are the compact key format of fssb200_pack_rows --
+// ncw 16-byte `s` entries followed by one 16-byte word of flag bits (bit i = the bool at byte 16 of entry i) -- so a
+// 64-byte chunk holds FOUR levels and the flags travel in registers.  Same box, swizzle and barriers.
+template <bool PACKED>
+struct CwTileT {
+  static constexpr uint32_t kBuf = 2048u;          // 32 keys x 64 B (2 levels x 32 B, or 4 packed levels x 16 B)
   static constexpr uint32_t kWarpBytes = 2u * kBuf;
+  static constexpr int kLpcBits = PACKED ? 2 : 1;  // log2(levels per chunk)
   uint32_t buf;        // the warp's two tiles (512-byte aligned)
   uint32_t mbar;       // the warp's two mbarriers
   const void *tmap;
@@ -181,6 +187,7 @@ struct CwTile {
   int row0, next_row0;  // first key of this tile / of the warp's next tile (-1: none)
   int nchunks;
   uint32_t *seq;       // chunks this warp has waited for so far (kernel lifetime; buffer = seq & 1, parity = seq >> 1)
+  blk fl;              // PACKED: this key's flag bits
 
   static FSS_D void init_barriers(uint32_t mbar, uint32_t lane) {
     if (lane == 0) {
@@ -202,8 +209,8 @@ struct CwTile {
         : "memory");
   }
   FSS_D void begin_level(int j) const {
-    if (j & 1) return;
-    const int c = j >> 1;
+    if (j & ((1 << kLpcBits) - 1)) return;
+    const int c = j >> kLpcBits;
     const uint32_t q = *seq;
     __syncwarp();  // every lane is done with chunk q-1, whose buffer the next request overwrites
     if (lane == 0) {
@@ -225,11 +232,16 @@ struct CwTile {
   // 16-byte piece h (0 = s, 1 = v / flag word) of level j in this lane's row of the current tile
   FSS_D uint32_t at(int j, uint32_t h) const {
     const uint32_t b = (*seq - 1u) & 1u;
-    return buf + b * kBuf + rowoff + ((((uint32_t(j) & 1u) * 2u + h) ^ sw) << 4);
+    const uint32_t piece = PACKED ? (uint32_t(j) & 3u) : (uint32_t(j) & 1u) * 2u + h;
+    return buf + b * kBuf + rowoff + ((piece ^ sw) << 4);
   }
   FSS_D blk s(int j) const { return lds_blk(at(j, 0)); }
-  FSS_D blk v(int j) const { return lds_blk(at(j, 1)); }
+  FSS_D blk v(int j) const { return lds_blk(at(j, 1)); }  // (not PACKED: DCF rows have no padding to strip)
   FSS_D uint32_t flag(int j) const {
+    if (PACKED) {
+      const uint32_t w = j < 64 ? (j < 32 ? fl.x : fl.y) : (j < 96 ? fl.z : fl.w);
+      return (w >> (uint32_t(j) & 31u)) & 1u;
+    }
     uint32_t w;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(at(j, 1)) : "memory");
     return (w & 0xffu) != 0;
@@ -237,6 +249,7 @@ struct CwTile {
   FSS_D blk out_s(int n) const { return s(n); }
   FSS_D blk out_v(int n) const { return v(n); }
 };
+typedef CwTileT<false> CwTile;
 
 // ---- batched point evaluation --------------------------------------------------------------------------------
 // One key per thread; warps own tiles of 32 consecutive keys (grid-stride over tiles).
@@ -247,10 +260,11 @@ struct CwTile {
 //       3 = key-major, direct per-thread global loads (the round-1 first version; kept for A/B runs)
 //       4 = key-major, TMA tiles (CwTile), 512 threads
 //       5 = key-major, TMA tiles (CwTile), 768 threads (<= 85 regs)
-constexpr int kPointModes = 6;
+//       6 = packed rows (fssb200_pack_rows / fssb200_eval_packed), TMA tiles, 768 threads; DPF / Half-Tree only
+constexpr int kPointModes = 7;
 template <int MODE>
 struct PointMode {
-  static constexpr int kMaxThreads = MODE == 1 ? 1024 : (MODE == 5 ? 768 : 512);
+  static constexpr int kMaxThreads = MODE == 1 ? 1024 : (MODE >= 5 ? 768 : 512);
   static constexpr int kL = MODE == 1 ? 2 : 4;
   static constexpr bool kStaged = MODE <= 1;
   static constexpr bool kTma = MODE >= 4;
@@ -323,7 +337,7 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
       __syncwarp();
     } else if (PM::kTma) {
-      CwTile cw;
+      CwTileT<MODE == 6> cw;
       cw.buf = slab;
       cw.mbar = mbar;
       cw.tmap = A.tmap;
@@ -332,8 +346,9 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       cw.sw = (lane >> 1) & 3u;
       cw.row0 = int(tile * 32);
       cw.next_row0 = tile + tile_stride < ntiles ? int((tile + tile_stride) * 32) : -1;
-      cw.nchunks = (ncw + 1) >> 1;
+      cw.nchunks = MODE == 6 ? (ncw + 3) >> 2 : (ncw + 1) >> 1;
       cw.seq = &tma_seq;
+      cw.fl = MODE == 6 ? ld_blk(A.cws + kk * (uint64_t(ncw) * 16u + 16u) + uint64_t(ncw) * 16u) : blk{0u, 0u, 0u, 0u};
       y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
     } else if (MODE == 2) {
       const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, kk};

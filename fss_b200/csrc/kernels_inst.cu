@@ -51,6 +51,12 @@ static cudaError_t point_launch(const KParams &P, const PointArgs &A, const Laun
 }
 point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, int mode) {
   switch (gk) {
+// mode 6 (packed rows): only for the schemes whose Cw carries padding (DPF, Half-Tree, VDPF); DCF rows are all payload
+#if FSS_INST_SCHEME != 1
+#define FSS_CASE_PACKED(GK) case 6: return &point_launch<GK, 6>;
+#else
+#define FSS_CASE_PACKED(GK)
+#endif
 #define X(GK)                                                   \
   case GK:                                                      \
     switch (mode) {                                             \
@@ -60,6 +66,7 @@ point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, int mode) {
       case 3: return &point_launch<GK, 3>;                      \
       case 4: return &point_launch<GK, 4>;                      \
       case 5: return &point_launch<GK, 5>;                      \
+      FSS_CASE_PACKED(GK)                                       \
     }                                                           \
     return nullptr;
     FOR_EACH_GK(X)

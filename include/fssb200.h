@@ -303,6 +303,24 @@ int fssb200_eval_levelmajor_host(fssb200_ctx *ctx, int party, const void *seeds,
                                  const void *cw_v, const void *extra, const void *out_cw,
                                  const void *ocws, const void *xs, void *ys, size_t nkeys);
 
+/* ---- packed rows: compact key format for DPF / Half-Tree keys ---------------------------
+ * Dpf::Cw (dpf.cuh:76-81) and HalfTreeDpf::Cw (half_tree_dpf.cuh:53-57) are {int4 s; bool flag}
+ * padded to 32 bytes: 15 of every 32 bytes carry nothing.  A packed row holds the ncw 16-byte
+ * `s` entries of a key followed by one 16-byte word of flag bits (bit i = the bool at byte 16
+ * of entry i, i < 128): fssb200_packed_row_bytes() = ncw*16 + 16 (0 for schemes whose Cw has
+ * no padding).  fssb200_pack_rows() converts HOST arrays (reference layout in, packed rows
+ * out; multi-threaded on the worker threads of fssb200_ctx_reserve_host when they exist) --
+ * a format conversion, no evaluation happens on the CPU.  fssb200_eval_packed() is
+ * fssb200_eval() on packed rows in device memory (rows fetched by the TMA unit, four levels per
+ * 64-byte chunk).  fssb200_eval_host() uses both internally when this process has enough cores
+ * to strip the padding faster than the PCIe link would move it (see fssb200_ctx_reserve_host). */
+size_t fssb200_packed_row_bytes(const fssb200_ctx *ctx);
+/* Threads fssb200_eval_host() packs with (0: it copies the reference layout as it is). */
+int fssb200_ctx_host_pack_threads(const fssb200_ctx *ctx);
+int fssb200_pack_rows(const fssb200_ctx *ctx, const void *cws, void *rows, size_t nkeys);
+int fssb200_eval_packed(const fssb200_ctx *ctx, int party, const void *seeds, const void *rows,
+                        const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream);
+
 /* ---- introspection / measurement helpers -------------------------------------- */
 
 /* PRG known-answer hook: out[i] = block i of prg.Gen(seed), i < mul, for nseeds

@@ -226,6 +226,56 @@ def test_host_entry_points(dev, orc):
     assert np.array_equal(N(ya), orc.evalall(p2, 0, s0s[:, 0], oc, threads=8))
 
 
+# ---- packed rows (compact key format) and the packing host path -----------------------------------------------------
+
+@pytest.mark.parametrize("scheme,n,group,prg,nkeys", [
+    ("dpf", 32, "bytes", "aes128_mmo", 20000), ("halftree", 20, "u64", "aes128_mmo", 9001),
+    ("dpf", 64, "u128", "chacha", 8200), ("dpf", 128, "bytes", "aes128_mmo", 300), ("dpf", 5, "u32", "aes128_mmo", 33),
+    ("halftree", 32, "bytes", "chacha", 1), ("dpf", 3, "bytes", "aes128_mmo", 8193), ("halftree", 1, "u32", "aes128_mmo", 70),
+])
+def test_packed_rows(dev, orc, monkeypatch, scheme, n, group, prg, nkeys):
+    p = Params(scheme=scheme, in_bits=n, group=group, prg=prg, hash_key=HASH_KEY_BENCH)
+    s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=7 * n + nkeys)
+    xs[0] = (1 << n) - 1
+    o = orc.gen(p, s0s, alphas, betas, threads=8)
+    oc, ooc = o if scheme == "halftree" else (o, None)
+    want = [orc.eval(p, party, s0s[:, party], oc, xs, ooc, threads=8) for party in (0, 1)]
+    ctx = mkctx(p)
+    cws_h = torch.from_numpy(oc.view(np.int32))
+    ocws_d = None if ooc is None else T(ooc, dev)
+    # the format itself: ncw 16-byte s entries + 16 bytes of flag bits (bit i = byte 16 of entry i != 0)
+    rows = ctx.pack_rows(cws_h)
+    ncw = p.ncw
+    assert rows.shape == (nkeys, ncw * 16 + 16) and ctx.packed_row_bytes() == ncw * 16 + 16
+    r = rows.numpy()
+    raw = oc.view(np.uint8).reshape(nkeys, ncw, 32)
+    assert np.array_equal(r[:, :ncw * 16].reshape(nkeys, ncw, 16), raw[:, :, :16])
+    bits = (raw[:, :min(ncw, 128), 16] != 0)
+    flags = np.zeros((nkeys, 128), dtype=bool)
+    flags[:, :bits.shape[1]] = bits
+    assert np.array_equal(r[:, ncw * 16:], np.packbits(flags, axis=1, bitorder="little"))
+    # device evaluation on packed rows
+    rows_d = rows.to(dev)
+    for party in (0, 1):
+        ys = ctx.eval_packed(party, T(s0s[:, party], dev), rows_d, xs, ocws_d)
+        assert np.array_equal(N(ys), want[party]), party
+    # host entry point with the packing pipeline forced on (several chunks, three staging slots) and forced off
+    for threads in ("7", "0"):
+        monkeypatch.setenv("FSSB200_PACK_THREADS", threads)
+        ctx_h = mkctx(p)
+        ctx_h.reserve_host(2048)
+        ys = ctx_h.eval(1, torch.from_numpy(np.ascontiguousarray(s0s[:, 1]).view(np.int32)), cws_h, xs,
+                        None if ooc is None else torch.from_numpy(ooc.view(np.int32)))
+        assert ys.device.type == "cpu" and np.array_equal(N(ys), want[1]), threads
+
+
+def test_packed_rows_rejects_dcf(dev):
+    ctx = mkctx(Params(scheme="dcf", in_bits=16))
+    assert ctx.packed_row_bytes() == 0
+    with pytest.raises(ValueError):
+        ctx.pack_rows(torch.zeros((4, 17, 8), dtype=torch.int32))
+
+
 # ---- full-size configurations through size-independent properties ---------------------------------------------------------
 
 def test_c2_full_size_reconstruction(dev, orc):
