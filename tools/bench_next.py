@@ -124,7 +124,14 @@ def main():
         ms = timed(lambda: ctx.eval(0, seeds0, cws, xs, out=ys))
         rows["eval_keymajor_dpf_n32"] = {"keys": K, "ms": ms, "evals_per_s": K / (ms * 1e-3),
                                          "lsu_roofline_frac": lsu(K, 32, ms)}
-        del cws, lay, ys, s0s, betas, seeds0
+        # packed rows (fssb200_pack_rows / fssb200_eval_packed): 16 B + 1 bit per level, key-major
+        kp = min(K, 1 << 21)
+        prow = ctx.pack_rows(cws[:kp].cpu()).to(dev)
+        ms = timed(lambda: ctx.eval_packed(0, seeds0[:kp], prow, xs[:kp], out=ys[:kp]))
+        rows_ok = torch.equal(ctx.eval_packed(0, seeds0[:kp], prow, xs[:kp]), ctx.eval(0, seeds0[:kp], cws[:kp], xs[:kp]))
+        rows["eval_packed_dpf_n32"] = {"keys": kp, "ms": ms, "evals_per_s": kp / (ms * 1e-3), "matches_keymajor": bool(rows_ok),
+                                       "lsu_roofline_frac": lsu(kp, 32, ms)}
+        del cws, lay, ys, s0s, betas, seeds0, prow
         torch.cuda.empty_cache()
 
     # ---- f-3: DCF EvalAll, Half-Tree EvalAll, Grotto --------------------------------------------------------------------------
