@@ -906,12 +906,19 @@ int fssb200_ctx_reserve_host(fssb200_ctx *c, size_t max_keys_per_chunk) {
   if (const char *e = std::getenv("FSSB200_PACK_THREADS")) threads = std::atoi(e);
   const size_t row = fssb200_packed_row_bytes(c);
   if (row && threads >= 6) {
-    for (int i = 0; i < kStageSlots; ++i) {
-      CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&a.stage[i]), row * max_keys_per_chunk, cudaHostAllocDefault));
-      if (!a.stage_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&a.stage_ev[i], cudaEventDisableTiming));
+    // packing is an optimisation: if the pinned staging cannot be had, the call copies the reference layout as it is
+    bool ok = true;
+    for (int i = 0; i < kStageSlots && ok; ++i) {
+      ok = cudaHostAlloc(reinterpret_cast<void **>(&a.stage[i]), row * max_keys_per_chunk, cudaHostAllocDefault) == cudaSuccess;
+      if (ok && !a.stage_ev[i]) ok = cudaEventCreateWithFlags(&a.stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
     }
-    a.pool = new (std::nothrow) PackPool(threads - 1);
-    if (!a.pool) return FSSB200_EINVAL;
+    if (ok) a.pool = new (std::nothrow) PackPool(threads - 1);
+    if (!ok || !a.pool) {
+      (void)cudaGetLastError();
+      for (int i = 0; i < kStageSlots; ++i) {
+        if (a.stage[i]) { cudaFreeHost(a.stage[i]); a.stage[i] = nullptr; }
+      }
+    }
   }
   return 0;
 }
