@@ -74,4 +74,20 @@ struct DeviceBlock {
   DeviceBlock &operator=(const DeviceBlock &) = delete;
 };
 
+// A device array with blocking transfers, for the single-key members that take host arrays.
+template <typename T>
+struct DeviceArray {
+  T *ptr = nullptr;
+  explicit DeviceArray(size_t n) {
+    if (cudaMalloc(reinterpret_cast<void **>(&ptr), sizeof(T) * (n ? n : 1)) != cudaSuccess) throw std::bad_alloc();
+  }
+  ~DeviceArray() {
+    if (ptr) cudaFree(ptr);
+  }
+  void Upload(size_t at, const T *src, size_t n) { cudaMemcpy(ptr + at, src, sizeof(T) * n, cudaMemcpyHostToDevice); }
+  void Download(size_t at, T *dst, size_t n) { cudaMemcpy(dst, ptr + at, sizeof(T) * n, cudaMemcpyDeviceToHost); }
+  DeviceArray(const DeviceArray &) = delete;
+  DeviceArray &operator=(const DeviceArray &) = delete;
+};
+
 }  // namespace fss::b200

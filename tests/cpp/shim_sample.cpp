@@ -14,9 +14,11 @@
 #include <fss/group/bytes.cuh>
 #include <fss/group/uint.cuh>
 #include <fss/half_tree_dpf.cuh>
+#include <fss/hash/blake3.cuh>
 #include <fss/point_eval_gpu.cuh>
 #include <fss/prg/aes128_mmo.cuh>
 #include <fss/prg/chacha.cuh>
+#include <fss/vdpf.cuh>
 
 static int g_fail = 0;
 #define EXPECT(cond, what)                     \
@@ -211,8 +213,79 @@ static void BatchedChaCha() {
   cudaDeviceSynchronize();
 }
 
+// Verifiable DPF (flow of samples/vdpf_cpu.cu restated; Blake3 for both hashes as in src/bench_gpu.cu)
+static void VdpfN8() {
+  using Group = fss::group::Bytes;
+  using Prg = fss::prg::Aes128Mmo<2>;
+  using H = fss::hash::Blake3;
+  using Vdpf = fss::Vdpf<8, Group, Prg, H, H, uint8_t>;
+  const unsigned char *keys[2] = {k0, k1};
+  auto ctxs = Prg::CreateCtxs(keys);
+  Prg prg(ctxs);
+  const int4 iv0[2] = {{0x12345678, int(0x9abcdef0u), 0x13572468, 0x2468ace0}, {1, 2, 3, 4}};
+  const int4 iv1[2] = {{int(0x0fedcba9u), int(0x87654321u), 0x2468ace0, 0x13572468}, {5, 6, 7, 8}};
+  H xor_hash{cuda::std::span<const int4, 2>(iv0, 2)}, hash{cuda::std::span<const int4, 2>(iv1, 2)};
+  Vdpf vdpf{prg, xor_hash, hash};
+  Vdpf::Cw cws[8];
+  cuda::std::array<int4, 4> cs;
+  int4 ocw, seeds[2];
+  int ret, r = 0;
+  do {  // Gen returns 1 when the seeds hit t0 == t1: the dealer resamples (vdpf.cuh:169)
+    seeds[0] = {0x11111111 + r, 0x22222222 + r, 0x33333333 + r, 0x44444440 + r};
+    seeds[1] = {0x55555555 + r, 0x66666666 + r, 0x77777777 + r, int(0x88888880u) + r};
+    ret = vdpf.Gen(cws, cs, ocw, cuda::std::span<const int4, 2>(seeds, 2), 42, kBeta);
+    ++r;
+  } while (ret != 0 && r < 64);
+  EXPECT(ret == 0, "vdpf Gen succeeds within 64 seed pairs");
+  const auto cwspan = cuda::std::span<const Vdpf::Cw>(cws, 8);
+  const auto csspan = cuda::std::span<const int4, 4>(cs);
+  int4 y0, y1;
+  auto pt0 = vdpf.Eval(false, seeds[0], cwspan, csspan, ocw, 42, y0);
+  auto pt1 = vdpf.Eval(true, seeds[1], cwspan, csspan, ocw, 42, y1);
+  EXPECT(Eq(Add<Group>(y0, y1), kBeta), "vdpf reconstruct at alpha");
+  EXPECT(std::memcmp(pt0.data(), pt1.data(), 64) == 0, "vdpf per-point hashes agree between the parties");
+  cuda::std::array<int4, 4> pi0, pi1;
+  vdpf.Prove(cuda::std::span<const cuda::std::array<int4, 4>>(&pt0, 1), csspan, pi0);
+  vdpf.Prove(cuda::std::span<const cuda::std::array<int4, 4>>(&pt1, 1), csspan, pi1);
+  EXPECT(Vdpf::Verify(cuda::std::span<const int4, 4>(pi0), cuda::std::span<const int4, 4>(pi1)), "vdpf Verify (one point)");
+  // full domain: outputs reconstruct, proofs match, and the proof equals Prove over the per-point hashes in order
+  int4 ys0[256], ys1[256];
+  cuda::std::array<int4, 4> qa, qb;
+  vdpf.EvalAll(false, seeds[0], cwspan, csspan, ocw, cuda::std::span<int4>(ys0), qa);
+  vdpf.EvalAll(true, seeds[1], cwspan, csspan, ocw, cuda::std::span<int4>(ys1), qb);
+  int bad = 0;
+  for (int x = 0; x < 256; ++x) bad += !Eq(Add<Group>(ys0[x], ys1[x]), x == 42 ? kBeta : kZero);
+  EXPECT(bad == 0, "vdpf EvalAll reconstruct");
+  EXPECT(Vdpf::Verify(cuda::std::span<const int4, 4>(qa), cuda::std::span<const int4, 4>(qb)), "vdpf EvalAll Verify");
+  std::vector<cuda::std::array<int4, 4>> pts(256);
+  int4 yx;
+  bool same = true;
+  for (int x = 0; x < 256; ++x) {
+    pts[x] = vdpf.Eval(false, seeds[0], cwspan, csspan, ocw, uint8_t(x), yx);
+    same = same && Eq(yx, ys0[x]);
+  }
+  EXPECT(same, "vdpf EvalAll == Eval");
+  cuda::std::array<int4, 4> qp;
+  vdpf.Prove(cuda::std::span<const cuda::std::array<int4, 4>>(pts.data(), pts.size()), csspan, qp);
+  EXPECT(std::memcmp(qp.data(), qa.data(), 64) == 0, "vdpf Prove(all points) == EvalAll proof");
+  // a tampered key is caught
+  Vdpf::Cw badcws[8];
+  std::memcpy(badcws, cws, sizeof(cws));
+  badcws[3].s.x ^= 4;
+  vdpf.EvalAll(true, seeds[1], cuda::std::span<const Vdpf::Cw>(badcws, 8), csspan, ocw, cuda::std::span<int4>(ys1), qb);
+  EXPECT(!Vdpf::Verify(cuda::std::span<const int4, 4>(qa), cuda::std::span<const int4, 4>(qb)), "vdpf Verify rejects a tampered key");
+  // the hash plugin on its own: deterministic, IV-dependent, XorHash separates its two halves
+  const int4 msg[4] = {{1, 2, 3, 4}, {5, 6, 7, 8}, {9, 10, 11, 12}, {13, 14, 15, 16}};
+  auto h1 = hash.Hash(cuda::std::span<const int4, 4>(msg, 4)), h2 = xor_hash.Hash(cuda::std::span<const int4, 4>(msg, 4));
+  EXPECT(!Eq(h1[0], h2[0]), "Blake3 output depends on the IV");
+  auto x4 = xor_hash.Hash(cuda::std::tuple<int4, const int4>(msg[0], msg[1]));
+  EXPECT(!Eq(x4[0], x4[2]), "Blake3 XorHash halves differ");
+  Prg::FreeCtxs(ctxs);
+}
+
 int main() {
   try {
+    VdpfN8();
     DpfN8();
     DcfN64();
     HalfTreeAndGrotto();
