@@ -549,7 +549,9 @@ FSS_HD void dcf_expand(const PrgKeys &K, const GroupArgs &ga, const typename Prg
   typedef Grp<G> GR;
   const uint32_t tm = 0u - lsb(st);
 #if FSS_LOOPED_DCF
-  if (Prg<PRG>::kPerBlock) {
+  // (only for the groups with multi-word / modular arithmetic: for Bytes / u32 / u64 the four inlined copies still fit and
+  // their extra instruction-level parallelism wins at 8 warps per SM: Bytes 0.861 inlined vs 0.835 looped, u127 0.854 vs 0.874)
+  if (Prg<PRG>::kPerBlock && G >= kGrpU127) {
     // one side per iteration (2 AES copies in the loop body instead of 4: 29 KB + the group arithmetic does not fit
     // the 32 KB instruction cache)
     const blk in = clamp(st);
