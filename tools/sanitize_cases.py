@@ -52,7 +52,10 @@ for scheme, n, group, prg, nkeys in (("dpf", 32, "bytes", "aes128_mmo", 1000), (
 if not only or "evalall" in only:
     for scheme, n, group, prg, nkeys in (("dpf", 18, "bytes", "aes128_mmo", 2), ("dpf", 11, "u64", "chacha", 3),
                                          ("halftree", 18, "bytes", "aes128_mmo", 2), ("dcf", 17, "u128", "aes128_mmo", 1),
-                                         ("grotto", 18, "bytes", "aes128_mmo", 2)):
+                                         ("grotto", 18, "bytes", "aes128_mmo", 2),
+                                         # cooperative bottom stage with the shortest walks / both PRGs
+                                         ("dpf", 13, "u32", "aes128_mmo", 3), ("halftree", 12, "bytes", "chacha", 2),
+                                         ("dpf", 14, "u128", "chacha", 1)):
         tag = f"{scheme}-{n}-{group}-{prg}"
         p = Params(scheme=scheme, in_bits=n, group=group, prg=prg)
         s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=100 + n)
@@ -98,5 +101,21 @@ if not only or "host" in only:
     cws = ctx.gen(hs, alphas, torch.from_numpy(betas.view(np.int32)).pin_memory())
     ys = ctx.eval(0, hs[:, 0].contiguous().pin_memory(), cws.pin_memory(), xs)
     same("eval_host", ys, orc.eval(p, 0, s0s[:, 0], cws.numpy().view(np.uint32), xs))
+if not only or "packed" in only:
+    for scheme, n, group, prg, nkeys in (("dpf", 32, "bytes", "aes128_mmo", 8500), ("halftree", 17, "u64", "chacha", 777)):
+        p = Params(scheme=scheme, in_bits=n, group=group, prg=prg)
+        s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=n + 1)
+        o = orc.gen(p, s0s, alphas, betas, threads=4)
+        oc, ooc = o if scheme == "halftree" else (o, None)
+        ctx = fss_b200.Context(scheme, n, group, p.mod, prg, p.pred, p.prg_key, p.hash_key, p.in_bytes)
+        os.environ["FSSB200_PACK_THREADS"] = "6"
+        ctx.reserve_host(4096)
+        rows = ctx.pack_rows(torch.from_numpy(oc.view(np.int32)))
+        w = orc.eval(p, 1, s0s[:, 1], oc, xs, ooc, threads=4)
+        ys = ctx.eval_packed(1, t(s0s[:, 1]), rows.to(dev), xs, None if ooc is None else t(ooc))
+        same(f"eval_packed {scheme}-{n}", ys, w)
+        yh = ctx.eval(1, torch.from_numpy(np.ascontiguousarray(s0s[:, 1]).view(np.int32)), torch.from_numpy(oc.view(np.int32)),
+                      xs, None if ooc is None else torch.from_numpy(ooc.view(np.int32)))
+        same(f"eval_host packed pipeline {scheme}-{n}", yh, w)
 torch.cuda.synchronize()
 print("ALL OK")
