@@ -280,7 +280,12 @@ int fssb200_eval_levelmajor(const fssb200_ctx *ctx, int party, const void *seeds
  * device in chunks, evaluated, and results copied back, with copies and kernels
  * overlapped on internal streams.  The call returns when ys is complete.
  * fssb200_ctx_reserve_host() creates the staging arena once (the only allocating
- * call); max_keys_per_chunk = 0 picks a default. */
+ * call); max_keys_per_chunk = 0 picks a default.  For DPF / Half-Tree contexts it also
+ * starts the worker threads and pinned staging of the row-packing path (see "packed rows"
+ * below) when this process is the only rank on the host (LOCAL_WORLD_SIZE unset or 1) and
+ * has at least 6 usable cores; FSSB200_PACK_THREADS overrides the count (0 = off).
+ * The _host calls of ONE context use its arena and are therefore not re-entrant: call them
+ * from one thread at a time per context (different contexts are independent). */
 int fssb200_ctx_reserve_host(fssb200_ctx *ctx, size_t max_keys_per_chunk);
 int fssb200_eval_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
                       const void *ocws, const void *xs, void *ys, size_t nkeys);
