@@ -52,6 +52,7 @@ SYMBOLS = {
     "fssb200_grotto_expand": (_I, [_VP, _I, _VP, _VP, _VP, _SZ, _U64, _U64, _VP]),
     "fssb200_grotto_preprocess": (_I, [_VP, _I, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_grotto_eval": (_I, [_VP, _VP, _VP, _VP, _SZ, _VP]),
+    "fssb200_grotto_eval_walk": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_vdpf_gen": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_vdpf_eval": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_vdpf_eval_levelmajor": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
@@ -63,6 +64,10 @@ SYMBOLS = {
     "fssb200_relayout": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_eval_levelmajor": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_ctx_reserve_host": (_I, [_VP, _SZ]),
+    "fssb200_ctx_set_host_mode": (_I, [_VP, _I]),
+    "fssb200_ctx_host_stats": (_I, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "fssb200_host_trim": (None, []),
+    "fssb200_host_cached_bytes": (_I, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fssb200_eval_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _SZ]),
     "fssb200_eval_all_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _SZ, _U64, _U64]),
     "fssb200_gen_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
@@ -72,6 +77,7 @@ SYMBOLS = {
     "fssb200_pack_rows": (_I, [_VP, _VP, _VP, _SZ]),
     "fssb200_eval_packed": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_prg_gen": (_I, [_VP, _VP, _VP, _I, _SZ, _VP]),
+    "fssb200_prg_gen_host": (_I, [_VP, _VP, _VP, _I, _SZ]),
     "fssb200_ctx_launch_count": (_U64, [_VP]),
     "fssb200_microbench": (_I, [_I, _I, C.POINTER(C.c_double)]),
 }

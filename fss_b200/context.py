@@ -67,7 +67,6 @@ class Context:
         self.ncw = in_bits if scheme in ("halftree", "vdpf") else in_bits + 1
         self.mul = {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2, "vdpf": 2}[scheme]
         self._handles: dict[int, C.c_void_p] = {}
-        self._host_reserved: dict[int, int] = {}
 
     # ---- context handles -------------------------------------------------------------------------
     def _params(self, device: int) -> L.Params:
@@ -97,7 +96,6 @@ class Context:
         for h in self._handles.values():
             L.lib.fssb200_ctx_destroy(h)
         self._handles.clear()
-        self._host_reserved.clear()
 
     def __del__(self):
         try:
@@ -112,14 +110,23 @@ class Context:
         return int(L.lib.fssb200_eval_all_granule(self.handle(device)))
 
     def reserve_host(self, max_keys_per_chunk: int = 0, device: Optional[int] = None) -> None:
-        if device is None:
-            device = torch.cuda.current_device()
+        """Preferred keys per chunk of the host-buffer calls (0 = library default).  Allocates nothing: the
+        staging arenas belong to a process-wide pool and are sized per call (include/fssb200.h)."""
         L.check(L.lib.fssb200_ctx_reserve_host(self.handle(device), max_keys_per_chunk), "fssb200_ctx_reserve_host")
-        self._host_reserved[device] = max_keys_per_chunk or (1 << 18)
 
-    def _ensure_host(self, device: int) -> None:
-        if device not in self._host_reserved:
-            self.reserve_host(0, device)
+    def set_host_mode(self, mode: int, device: Optional[int] = None) -> None:
+        """eval() on CPU tensors: 0 = adaptive pack / direct pipeline, 1 = reference layout only, 2 = staged only."""
+        L.check(L.lib.fssb200_ctx_set_host_mode(self.handle(device), mode), "fssb200_ctx_set_host_mode")
+
+    def host_stats(self, device: Optional[int] = None) -> dict:
+        """Of the last host-buffer eval(): keys that crossed the link packed / in the reference layout, threads."""
+        p, d, t = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        L.check(L.lib.fssb200_ctx_host_stats(self.handle(device), C.byref(p), C.byref(d), C.byref(t)),
+                "fssb200_ctx_host_stats")
+        return {"packed_keys": int(p.value), "direct_keys": int(d.value), "threads": int(t.value)}
+
+    def _ensure_host(self, device: int) -> None:  # (0.1 needed an explicit arena; calls size their own now)
+        pass
 
     # ---- helpers -----------------------------------------------------------------------------------------
     def in_tensor(self, vals: IntLike, device: torch.device) -> torch.Tensor:
@@ -152,6 +159,25 @@ class Context:
         return False, torch.cuda.current_device()
 
     @staticmethod
+    def _need_cuda(what: str, *tensors: Optional[torch.Tensor]) -> None:
+        """Device-pointer-only entry points: a host pointer handed to them would be dereferenced by a kernel."""
+        for t in tensors:
+            if t is not None and t.device.type != "cuda":
+                raise RuntimeError(f"{what} takes CUDA tensors (got a {t.device.type} tensor); move the inputs to the GPU")
+
+    @staticmethod
+    def _need_rows(name: str, t: Optional[torch.Tensor], n: int) -> None:
+        if t is not None and t.shape[0] != n:
+            raise TypeError(f"{name} must have {n} rows, got {t.shape[0]}")
+
+    @staticmethod
+    def _check_out(out: Optional[torch.Tensor], shape, dtype, device) -> None:
+        if out is None:
+            return
+        if tuple(out.shape) != tuple(shape) or out.dtype != dtype or out.device != device or not out.is_contiguous():
+            raise TypeError(f"out must be a contiguous {dtype} tensor of shape {tuple(shape)} on {device}")
+
+    @staticmethod
     def _stream(dev: int) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
@@ -161,8 +187,10 @@ class Context:
         n = s0s.shape[0]
         on_gpu, dev = self._dev(s0s)
         al = self.in_tensor(alphas, s0s.device)
+        self._need_rows("alphas", al, n)
         if self.scheme != "grotto":
             betas = betas.contiguous()
+            self._need_rows("betas", betas, n)
         cws = torch.empty((n, self.ncw, 8), dtype=torch.int32, device=s0s.device)
         ocws = torch.empty((n, 4), dtype=torch.int32, device=s0s.device) if self.scheme == "halftree" else None
         h = self.handle(dev)
@@ -184,6 +212,10 @@ class Context:
         on_gpu, dev = self._dev(seeds)
         x = self.in_tensor(xs, seeds.device)
         ocws = None if ocws is None else ocws.contiguous()
+        self._need_rows("xs", x, n)
+        self._need_rows("cws", cws, n)
+        self._need_rows("ocws", ocws, n)
+        self._check_out(out, (n, 4), torch.int32, seeds.device)
         ys = out if out is not None else torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
         h = self.handle(dev)
         if on_gpu:
@@ -226,6 +258,10 @@ class Context:
             raise RuntimeError("eval_packed takes device tensors (the host entry point packs internally)")
         x = self.in_tensor(xs, seeds.device)
         ocws = None if ocws is None else ocws.contiguous()
+        self._need_cuda("eval_packed", rows, x, ocws)
+        self._need_rows("xs", x, n)
+        self._need_rows("rows", rows, n)
+        self._check_out(out, (n, 4), torch.int32, seeds.device)
         ys = out if out is not None else torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
         with torch.cuda.device(dev):
             L.check(L.lib.fssb200_eval_packed(self.handle(dev), party, _ptr(seeds), _ptr(rows), _ptr(ocws), _ptr(x),
@@ -240,7 +276,11 @@ class Context:
         on_gpu, dev = self._dev(seeds)
         cnt = leaf_count or ((1 << self.in_bits) - leaf_begin)
         ocws = None if ocws is None else ocws.contiguous()
+        self._need_rows("cws", cws, n)
+        self._need_rows("ocws", ocws, n)
         if out is not None:
+            want = (n, cnt) if self.scheme == "grotto" else (n, cnt, 4)
+            self._check_out(out, want, torch.uint8 if self.scheme == "grotto" else torch.int32, seeds.device)
             ys = out
         elif self.scheme == "grotto":
             ys = torch.empty((n, cnt), dtype=torch.uint8, device=seeds.device)
@@ -260,6 +300,7 @@ class Context:
     # ---- level-major layout (point_eval_gpu.cuh:324-492) ----------------------------------------------------------
     def relayout(self, cws: torch.Tensor):
         cws = cws.contiguous()
+        self._need_cuda("relayout", cws)
         n, nb = cws.shape[0], self.in_bits
         _, dev = self._dev(cws)
         d = cws.device
@@ -281,6 +322,11 @@ class Context:
         n = seeds.shape[0]
         on_gpu, dev = self._dev(seeds)
         x = self.in_tensor(xs, seeds.device)
+        self._need_rows("xs", x, n)
+        for t in (cw_s, cw_v, extra):
+            if t is not None and (t.shape[1] != n or t.device != seeds.device):
+                raise TypeError(f"level-major arrays must hold {n} keys on {seeds.device}")
+        self._check_out(out, (n, 4), torch.int32, seeds.device)
         ys = out if out is not None else torch.empty((n, 4), dtype=torch.int32, device=seeds.device)
         if on_gpu:
             with torch.cuda.device(dev):
@@ -298,7 +344,9 @@ class Context:
     def grotto_expand(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, leaf_begin: int = 0,
                       leaf_count: int = 0) -> torch.Tensor:
         seeds, cws = seeds.contiguous(), cws.contiguous()
+        self._need_cuda("grotto_expand", seeds, cws)
         n = seeds.shape[0]
+        self._need_rows("cws", cws, n)
         _, dev = self._dev(seeds)
         cnt = leaf_count or ((1 << self.in_bits) - leaf_begin)
         t = torch.empty((n, cnt), dtype=torch.uint8, device=seeds.device)
@@ -309,7 +357,9 @@ class Context:
 
     def grotto_preprocess(self, party: int, seeds: torch.Tensor, cws: torch.Tensor) -> torch.Tensor:
         seeds, cws = seeds.contiguous(), cws.contiguous()
+        self._need_cuda("grotto_preprocess", seeds, cws)
         n = seeds.shape[0]
+        self._need_rows("cws", cws, n)
         _, dev = self._dev(seeds)
         pt = torch.empty((n, (2 << self.in_bits) - 1), dtype=torch.uint8, device=seeds.device)
         with torch.cuda.device(dev):
@@ -319,13 +369,36 @@ class Context:
 
     def grotto_lookup(self, pt: torch.Tensor, xs: IntLike) -> torch.Tensor:
         pt = pt.contiguous()
+        self._need_cuda("grotto_lookup", pt)
         n = pt.shape[0]
         _, dev = self._dev(pt)
         x = self.in_tensor(xs, pt.device)
+        self._need_rows("xs", x, n)
+        if pt.dim() != 2 or pt.shape[1] != (2 << self.in_bits) - 1 or pt.dtype != torch.uint8:
+            raise TypeError(f"pt must be a (N, {(2 << self.in_bits) - 1}) uint8 tensor")
         ys = torch.empty((n,), dtype=torch.uint8, device=pt.device)
         with torch.cuda.device(dev):
             L.check(L.lib.fssb200_grotto_eval(self.handle(dev), _ptr(pt), _ptr(x), _ptr(ys), n, self._stream(dev)),
                     "fssb200_grotto_eval")
+        return ys
+
+    def grotto_walk(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, xs: IntLike,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """O(n) Grotto point evaluation (fssb200_grotto_eval_walk): (N,) uint8 shares with
+        share0 ^ share1 = 1[alpha <= x]; reconstruction-equal to GrottoDcf::Eval (grotto_dcf.cuh:116-135), per-party
+        bits differ.  Works for any in_bits (no 2N-1-byte parity tree)."""
+        seeds, cws = seeds.contiguous(), cws.contiguous()
+        self._need_cuda("grotto_walk", seeds, cws)
+        n = seeds.shape[0]
+        _, dev = self._dev(seeds)
+        x = self.in_tensor(xs, seeds.device)
+        self._need_rows("xs", x, n)
+        self._need_rows("cws", cws, n)
+        self._check_out(out, (n,), torch.uint8, seeds.device)
+        ys = out if out is not None else torch.empty((n,), dtype=torch.uint8, device=seeds.device)
+        with torch.cuda.device(dev):
+            L.check(L.lib.fssb200_grotto_eval_walk(self.handle(dev), party, _ptr(seeds), _ptr(cws), _ptr(x), _ptr(ys), n,
+                                                   self._stream(dev)), "fssb200_grotto_eval_walk")
         return ys
 
     # ---- VDPF (vdpf.cuh) ---------------------------------------------------------------------------------------------
@@ -337,6 +410,8 @@ class Context:
         on_gpu, dev = self._dev(s0s)
         d = s0s.device
         al = self.in_tensor(alphas, d)
+        self._need_rows("alphas", al, n)
+        self._need_rows("betas", betas, n)
         cws = torch.empty((n, self.ncw, 8), dtype=torch.int32, device=d)
         cs = torch.empty((n, 4, 4), dtype=torch.int32, device=d)
         ocws = torch.zeros((n, 4), dtype=torch.int32, device=d)
@@ -361,11 +436,15 @@ class Context:
         on_gpu, dev = self._dev(seeds)
         d = seeds.device
         x = self.in_tensor(xs, d)
+        self._need_rows("xs", x, n)
+        self._need_rows("cs", cs, n)
+        self._need_rows("ocws", ocws, n)
         ys = torch.empty((n, 4), dtype=torch.int32, device=d)
         pis = torch.empty((n, 4, 4), dtype=torch.int32, device=d)
         h = self.handle(dev)
         if layout is not None:
             cw_s, extra = layout
+            self._need_cuda("vdpf_eval(layout=...)", seeds, cw_s, extra, cs, ocws)
             with torch.cuda.device(dev):
                 L.check(L.lib.fssb200_vdpf_eval_levelmajor(h, party, _ptr(seeds), _ptr(cw_s), _ptr(extra), _ptr(cs),
                                                            _ptr(ocws), _ptr(x), _ptr(ys), _ptr(pis), n,
@@ -385,7 +464,9 @@ class Context:
     def vdpf_prove(self, pi_tildes: torch.Tensor, cs: torch.Tensor) -> torch.Tensor:
         """Vdpf::Prove (vdpf.cuh:254-264): pi_tildes (N,m,4,4), cs (N,4,4) -> proofs (N,4,4)."""
         pi_tildes, cs = pi_tildes.contiguous(), cs.contiguous()
+        self._need_cuda("vdpf_prove", pi_tildes, cs)
         n, m = cs.shape[0], pi_tildes.shape[1]
+        self._need_rows("pi_tildes", pi_tildes, n)
         _, dev = self._dev(cs)
         pis = torch.empty((n, 4, 4), dtype=torch.int32, device=cs.device)
         with torch.cuda.device(dev):
@@ -397,6 +478,7 @@ class Context:
                       ocws: torch.Tensor):
         """Vdpf::EvalAll (vdpf.cuh:294-342) -> ys (N,2^n,4), proofs (N,4,4)."""
         seeds, cws, cs, ocws = seeds.contiguous(), cws.contiguous(), cs.contiguous(), ocws.contiguous()
+        self._need_cuda("vdpf_eval_all", seeds, cws, cs, ocws)
         n = seeds.shape[0]
         _, dev = self._dev(seeds)
         ys = torch.empty((n, 1 << self.in_bits, 4), dtype=torch.int32, device=seeds.device)
@@ -414,6 +496,7 @@ class Context:
     def hash(self, which: int, msgs: torch.Tensor) -> torch.Tensor:
         """Blake3 plugin known-answer hook: which 0 = XorHash (N,2,4)->(N,4,4), 1 = Hash (N,4,4)->(N,2,4)."""
         msgs = msgs.contiguous()
+        self._need_cuda("hash", msgs)
         n = msgs.shape[0]
         _, dev = self._dev(msgs)
         out = torch.empty((n, 4 if which == 0 else 2, 4), dtype=torch.int32, device=msgs.device)
@@ -425,6 +508,7 @@ class Context:
     # ---- PRG known-answer hook -----------------------------------------------------------------------------------------
     def prg_gen(self, seeds: torch.Tensor, mul: int) -> torch.Tensor:
         seeds = seeds.contiguous()
+        self._need_cuda("prg_gen", seeds)
         n = seeds.shape[0]
         _, dev = self._dev(seeds)
         out = torch.empty((n, mul, 4), dtype=torch.int32, device=seeds.device)

@@ -39,8 +39,9 @@ prg_launch_fn get_prg_launcher(int prg, int mul);
   point_launch_fn point_launcher_##PRGNAME##_##SCHNAME(int gk, int mode);
 #define FSS_DECL_GEN(PRGNAME, SCHNAME) gen_launch_fn gen_launcher_##PRGNAME##_##SCHNAME(int gk, int out_mode);
 #define FSS_DECL_EVALALL(PRGNAME, MODENAME) evalall_launch_fn evalall_launcher_##PRGNAME##_##MODENAME(int gk);
-FSS_DECL_POINT(aes, dpf) FSS_DECL_POINT(aes, dcf) FSS_DECL_POINT(aes, ht) FSS_DECL_POINT(aes, vdpf)
+FSS_DECL_POINT(aes, dpf) FSS_DECL_POINT(aes, dcf) FSS_DECL_POINT(aes, ht) FSS_DECL_POINT(aes, vdpf) FSS_DECL_POINT(aes, grotto)
 FSS_DECL_POINT(chacha, dpf) FSS_DECL_POINT(chacha, dcf) FSS_DECL_POINT(chacha, ht) FSS_DECL_POINT(chacha, vdpf)
+FSS_DECL_POINT(chacha, grotto)
 FSS_DECL_GEN(aes, dpf) FSS_DECL_GEN(aes, dcf) FSS_DECL_GEN(aes, ht) FSS_DECL_GEN(aes, vdpf)
 FSS_DECL_GEN(chacha, dpf) FSS_DECL_GEN(chacha, dcf) FSS_DECL_GEN(chacha, ht) FSS_DECL_GEN(chacha, vdpf)
 FSS_DECL_EVALALL(aes, dpf) FSS_DECL_EVALALL(aes, ht) FSS_DECL_EVALALL(aes, grotto) FSS_DECL_EVALALL(aes, dcf)

@@ -1,0 +1,1023 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// host_api.cu -- the host-buffer entry points of include/fssb200.h (`fssb200_*_host`, fssb200_pack_rows): what a
+// CPU caller of the reference binds.  Inputs live in HOST memory in the reference's layouts; every call stages them
+// to the device, launches the sm_100a kernels of api.cu and brings the results back.  No evaluation happens on the
+// CPU: the host threads below only move and re-pack bytes.
+//
+// Re-entrancy (the reference's Eval is a const pure function used under `#pragma omp parallel for`,
+// src/bench_cpu.cu:157-161): a context owns no staging memory.  Every call checks an ARENA (device staging +
+// pinned staging + 3 streams + events) out of a process-wide per-device pool, sized from the call's own batch, and
+// returns it on every exit path after both the streams and the worker threads are quiescent.  A 1-key call takes a
+// 1 MiB arena; concurrent calls take different arenas.
+//
+// fssb200_eval_host, large batches: ADAPTIVE PACK / DIRECT PIPELINE.  15 of the 32 bytes of a Dpf::Cw /
+// HalfTreeDpf::Cw are padding, and the call is bound by the PCIe link (or, with several GPUs, by whatever the
+// host gives each link).  Worker threads strip the padding of chunk after chunk (from the front of the batch) into
+// a ring of pinned staging slots; the calling thread submits every finished slot as ONE H2D copy + kernel + D2H, and
+// whenever the link is about to run dry while no packed chunk is ready it sends a chunk from the BACK of the
+// batch in the reference layout straight from the caller's buffer.  So the split between "CPU packs, link moves
+// 17 B/level" and "link moves 32 B/level" settles by itself at the point where cores and link finish together,
+// for any core count per rank (1 GPU with 16 cores: almost everything packed; 8 ranks with 4 cores each: about
+// half).  No barriers: workers claim 512-key blocks with one fetch_add, hand-offs are per-chunk counters.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+#include "ctx.h"
+
+using namespace fssb200;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// row packing (format conversion only)
+// ---------------------------------------------------------------------------------------------------------------
+// rows [k0, k1): ncw x {16 B s} + 16 B of flag bits (bit i = byte 16 of entry i != 0, i < 128).
+// STREAM: non-temporal stores for the whole row, flag word included -- a regular store into a line that is still
+// being assembled in a write-combining buffer forces a flush + read-for-ownership and cost 3.5x (measured).
+template <bool STREAM>
+void pack_rows_range_t(const uint8_t *src, uint8_t *dst, size_t k0, size_t k1, int ncw) {
+  const size_t in_row = size_t(ncw) * 32u, out_row = size_t(ncw) * 16u + 16u;
+  const int nflag = ncw < 128 ? ncw : 128;
+  for (size_t k = k0; k < k1; ++k) {
+    const uint8_t *r = src + k * in_row;
+    uint8_t *o = dst + k * out_row;
+    uint64_t f0 = 0, f1 = 0;
+    for (int i = 0; i < nflag && i < 64; ++i) f0 |= uint64_t(r[32 * i + 16] != 0) << i;
+    for (int i = 64; i < nflag; ++i) f1 |= uint64_t(r[32 * i + 16] != 0) << (i - 64);
+#if defined(__SSE2__)
+    for (int i = 0; i < ncw; ++i) {
+      const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(r + 32 * i));
+      if (STREAM) _mm_stream_si128(reinterpret_cast<__m128i *>(o + 16 * i), v);
+      else _mm_storeu_si128(reinterpret_cast<__m128i *>(o + 16 * i), v);
+    }
+    const __m128i fv = _mm_set_epi64x(static_cast<long long>(f1), static_cast<long long>(f0));
+    if (STREAM) _mm_stream_si128(reinterpret_cast<__m128i *>(o + size_t(ncw) * 16u), fv);
+    else _mm_storeu_si128(reinterpret_cast<__m128i *>(o + size_t(ncw) * 16u), fv);
+#else
+    for (int i = 0; i < ncw; ++i) std::memcpy(o + 16 * i, r + 32 * i, 16);
+    const uint64_t f[2] = {f0, f1};
+    std::memcpy(o + size_t(ncw) * 16u, f, 16);
+#endif
+  }
+#if defined(__SSE2__)
+  if (STREAM) _mm_sfence();
+#endif
+}
+void pack_rows_range(const uint8_t *src, uint8_t *dst, size_t k0, size_t k1, int ncw, bool stream_stores) {
+  if (stream_stores) pack_rows_range_t<true>(src, dst, k0, k1, ncw);
+  else pack_rows_range_t<false>(src, dst, k0, k1, ncw);
+}
+// plain staging copy (16-byte granules; dst 16-byte aligned); non-temporal when `stream_stores`
+void stage_copy(const uint8_t *src, uint8_t *dst, size_t bytes, bool stream_stores) {
+#if defined(__SSE2__)
+  if (stream_stores && !(bytes & 15u)) {
+    for (size_t i = 0; i < bytes; i += 16)
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i)));
+    _mm_sfence();
+    return;
+  }
+#endif
+  std::memcpy(dst, src, bytes);
+}
+
+inline void cpu_relax() {
+#if defined(__SSE2__)
+  _mm_pause();
+#endif
+}
+
+int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e && *e ? std::atoi(e) : dflt;
+}
+
+int usable_cpus() {
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) return CPU_COUNT(&set);
+#endif
+  const unsigned h = std::thread::hardware_concurrency();
+  return h ? int(h) : 1;
+}
+
+// Threads one call of this process may use to stage rows, the calling thread included: the usable cores divided by
+// the ranks that share the host (torchrun's LOCAL_WORLD_SIZE), at most 32.  FSSB200_PACK_THREADS overrides (0 or 1: the
+// reference layout always crosses the link as it is).
+int host_thread_budget() {
+  int lws = env_int("LOCAL_WORLD_SIZE", 1);
+  if (lws < 1) lws = 1;
+  int t = usable_cpus() / lws;
+  if (t > 32) t = 32;
+  t = env_int("FSSB200_PACK_THREADS", t);
+  return t < 0 ? 0 : t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// worker threads: one process-wide crew, lent to one call at a time
+// ---------------------------------------------------------------------------------------------------------------
+struct CrewJob {
+  virtual void run() = 0;  // called once by every worker; returns when the job has nothing left for it
+  virtual ~CrewJob() {}
+};
+
+class Crew {
+ public:
+  static Crew *get() {
+    static Crew *crew = [] {
+      const int t = host_thread_budget();
+      return t >= 2 ? new (std::nothrow) Crew(t - 1) : nullptr;  // leaked on purpose: no teardown races at exit
+    }();
+    return crew;
+  }
+  int workers() const { return int(th_.size()); }
+  // Lends the crew to `job` if it is idle.  The caller must call end() before `job` dies.
+  bool try_begin(CrewJob *job) {
+    std::lock_guard<std::mutex> l(mu_);
+    if (job_) return false;
+    job_ = job;
+    running_ = int(th_.size());
+    ++gen_;
+    cv_start_.notify_all();
+    return true;
+  }
+  // Blocks until every worker has left the job.
+  void end() {
+    std::unique_lock<std::mutex> l(mu_);
+    cv_done_.wait(l, [this] { return running_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  explicit Crew(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); }), th_.back().detach();
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      CrewJob *job;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_start_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        job = job_;
+      }
+      job->run();
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--running_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_start_, cv_done_;
+  CrewJob *job_ = nullptr;
+  uint64_t gen_ = 0;
+  int running_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// arena pool
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kArenaStreams = 3;
+constexpr int kMaxSets = 8;
+
+struct Arena {
+  int device = -1;
+  uint8_t *dev = nullptr;
+  size_t dev_bytes = 0;
+  uint8_t *pin = nullptr;
+  size_t pin_bytes = 0;
+  cudaStream_t stream[kArenaStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t h2d_ev[kMaxSets] = {};
+  cudaEvent_t set_ev[kMaxSets] = {};
+};
+
+size_t round_arena(size_t b) {
+  if (b == 0) return 0;
+  size_t r = size_t(1) << 20;
+  while (r < b && r < (size_t(32) << 20)) r <<= 1;
+  return r >= b ? r : align_up(b, size_t(32) << 20);
+}
+
+class ArenaPool {
+ public:
+  static ArenaPool &get() {
+    static ArenaPool *p = new ArenaPool();  // leaked on purpose (CUDA may be gone when statics are destroyed)
+    return *p;
+  }
+  // device must be current.  Returns nullptr and *rc on failure.
+  Arena *checkout(int device, size_t dev_bytes, size_t pin_bytes, int *rc) {
+    dev_bytes = round_arena(dev_bytes);
+    pin_bytes = round_arena(pin_bytes);
+    Arena *a = nullptr;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      int best = -1, biggest = -1;
+      for (int i = 0; i < int(free_.size()); ++i) {
+        Arena *f = free_[i];
+        if (f->device != device) continue;
+        if (f->dev_bytes >= dev_bytes && f->pin_bytes >= pin_bytes && (best < 0 || f->dev_bytes < free_[best]->dev_bytes))
+          best = i;
+        if (biggest < 0 || f->dev_bytes > free_[biggest]->dev_bytes) biggest = i;
+      }
+      const int take = best >= 0 ? best : biggest;
+      if (take >= 0) {
+        a = free_[take];
+        free_.erase(free_.begin() + take);
+      }
+    }
+    if (!a) {
+      a = new (std::nothrow) Arena();
+      if (!a) { *rc = FSSB200_EINVAL; return nullptr; }
+      a->device = device;
+      cudaError_t e = cudaSuccess;
+      for (int i = 0; i < kArenaStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&a->stream[i], cudaStreamNonBlocking);
+      for (int i = 0; i < kMaxSets && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&a->h2d_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->set_ev[i], cudaEventDisableTiming);
+      }
+      if (e != cudaSuccess) { destroy(a); *rc = int(e); return nullptr; }
+    }
+    if (a->dev_bytes < dev_bytes) {
+      if (a->dev) cudaFree(a->dev);
+      a->dev = nullptr;
+      a->dev_bytes = 0;
+      const cudaError_t e = cudaMalloc(&a->dev, dev_bytes);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); destroy(a); *rc = int(e); return nullptr; }
+      a->dev_bytes = dev_bytes;
+    }
+    if (a->pin_bytes < pin_bytes) {
+      if (a->pin) cudaFreeHost(a->pin);
+      a->pin = nullptr;
+      a->pin_bytes = 0;
+      const cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&a->pin), pin_bytes, cudaHostAllocDefault);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); destroy(a); *rc = int(e); return nullptr; }
+      a->pin_bytes = pin_bytes;
+    }
+    *rc = 0;
+    return a;
+  }
+  void checkin(Arena *a) {
+    if (!a) return;
+    Arena *victim = nullptr;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      free_.push_back(a);
+      int on_dev = 0, smallest = -1;
+      for (int i = 0; i < int(free_.size()); ++i) {
+        if (free_[i]->device != a->device) continue;
+        ++on_dev;
+        if (smallest < 0 || free_[i]->dev_bytes + free_[i]->pin_bytes < free_[smallest]->dev_bytes + free_[smallest]->pin_bytes)
+          smallest = i;
+      }
+      if (on_dev > kKeepPerDevice) {
+        victim = free_[smallest];
+        free_.erase(free_.begin() + smallest);
+      }
+    }
+    if (victim) {
+      DeviceGuard g(victim->device);
+      destroy(victim);
+    }
+  }
+  void trim() {
+    std::vector<Arena *> all;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      all.swap(free_);
+    }
+    for (Arena *a : all) {
+      DeviceGuard g(a->device);
+      destroy(a);
+    }
+  }
+  size_t cached_bytes(size_t *pinned) {
+    std::lock_guard<std::mutex> l(mu_);
+    size_t d = 0, p = 0;
+    for (Arena *a : free_) { d += a->dev_bytes; p += a->pin_bytes; }
+    if (pinned) *pinned = p;
+    return d;
+  }
+
+ private:
+  static constexpr int kKeepPerDevice = 4;
+  static void destroy(Arena *a) {
+    if (a->dev) cudaFree(a->dev);
+    if (a->pin) cudaFreeHost(a->pin);
+    for (int i = 0; i < kArenaStreams; ++i)
+      if (a->stream[i]) cudaStreamDestroy(a->stream[i]);
+    for (int i = 0; i < kMaxSets; ++i) {
+      if (a->h2d_ev[i]) cudaEventDestroy(a->h2d_ev[i]);
+      if (a->set_ev[i]) cudaEventDestroy(a->set_ev[i]);
+    }
+    delete a;
+  }
+  std::mutex mu_;
+  std::vector<Arena *> free_;
+};
+
+// One host call's hold on an arena: sets the device, checks the arena out, and on every exit path drains the
+// arena's streams before handing it back (a failed call must not leave copies into the caller's buffers in flight).
+struct ArenaLease {
+  DeviceGuard guard;
+  Arena *a = nullptr;
+  int rc = 0;
+  ArenaLease(int device, size_t dev_bytes, size_t pin_bytes) : guard(device) {
+    if (guard.err != cudaSuccess) { rc = int(guard.err); return; }
+    a = ArenaPool::get().checkout(device, dev_bytes, pin_bytes, &rc);
+  }
+  // Synchronises the streams; returns the first error (or `rc_in` if that is already set).
+  int drain(int rc_in) {
+    if (!a) return rc_in ? rc_in : rc;
+    for (int i = 0; i < kArenaStreams; ++i) {
+      const cudaError_t e = cudaStreamSynchronize(a->stream[i]);
+      if (!rc_in && e != cudaSuccess) rc_in = int(e);
+    }
+    return rc_in;
+  }
+  ~ArenaLease() {
+    if (a) {
+      for (int i = 0; i < kArenaStreams; ++i) cudaStreamSynchronize(a->stream[i]);
+      ArenaPool::get().checkin(a);
+    }
+  }
+  ArenaLease(const ArenaLease &) = delete;
+  ArenaLease &operator=(const ArenaLease &) = delete;
+};
+
+size_t chunk_pref(const fssb200_ctx *c, size_t nkeys, size_t dflt) {
+  size_t ck = c->host_chunk_keys.load(std::memory_order_relaxed);
+  if (ck == 0) ck = dflt;
+  if (ck > nkeys) ck = nkeys;
+  return ck ? ck : 1;
+}
+
+bool is_pinned_or_device(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice;
+}
+
+// (cudaMemcpyDefault: the "host" arrays may just as well be managed or device memory)
+#define H2D(dst, src, bytes, s) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s)
+#define D2H(dst, src, bytes, s) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s)
+#define TRY_BREAK(expr)                                  \
+  {                                                      \
+    const cudaError_t e__ = (expr);                      \
+    if (e__ != cudaSuccess) { rc = int(e__); break; }    \
+  }
+
+// ---------------------------------------------------------------------------------------------------------------
+// the adaptive pipeline of fssb200_eval_host
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t kPackBlock = 512;  // keys a worker claims at a time
+
+struct EvalPipe : CrewJob {
+  // the call
+  fssb200_ctx *c;
+  int party;
+  const uint8_t *seeds, *cws, *ocws, *xs;
+  uint8_t *ys;
+  size_t nkeys;
+  // geometry
+  size_t ck, nchunks, cwb, rowb, ib;
+  bool pack;        // staged rows are packed rows (else: a plain copy of the reference layout)
+  bool nt_stores;
+  uint8_t *stage;   // ring of pinned slots
+  size_t slot_bytes, nslots;
+  // shared state
+  struct ChunkState {
+    std::atomic<uint32_t> next{0};  // next 512-key block to claim
+    std::atomic<uint32_t> done{0};  // keys staged so far
+  };
+  std::unique_ptr<ChunkState[]> st;
+  std::atomic<size_t> cur{0};        // chunk the workers are staging
+  std::atomic<size_t> tail{0};       // chunks [tail, nchunks) were sent in the reference layout
+  std::atomic<size_t> free_upto{0};  // staging may write chunk c iff c < free_upto
+  std::atomic<bool> stop{false};
+  std::mutex claim_mu;
+
+  size_t keys_of(size_t ch) const { return ch + 1 < nchunks ? ck : nkeys - ch * ck; }
+  // staged chunk layout in a slot (and, identically, in its device set): rows | seeds | xs | ocws
+  size_t staged_row_bytes() const { return pack ? rowb : cwb; }
+  size_t off_seeds(size_t k) const { return align_up(k * staged_row_bytes(), 256); }
+  size_t off_xs(size_t k) const { return off_seeds(k) + align_up(k * 16, 256); }
+  size_t off_ocws(size_t k) const { return off_xs(k) + align_up(k * ib, 256); }
+  size_t staged_bytes(size_t k) const { return off_ocws(k) + (ocws ? align_up(k * 16, 256) : 0); }
+
+  // Stages one block if there is one.  Returns false when there is nothing to do right now.
+  bool stage_step() {
+    const size_t ch = cur.load(std::memory_order_acquire);
+    if (ch >= tail.load(std::memory_order_acquire)) return false;
+    if (ch >= free_upto.load(std::memory_order_acquire)) return false;
+    const size_t k = keys_of(ch);
+    const uint32_t nblocks = uint32_t((k + kPackBlock - 1) / kPackBlock);
+    const uint32_t b = st[ch].next.fetch_add(1, std::memory_order_relaxed);
+    if (b >= nblocks) {
+      std::lock_guard<std::mutex> l(claim_mu);
+      if (cur.load(std::memory_order_relaxed) == ch) cur.store(ch + 1, std::memory_order_release);
+      return true;
+    }
+    const size_t k0 = size_t(b) * kPackBlock, k1 = std::min(k, k0 + kPackBlock), g0 = ch * ck;
+    uint8_t *slot = stage + (ch % nslots) * slot_bytes;
+    if (pack) pack_rows_range(cws + g0 * cwb, slot, k0, k1, c->ncw, nt_stores);
+    else stage_copy(cws + (g0 + k0) * cwb, slot + k0 * cwb, (k1 - k0) * cwb, nt_stores);
+    stage_copy(seeds + (g0 + k0) * 16, slot + off_seeds(k) + k0 * 16, (k1 - k0) * 16, nt_stores);
+    stage_copy(xs + (g0 + k0) * ib, slot + off_xs(k) + k0 * ib, (k1 - k0) * ib, false);
+    if (ocws) stage_copy(ocws + (g0 + k0) * 16, slot + off_ocws(k) + k0 * 16, (k1 - k0) * 16, nt_stores);
+    st[ch].done.fetch_add(uint32_t(k1 - k0), std::memory_order_release);
+    return true;
+  }
+  void run() override {
+    int idle = 0;
+    while (!stop.load(std::memory_order_acquire)) {
+      if (cur.load(std::memory_order_acquire) >= tail.load(std::memory_order_acquire)) break;
+      if (stage_step()) {
+        idle = 0;
+      } else if (++idle < 64) {
+        cpu_relax();
+      } else {
+        std::this_thread::yield();
+      }
+    }
+  }
+};
+
+// Large batches with worker threads available.  `allow_direct`: the caller's buffers are pinned, so chunks may also
+// cross the link straight from them.
+int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    const void *xs, void *ys, size_t nkeys, Crew *crew, bool allow_direct, bool ys_pinned) {
+  EvalPipe P;
+  P.c = c;
+  P.party = party;
+  P.seeds = static_cast<const uint8_t *>(seeds);
+  P.cws = static_cast<const uint8_t *>(cws);
+  P.ocws = static_cast<const uint8_t *>(ocws);
+  P.xs = static_cast<const uint8_t *>(xs);
+  P.ys = static_cast<uint8_t *>(ys);
+  P.nkeys = nkeys;
+  P.cwb = size_t(c->ncw) * 32;
+  P.rowb = fssb200_packed_row_bytes(c);
+  P.ib = size_t(c->p.in_bytes);
+  P.pack = P.rowb != 0;
+  P.nt_stores = env_int("FSSB200_PACK_NT", 1) != 0;
+  P.ck = chunk_pref(c, nkeys, size_t(1) << env_int("FSSB200_PIPE_CHUNK_BITS", 16));
+  P.nchunks = (nkeys + P.ck - 1) / P.ck;
+  P.nslots = size_t(std::max(2, std::min(16, env_int("FSSB200_PIPE_SLOTS", 6))));
+  if (P.nslots > P.nchunks) P.nslots = P.nchunks;
+  P.slot_bytes = align_up(P.staged_bytes(P.ck), 4096);
+  const int nsets = int(std::min<size_t>(kMaxSets, std::max<size_t>(2, std::min<size_t>(P.nchunks, 4))));
+  // device set: a staged chunk or a reference-layout chunk (rows | seeds | xs | ocws), then ys
+  const size_t direct_bytes = align_up(P.ck * P.cwb, 256) + align_up(P.ck * 16, 256) + align_up(P.ck * P.ib, 256) +
+      (ocws ? align_up(P.ck * 16, 256) : 0);
+  const size_t set_in = std::max(direct_bytes, P.staged_bytes(P.ck));
+  const size_t set_bytes = align_up(set_in + P.ck * 16, 4096);
+  const size_t ys_stage = ys_pinned ? 0 : align_up(P.ck * 16, 4096);  // pageable ys: results land in pinned memory first
+  ArenaLease L(c->p.device, set_bytes * nsets, P.nslots * P.slot_bytes + ys_stage * nsets);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  P.stage = A.pin;
+  uint8_t *ys_pin = A.pin + P.nslots * P.slot_bytes;
+  P.st.reset(new (std::nothrow) EvalPipe::ChunkState[P.nchunks]);
+  if (!P.st) return FSSB200_EINVAL;
+  P.tail.store(P.nchunks);
+  P.free_upto.store(P.nslots);
+
+  const bool crewed = crew && crew->try_begin(&P);
+  if (!crewed && !allow_direct) {
+    // no workers right now and pageable inputs: the calling thread stages alone (still correct, just slower)
+  }
+
+  struct Issue {
+    size_t chunk;
+    bool staged;
+  };
+  std::deque<Issue> link_fifo;           // H2D copies not yet known to be complete, in issue order
+  Issue set_use[kMaxSets];
+  bool set_busy[kMaxSets] = {};
+  size_t issued = 0, retired = 0;        // issue i uses device set i % nsets
+  size_t next_staged = 0, staged_copied = 0;
+  uint64_t direct_keys = 0;
+  int rc = 0;
+
+  auto retire_set = [&](int s, bool wait) -> bool {  // results of the issue in set s are on the host
+    if (!set_busy[s]) return true;
+    if (wait) {
+      const cudaError_t e = cudaEventSynchronize(A.set_ev[s]);
+      if (e != cudaSuccess) { rc = int(e); return false; }
+    } else {
+      const cudaError_t e = cudaEventQuery(A.set_ev[s]);
+      if (e == cudaErrorNotReady) return false;
+      if (e != cudaSuccess) { rc = int(e); return false; }
+    }
+    if (ys_stage) {
+      const size_t ch = set_use[s].chunk;
+      std::memcpy(P.ys + ch * P.ck * 16, ys_pin + size_t(s) * ys_stage, P.keys_of(ch) * 16);
+    }
+    set_busy[s] = false;
+    ++retired;
+    return true;
+  };
+  auto poll_link = [&]() {
+    while (!link_fifo.empty()) {
+      const int s = int((issued - link_fifo.size()) % size_t(nsets));
+      const cudaError_t e = cudaEventQuery(A.h2d_ev[s]);
+      if (e == cudaErrorNotReady) break;
+      if (e != cudaSuccess) { rc = int(e); break; }
+      if (link_fifo.front().staged) {
+        ++staged_copied;
+        P.free_upto.store(staged_copied + P.nslots, std::memory_order_release);
+      }
+      link_fifo.pop_front();
+    }
+  };
+  auto issue = [&](size_t ch, bool staged) {
+    const int s = int(issued % size_t(nsets));
+    cudaStream_t str = A.stream[issued % kArenaStreams];
+    const size_t k = P.keys_of(ch), g0 = ch * P.ck;
+    uint8_t *d = A.dev + size_t(s) * set_bytes;
+    uint8_t *d_rows = d, *d_seeds, *d_xs, *d_ocws, *d_ys = d + set_in;
+    do {
+      if (staged) {
+        d_seeds = d + P.off_seeds(k);
+        d_xs = d + P.off_xs(k);
+        d_ocws = d + P.off_ocws(k);
+        TRY_BREAK(H2D(d, P.stage + (ch % P.nslots) * P.slot_bytes, P.staged_bytes(k), str));
+      } else {
+        d_seeds = d + align_up(k * P.cwb, 256);
+        d_xs = d_seeds + align_up(k * 16, 256);
+        d_ocws = d_xs + align_up(k * P.ib, 256);
+        TRY_BREAK(H2D(d_rows, P.cws + g0 * P.cwb, k * P.cwb, str));
+        TRY_BREAK(H2D(d_seeds, P.seeds + g0 * 16, k * 16, str));
+        TRY_BREAK(H2D(d_xs, P.xs + g0 * P.ib, k * P.ib, str));
+        if (P.ocws) TRY_BREAK(H2D(d_ocws, P.ocws + g0 * 16, k * 16, str));
+        direct_keys += k;
+      }
+      TRY_BREAK(cudaEventRecord(A.h2d_ev[s], str));
+      rc = (staged && P.pack) ? fssb200_eval_packed(c, party, d_seeds, d_rows, P.ocws ? d_ocws : nullptr, d_xs, d_ys, k, str)
+                              : fssb200_eval(c, party, d_seeds, d_rows, P.ocws ? d_ocws : nullptr, d_xs, d_ys, k, str);
+      if (rc) break;
+      TRY_BREAK(D2H(ys_stage ? ys_pin + size_t(s) * ys_stage : P.ys + g0 * 16, d_ys, k * 16, str));
+      TRY_BREAK(cudaEventRecord(A.set_ev[s], str));
+    } while (0);
+    set_busy[s] = true;
+    set_use[s] = Issue{ch, staged};
+    link_fifo.push_back(Issue{ch, staged});
+    ++issued;
+  };
+
+  int idle = 0;
+  while (!rc) {
+    poll_link();
+    if (rc) break;
+    const size_t tl = P.tail.load(std::memory_order_acquire);
+    if (next_staged >= tl) break;  // every chunk has been issued
+    bool progressed = false;
+    const int s = int(issued % size_t(nsets));
+    const bool set_free = retire_set(s, false);
+    if (rc) break;
+    if (set_free) {
+      poll_link();  // (the set's previous H2D event is about to be re-recorded)
+      if (P.st[next_staged].done.load(std::memory_order_acquire) == uint32_t(P.keys_of(next_staged))) {
+        issue(next_staged++, true);
+        progressed = true;
+      } else if (allow_direct && link_fifo.size() < 2) {
+        // the link is about to run dry and no staged chunk is ready: send one from the back as it is
+        size_t take = ~size_t(0);
+        {
+          std::lock_guard<std::mutex> l(P.claim_mu);
+          const size_t t = P.tail.load(std::memory_order_relaxed);
+          if (t > 0 && t - 1 > P.cur.load(std::memory_order_relaxed)) {
+            take = t - 1;
+            P.tail.store(take, std::memory_order_release);
+          }
+        }
+        if (take != ~size_t(0)) {
+          issue(take, false);
+          progressed = true;
+        }
+      }
+    }
+    if (progressed) {
+      idle = 0;
+      continue;
+    }
+    if (P.stage_step()) {
+      idle = 0;
+    } else if (++idle < 64) {
+      cpu_relax();
+    } else {
+      std::this_thread::yield();
+    }
+  }
+  P.stop.store(true, std::memory_order_release);
+  if (crewed) crew->end();
+  // drain: results of every issued chunk
+  for (size_t i = retired; i < issued; ++i) {
+    const int first = rc;
+    rc = 0;
+    retire_set(int(i % size_t(nsets)), true);
+    if (first) rc = first;
+  }
+  rc = L.drain(rc);
+  c->last_direct_keys.store(direct_keys, std::memory_order_relaxed);
+  c->last_packed_keys.store(nkeys - direct_keys, std::memory_order_relaxed);  // staged: packed, or copied (no padding)
+  c->last_pack_threads.store(crewed ? crew->workers() + 1 : 1, std::memory_order_relaxed);
+  return rc;
+}
+
+// Small batches, or no worker threads: chunks of the reference layout through two device sets.
+int eval_host_simple(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws, const void *xs,
+    void *ys, size_t nkeys) {
+  const size_t ck = chunk_pref(c, nkeys, size_t(1) << 18), cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  const size_t set_bytes = align_up(ck * 16, 256) * 3 + align_up(ck * cwb, 256) + align_up(ck * ib, 256);
+  const int nsets = nkeys > ck ? 2 : 1;
+  ArenaLease L(c->p.device, set_bytes * nsets, 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = std::min(ck, nkeys - k0);
+    const int b = int(chunk & 1);
+    cudaStream_t s = A.stream[b];
+    uint8_t *d_seeds = A.dev + size_t(b) * set_bytes;
+    uint8_t *d_cws = d_seeds + align_up(k * 16, 256);
+    uint8_t *d_ocws = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_ys = d_xs + align_up(k * ib, 256);
+    // (a set is reused two chunks later on the same stream: stream order protects it)
+    TRY_BREAK(H2D(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, s));
+    TRY_BREAK(H2D(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, s));
+    if (ocws) TRY_BREAK(H2D(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, s));
+    TRY_BREAK(H2D(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, s));
+    rc = fssb200_eval(c, party, d_seeds, d_cws, ocws ? d_ocws : nullptr, d_xs, d_ys, k, s);
+    if (rc) break;
+    TRY_BREAK(D2H(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, s));
+  }
+  rc = L.drain(rc);
+  c->last_direct_keys.store(nkeys, std::memory_order_relaxed);
+  c->last_packed_keys.store(0, std::memory_order_relaxed);
+  c->last_pack_threads.store(0, std::memory_order_relaxed);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- packed rows: host-side format conversion ---------------------------------------------------------------------
+namespace {
+struct PackRowsJob : CrewJob {
+  const uint8_t *src;
+  uint8_t *dst;
+  size_t nkeys;
+  int ncw;
+  bool nt;
+  std::atomic<size_t> next{0};
+  void run() override {
+    for (;;) {
+      const size_t b = next.fetch_add(1024, std::memory_order_relaxed);
+      if (b >= nkeys) return;
+      pack_rows_range(src, dst, b, std::min(nkeys, b + 1024), ncw, nt);
+    }
+  }
+};
+}  // namespace
+
+int fssb200_pack_rows(const fssb200_ctx *c, const void *cws, void *rows, size_t nkeys) {
+  if (!c) return FSSB200_EINVAL;
+  if (!fssb200_packed_row_bytes(c)) return FSSB200_ESCHEME;
+  if (!cws || !rows) return FSSB200_EINVAL;
+  PackRowsJob job;
+  job.src = static_cast<const uint8_t *>(cws);
+  job.dst = static_cast<uint8_t *>(rows);
+  job.nkeys = nkeys;
+  job.ncw = c->ncw;
+  job.nt = aligned16(rows);
+  Crew *crew = nkeys >= 4096 ? Crew::get() : nullptr;
+  const bool crewed = crew && crew->try_begin(&job);
+  job.run();  // the calling thread takes blocks too
+  if (crewed) crew->end();
+  return 0;
+}
+
+int fssb200_ctx_host_pack_threads(const fssb200_ctx *c) {
+  if (!c || !fssb200_packed_row_bytes(c)) return 0;
+  Crew *crew = Crew::get();
+  return crew ? crew->workers() + 1 : 0;
+}
+
+int fssb200_ctx_host_stats(const fssb200_ctx *c, uint64_t *packed_keys, uint64_t *direct_keys, int *threads) {
+  if (!c) return FSSB200_EINVAL;
+  if (packed_keys) *packed_keys = c->last_packed_keys.load(std::memory_order_relaxed);
+  if (direct_keys) *direct_keys = c->last_direct_keys.load(std::memory_order_relaxed);
+  if (threads) *threads = c->last_pack_threads.load(std::memory_order_relaxed);
+  return 0;
+}
+
+int fssb200_ctx_set_host_mode(fssb200_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 2) return FSSB200_EINVAL;
+  c->host_mode.store(mode, std::memory_order_relaxed);
+  return 0;
+}
+
+int fssb200_ctx_reserve_host(fssb200_ctx *c, size_t max_keys_per_chunk) {
+  if (!c) return FSSB200_EINVAL;
+  c->host_chunk_keys.store(max_keys_per_chunk, std::memory_order_relaxed);
+  return 0;
+}
+
+void fssb200_host_trim(void) { ArenaPool::get().trim(); }
+
+int fssb200_host_cached_bytes(uint64_t *device_bytes, uint64_t *pinned_bytes) {
+  size_t p = 0;
+  const size_t d = ArenaPool::get().cached_bytes(&p);
+  if (device_bytes) *device_bytes = d;
+  if (pinned_bytes) *pinned_bytes = p;
+  return 0;
+}
+
+// ---- point evaluation ------------------------------------------------------------------------------------------------
+int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    const void *xs, void *ys, size_t nkeys) {
+  if (!c) return FSSB200_EINVAL;
+  if (c->p.scheme == FSSB200_SCHEME_GROTTO || c->p.scheme == FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (party != 0 && party != 1) return FSSB200_EINVAL;
+  if (!seeds || !cws || !xs || !ys) return FSSB200_EINVAL;
+  if (c->p.scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
+  if (nkeys == 0) return 0;
+  Crew *crew = nkeys >= 8192 ? Crew::get() : nullptr;
+  if (crew) {
+    DeviceGuard g(c->p.device);
+    if (g.err != cudaSuccess) return int(g.err);
+    const bool in_pinned = is_pinned_or_device(cws) && is_pinned_or_device(seeds) && is_pinned_or_device(xs) &&
+        (!ocws || is_pinned_or_device(ocws));
+    const bool packable = fssb200_packed_row_bytes(c) != 0;
+    // pinned inputs of a scheme without padding: nothing to gain from staging, the link takes the rows as they are
+    const int mode = c->host_mode.load(std::memory_order_relaxed);
+    if ((packable && mode != 1) || !in_pinned)
+      return eval_host_pipelined(c, party, seeds, cws, ocws, xs, ys, nkeys, crew, in_pinned && mode != 2,
+          is_pinned_or_device(ys));
+  }
+  return eval_host_simple(c, party, seeds, cws, ocws, xs, ys, nkeys);
+}
+
+// ---- VDPF ------------------------------------------------------------------------------------------------------------
+int fssb200_vdpf_gen_host(fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *cs,
+    void *ocws, void *status, size_t nkeys) {
+  if (!c) return FSSB200_EINVAL;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!s0s || !alphas || !betas || !cws || !cs || !ocws || !status) return FSSB200_EINVAL;
+  if (nkeys == 0) return 0;
+  const size_t ck = chunk_pref(c, nkeys, size_t(1) << 18), cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  const size_t set_bytes = align_up(ck * 32, 256) + align_up(ck * ib, 256) + align_up(ck * 16, 256) * 2 +
+      align_up(ck * cwb, 256) + align_up(ck * 64, 256) + align_up(ck * 4, 256);
+  ArenaLease L(c->p.device, set_bytes * (nkeys > ck ? 2 : 1), 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = std::min(ck, nkeys - k0);
+    const int b = int(chunk & 1);
+    cudaStream_t s = A.stream[b];
+    uint8_t *d_s0s = A.dev + size_t(b) * set_bytes;
+    uint8_t *d_al = d_s0s + align_up(k * 32, 256);
+    uint8_t *d_be = d_al + align_up(k * ib, 256);
+    uint8_t *d_cws = d_be + align_up(k * 16, 256);
+    uint8_t *d_cs = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_ocws = d_cs + align_up(k * 64, 256);
+    uint8_t *d_st = d_ocws + align_up(k * 16, 256);
+    TRY_BREAK(H2D(d_s0s, static_cast<const uint8_t *>(s0s) + k0 * 32, k * 32, s));
+    TRY_BREAK(H2D(d_al, static_cast<const uint8_t *>(alphas) + k0 * ib, k * ib, s));
+    TRY_BREAK(H2D(d_be, static_cast<const uint8_t *>(betas) + k0 * 16, k * 16, s));
+    TRY_BREAK(cudaMemsetAsync(d_ocws, 0, k * 16, s));  // Gen leaves ocw untouched when it returns 1
+    rc = fssb200_vdpf_gen(c, d_s0s, d_al, d_be, d_cws, d_cs, d_ocws, d_st, k, s);
+    if (rc) break;
+    TRY_BREAK(D2H(static_cast<uint8_t *>(cws) + k0 * cwb, d_cws, k * cwb, s));
+    TRY_BREAK(D2H(static_cast<uint8_t *>(cs) + k0 * 64, d_cs, k * 64, s));
+    TRY_BREAK(D2H(static_cast<uint8_t *>(ocws) + k0 * 16, d_ocws, k * 16, s));
+    TRY_BREAK(D2H(static_cast<uint8_t *>(status) + k0 * 4, d_st, k * 4, s));
+  }
+  return L.drain(rc);
+}
+
+int fssb200_vdpf_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *cs,
+    const void *ocws, const void *xs, void *ys, void *pis, size_t nkeys) {
+  if (!c) return FSSB200_EINVAL;
+  if (c->p.scheme != FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!seeds || !cws || !cs || !ocws || !xs || !ys || !pis) return FSSB200_EINVAL;
+  if (nkeys == 0) return 0;
+  const size_t ck = chunk_pref(c, nkeys, size_t(1) << 18), cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  const size_t set_bytes = align_up(ck * 16, 256) * 3 + align_up(ck * cwb, 256) + align_up(ck * 64, 256) * 2 +
+      align_up(ck * ib, 256);
+  ArenaLease L(c->p.device, set_bytes * (nkeys > ck ? 2 : 1), 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = std::min(ck, nkeys - k0);
+    const int b = int(chunk & 1);
+    cudaStream_t s = A.stream[b];
+    uint8_t *d_seeds = A.dev + size_t(b) * set_bytes;
+    uint8_t *d_cws = d_seeds + align_up(k * 16, 256);
+    uint8_t *d_cs = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_ocws = d_cs + align_up(k * 64, 256);
+    uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_ys = d_xs + align_up(k * ib, 256);
+    uint8_t *d_pis = d_ys + align_up(k * 16, 256);
+    TRY_BREAK(H2D(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, s));
+    TRY_BREAK(H2D(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, s));
+    TRY_BREAK(H2D(d_cs, static_cast<const uint8_t *>(cs) + k0 * 64, k * 64, s));
+    TRY_BREAK(H2D(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, s));
+    TRY_BREAK(H2D(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, s));
+    rc = fssb200_vdpf_eval(c, party, d_seeds, d_cws, d_cs, d_ocws, d_xs, d_ys, d_pis, k, s);
+    if (rc) break;
+    TRY_BREAK(D2H(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, s));
+    TRY_BREAK(D2H(static_cast<uint8_t *>(pis) + k0 * 64, d_pis, k * 64, s));
+  }
+  return L.drain(rc);
+}
+
+// ---- level-major host arrays -----------------------------------------------------------------------------------------
+int fssb200_eval_levelmajor_host(fssb200_ctx *c, int party, const void *seeds, const void *cw_s, const void *cw_v,
+    const void *extra, const void *out_cw, const void *ocws, const void *xs, void *ys, size_t nkeys) {
+  if (!c) return FSSB200_EINVAL;
+  const int scheme = c->p.scheme;
+  if (scheme == FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  if (!seeds || !cw_s || !xs || !ys) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_DCF && (!cw_v || !out_cw)) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_DPF && (!extra || !out_cw)) return FSSB200_EINVAL;
+  if (scheme == FSSB200_SCHEME_HALFTREE && (!extra || !ocws)) return FSSB200_EINVAL;
+  if (nkeys == 0) return 0;
+  const size_t ck = chunk_pref(c, nkeys, size_t(1) << 18), ib = size_t(c->p.in_bytes), n = size_t(c->p.in_bits),
+               nw = (n + 31) / 32;
+  // one set: seeds | cw_s[n][k] | cw_v[n][k] | extra[nw][k] | out_cw | ocws | xs | ys
+  const size_t set_bytes = align_up(ck * 16, 256) * 4 + align_up(n * ck * 16, 256) * (cw_v ? 2 : 1) +
+      (extra ? align_up(nw * ck * 4, 256) : 0) + align_up(ck * ib, 256);
+  ArenaLease L(c->p.device, set_bytes * (nkeys > ck ? 2 : 1), 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  const uint8_t *h_s = static_cast<const uint8_t *>(cw_s), *h_v = static_cast<const uint8_t *>(cw_v),
+                *h_e = static_cast<const uint8_t *>(extra);
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = std::min(ck, nkeys - k0);
+    const int b = int(chunk & 1);
+    cudaStream_t st = A.stream[b];
+    uint8_t *d_seeds = A.dev + size_t(b) * set_bytes;
+    uint8_t *d_s = d_seeds + align_up(k * 16, 256);
+    uint8_t *d_v = d_s + align_up(n * k * 16, 256);
+    uint8_t *d_e = d_v + (cw_v ? align_up(n * k * 16, 256) : 0);
+    uint8_t *d_oc = d_e + (extra ? align_up(nw * k * 4, 256) : 0);
+    uint8_t *d_ocws = d_oc + align_up(k * 16, 256);
+    uint8_t *d_xs = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_ys = d_xs + align_up(k * ib, 256);
+    TRY_BREAK(H2D(d_seeds, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, st));
+    TRY_BREAK(cudaMemcpy2DAsync(d_s, k * 16, h_s + k0 * 16, nkeys * 16, k * 16, n, cudaMemcpyDefault, st));
+    if (cw_v) TRY_BREAK(cudaMemcpy2DAsync(d_v, k * 16, h_v + k0 * 16, nkeys * 16, k * 16, n, cudaMemcpyDefault, st));
+    if (extra) TRY_BREAK(cudaMemcpy2DAsync(d_e, k * 4, h_e + k0 * 4, nkeys * 4, k * 4, nw, cudaMemcpyDefault, st));
+    if (out_cw) TRY_BREAK(H2D(d_oc, static_cast<const uint8_t *>(out_cw) + k0 * 16, k * 16, st));
+    if (ocws) TRY_BREAK(H2D(d_ocws, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, st));
+    TRY_BREAK(H2D(d_xs, static_cast<const uint8_t *>(xs) + k0 * ib, k * ib, st));
+    rc = fssb200_eval_levelmajor(c, party, d_seeds, d_s, cw_v ? d_v : nullptr, extra ? d_e : nullptr,
+        out_cw ? d_oc : nullptr, ocws ? d_ocws : nullptr, d_xs, d_ys, k, st);
+    if (rc) break;
+    TRY_BREAK(D2H(static_cast<uint8_t *>(ys) + k0 * 16, d_ys, k * 16, st));
+  }
+  return L.drain(rc);
+}
+
+// ---- key generation ----------------------------------------------------------------------------------------------------
+int fssb200_gen_host(fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *ocws,
+    size_t nkeys) {
+  if (!c) return FSSB200_EINVAL;
+  if (c->p.scheme == FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!s0s || !alphas || !cws) return FSSB200_EINVAL;
+  const bool grotto = c->p.scheme == FSSB200_SCHEME_GROTTO, half = c->p.scheme == FSSB200_SCHEME_HALFTREE;
+  if ((!grotto && !betas) || (half && !ocws)) return FSSB200_EINVAL;
+  if (nkeys == 0) return 0;
+  const size_t ck = chunk_pref(c, nkeys, size_t(1) << 18), cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+  const size_t set_bytes = align_up(ck * 32, 256) + align_up(ck * cwb, 256) + align_up(ck * 16, 256) * 2 + align_up(ck * ib, 256);
+  ArenaLease L(c->p.device, set_bytes * (nkeys > ck ? 2 : 1), 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += ck, ++chunk) {
+    const size_t k = std::min(ck, nkeys - k0);
+    const int b = int(chunk & 1);
+    cudaStream_t s = A.stream[b];
+    uint8_t *d_s0s = A.dev + size_t(b) * set_bytes;
+    uint8_t *d_cws = d_s0s + align_up(k * 32, 256);
+    uint8_t *d_ocws = d_cws + align_up(k * cwb, 256);
+    uint8_t *d_al = d_ocws + align_up(k * 16, 256);
+    uint8_t *d_be = d_al + align_up(k * ib, 256);
+    TRY_BREAK(H2D(d_s0s, static_cast<const uint8_t *>(s0s) + k0 * 32, k * 32, s));
+    TRY_BREAK(H2D(d_al, static_cast<const uint8_t *>(alphas) + k0 * ib, k * ib, s));
+    if (!grotto) TRY_BREAK(H2D(d_be, static_cast<const uint8_t *>(betas) + k0 * 16, k * 16, s));
+    rc = fssb200_gen(c, d_s0s, d_al, grotto ? nullptr : d_be, d_cws, half ? d_ocws : nullptr, k, s);
+    if (rc) break;
+    TRY_BREAK(D2H(static_cast<uint8_t *>(cws) + k0 * cwb, d_cws, k * cwb, s));
+    if (half) TRY_BREAK(D2H(static_cast<uint8_t *>(ocws) + k0 * 16, d_ocws, k * 16, s));
+  }
+  return L.drain(rc);
+}
+
+// ---- PRG blocks of host seeds (the `prg.Gen(seed)` member of the header shim) -----------------------------------------
+int fssb200_prg_gen_host(fssb200_ctx *c, const void *seeds, void *out, int mul, size_t nseeds) {
+  if (!c) return FSSB200_EINVAL;
+  if (!seeds || !out || (mul != 1 && mul != 2 && mul != 4)) return FSSB200_EINVAL;
+  if (nseeds == 0) return 0;
+  const size_t ck = std::min<size_t>(nseeds, size_t(1) << 20);
+  const size_t set_bytes = align_up(ck * 16, 256) + align_up(ck * 16 * size_t(mul), 256);
+  ArenaLease L(c->p.device, set_bytes * (nseeds > ck ? 2 : 1), 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k0 = 0; k0 < nseeds && !rc; k0 += ck, ++chunk) {
+    const size_t k = std::min(ck, nseeds - k0);
+    const int b = int(chunk & 1);
+    cudaStream_t s = A.stream[b];
+    uint8_t *d_in = A.dev + size_t(b) * set_bytes, *d_out = d_in + align_up(k * 16, 256);
+    TRY_BREAK(H2D(d_in, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, s));
+    rc = fssb200_prg_gen(c, d_in, d_out, mul, k, s);
+    if (rc) break;
+    TRY_BREAK(D2H(static_cast<uint8_t *>(out) + k0 * 16 * size_t(mul), d_out, k * 16 * size_t(mul), s));
+  }
+  return L.drain(rc);
+}
+
+// ---- full-domain evaluation -------------------------------------------------------------------------------------------
+int fssb200_eval_all_host(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
+    void *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count) {
+  if (!c) return FSSB200_EINVAL;
+  if (c->p.scheme == FSSB200_SCHEME_VDPF) return FSSB200_ESCHEME;
+  if (!seeds || !cws || !ys) return FSSB200_EINVAL;
+  const bool half = c->p.scheme == FSSB200_SCHEME_HALFTREE, grotto = c->p.scheme == FSSB200_SCHEME_GROTTO;
+  if (half && !ocws) return FSSB200_EINVAL;
+  const int n = c->p.in_bits;
+  if (n > 40) return FSSB200_EDOMAIN;
+  const uint64_t N = uint64_t(1) << n;
+  if (leaf_begin >= N) return FSSB200_ERANGE;
+  if (leaf_count == 0) leaf_count = N - leaf_begin;
+  if (leaf_count > N - leaf_begin) return FSSB200_ERANGE;
+  const uint64_t granule = fssb200_eval_all_granule(c);
+  if ((leaf_begin | leaf_count) & (granule - 1)) return FSSB200_ERANGE;
+  if (grotto && leaf_begin != 0) return FSSB200_ERANGE;
+  if (nkeys == 0) return 0;
+  const size_t cwb = size_t(c->ncw) * 32, leaf_bytes = grotto ? 1 : 16;
+  // key material of one key (seed + cws + ocw) at the front of each set, leaves behind it
+  const size_t hdr = align_up(16 + cwb + 16, 256);
+  // 64 MiB of leaves per set (Grotto: the scan needs whole keys)
+  uint64_t leaves_per_chunk = grotto ? leaf_count : std::min<uint64_t>(leaf_count, (uint64_t(64) << 20) / leaf_bytes);
+  leaves_per_chunk = std::max<uint64_t>(granule, leaves_per_chunk / granule * granule);
+  const size_t set_bytes = align_up(hdr + leaves_per_chunk * leaf_bytes, 256);
+  const bool many = nkeys > 1 || leaf_count > leaves_per_chunk;
+  ArenaLease L(c->p.device, set_bytes * (many ? 2 : 1), 0);
+  if (!L.a) return L.rc;
+  Arena &A = *L.a;
+  int rc = 0;
+  size_t chunk = 0;
+  for (size_t k = 0; k < nkeys && !rc; ++k) {
+    for (uint64_t l0 = 0; l0 < leaf_count && !rc; l0 += leaves_per_chunk, ++chunk) {
+      const uint64_t cnt = std::min<uint64_t>(leaves_per_chunk, leaf_count - l0);
+      const int b = int(chunk & 1);
+      cudaStream_t s = A.stream[b];
+      uint8_t *d_seed = A.dev + size_t(b) * set_bytes, *d_cws = d_seed + 16, *d_ocw = d_cws + cwb, *d_ys = d_seed + hdr;
+      TRY_BREAK(H2D(d_seed, static_cast<const uint8_t *>(seeds) + k * 16, 16, s));
+      TRY_BREAK(H2D(d_cws, static_cast<const uint8_t *>(cws) + k * cwb, cwb, s));
+      if (half) TRY_BREAK(H2D(d_ocw, static_cast<const uint8_t *>(ocws) + k * 16, 16, s));
+      rc = fssb200_eval_all(c, party, d_seed, d_cws, half ? d_ocw : nullptr, d_ys, 1, leaf_begin + l0, cnt, s);
+      if (rc) break;
+      TRY_BREAK(D2H(static_cast<uint8_t *>(ys) + (k * leaf_count + l0) * leaf_bytes, d_ys, cnt * leaf_bytes, s));
+    }
+  }
+  return L.drain(rc);
+}
+
+}  // extern "C"

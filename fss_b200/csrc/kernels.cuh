@@ -253,7 +253,7 @@ typedef CwTileT<false> CwTile;
 
 // ---- batched point evaluation --------------------------------------------------------------------------------
 // One key per thread; warps own tiles of 32 consecutive keys (grid-stride over tiles).
-// SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE}.
+// SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE,VDPF}, or GROTTO = the O(n) Grotto point walk (schemes.cuh).
 // MODE: 0 = key-major, staged, <= 512 threads, L = 4      (default)
 //       1 = key-major, staged, 1024 threads (<= 64 regs), L = 2
 //       2 = level-major arrays (fssb200_eval_levelmajor), direct coalesced loads
@@ -284,6 +284,8 @@ FSS_D blk point_eval_one(const KParams &P, const typename Prg<PRG>::ctx_t &pc, c
     }
     return y;
   }
+  if (SCHEME == FSSB200_SCHEME_GROTTO)  // O(n) walk: the share bit travels in .x (fssb200_grotto_eval_walk)
+    return make_blk(grotto_walk_body<PRG>(P.keys, pc, n, A.in_bytes, uint32_t(A.party), s0, x, cw), 0u, 0u, 0u);
   if (SCHEME == FSSB200_SCHEME_DPF) return dpf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
   if (SCHEME == FSSB200_SCHEME_DCF) return dcf_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw);
   return ht_eval_body<G, PRG>(P.keys, P.ga, pc, n, uint32_t(A.party), s0, x, cw, ld_blk(A.ocws + k));
@@ -357,7 +359,10 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       const CwKeyMajor cw{A.cws + kk * uint64_t(ncw) * 32u};
       y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
     }
-    if (valid) st_blk(A.ys + k, y);
+    if (valid) {
+      if (SCHEME == FSSB200_SCHEME_GROTTO) reinterpret_cast<uint8_t *>(A.ys)[k] = uint8_t(y.x);  // bool ys[nkeys]
+      else st_blk(A.ys + k, y);
+    }
   }
 }
 

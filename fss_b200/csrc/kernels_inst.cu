@@ -44,7 +44,16 @@ constexpr int kInstPrg = kPrgChaCha;
 
 #define FOR_EACH_GK(X) X(kGrpBytes) X(kGrpU32) X(kGrpU64) X(kGrpU127) X(kGrpU32Mod) X(kGrpU64Mod) X(kGrpU128Mod)
 
-#if FSS_INST_KIND == 1
+#if FSS_INST_KIND == 1 && FSS_INST_SCHEME == 3
+// Grotto point walk: defined over group::Bytes only; key-major Cw through the TMA unit (modes 4 / 5), or direct loads (3)
+template <int MODE>
+static cudaError_t point_launch_grotto(const KParams &P, const PointArgs &A, const LaunchCfg &c) {
+  return launch_kernel(point_kernel<FSSB200_SCHEME_GROTTO, kGrpBytes, kInstPrg, MODE>, c, P, A);
+}
+point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int, int mode) {
+  return mode == 3 ? &point_launch_grotto<3> : (mode == 4 ? &point_launch_grotto<4> : (mode == 5 ? &point_launch_grotto<5> : nullptr));
+}
+#elif FSS_INST_KIND == 1
 template <int G, int MODE>
 static cudaError_t point_launch(const KParams &P, const PointArgs &A, const LaunchCfg &c) {
   return launch_kernel(point_kernel<FSS_INST_SCHEME, G, kInstPrg, MODE>, c, P, A);

@@ -183,11 +183,15 @@ cudaError_t launch_prefix_xor(uint8_t *ys, uint64_t nkeys, uint64_t len, cudaStr
     return cudaGetLastError();
   }
   const uint64_t tiles = (len + kScanTile - 1) / kScanTile;
-  const dim3 grid = dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(nkeys), 1);
-  scan_tile_kernel<<<grid, kScanThreads, 0, stream>>>(ys, len);
-  if (tiles > 1) {
-    scan_carry_kernel<<<unsigned(nkeys), 1024, 0, stream>>>(ys, len, tiles);
-    scan_apply_kernel<<<grid, kScanThreads, 0, stream>>>(ys, len);
+  for (uint64_t k0 = 0; k0 < nkeys; k0 += 65535) {  // grid.y limit
+    const uint64_t kn = nkeys - k0 < 65535 ? nkeys - k0 : 65535;
+    uint8_t *rows = ys + k0 * len;
+    const dim3 grid = dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(kn), 1);
+    scan_tile_kernel<<<grid, kScanThreads, 0, stream>>>(rows, len);
+    if (tiles > 1) {
+      scan_carry_kernel<<<unsigned(kn), 1024, 0, stream>>>(rows, len, tiles);
+      scan_apply_kernel<<<grid, kScanThreads, 0, stream>>>(rows, len);
+    }
   }
   return cudaGetLastError();
 }

@@ -49,6 +49,10 @@ struct Prg<kPrgAes> {
   static FSS_HD blk gen1(const PrgKeys &k, const ctx_t &c, const blk s) {
     return aes128_mmo(c, KeyFixed{k.rk[0]}, s);
   }
+  // left child of a 2-block PRG alone (Grotto walk, last level)
+  static FSS_HD blk gen_left(const PrgKeys &k, const ctx_t &c, const blk s) {
+    return aes128_mmo(c, KeyFixed{k.rk[0]}, s);
+  }
   // output block I alone (every block has its own key): lets a caller consume blocks one at a time
   static constexpr bool kPerBlock = true;
   template <int I>
@@ -123,6 +127,11 @@ struct Prg<kPrgChaCha> {
   static FSS_HD blk gen1(const PrgKeys &k, const ctx_t &, const blk s) {
     blk o[1];
     chacha_gen<1>(k, s, o);
+    return o[0];
+  }
+  static FSS_HD blk gen_left(const PrgKeys &k, const ctx_t &, const blk s) {
+    blk o[2];
+    chacha_gen<2>(k, s, o);
     return o[0];
   }
   static constexpr bool kPerBlock = false;  // one ChaCha block yields all rows

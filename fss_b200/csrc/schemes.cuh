@@ -588,4 +588,73 @@ FSS_HD blk dcf_leaf(const GroupArgs &ga, uint32_t party, blk st, typename Grp<G>
   return GR::into(ga, GR::cneg(ga, y, party));
 }
 
+// ---- Grotto DCF: O(n) point walk (no counterpart in the reference) ---------------------------
+// GrottoDcf::Eval (grotto_dcf.cuh:116-135) is a lookup in a per-key parity tree of 2N-1 bools that Preprocess
+// (:94-104) builds from ALL N leaves: 8 GiB per key at n = 32, so a batch of 2^20 such keys cannot exist.  The
+// share it returns is the parity of the leaf control bits of [0, x+1).  This walk returns a DIFFERENT share of the
+// same secret: [0, e), e = x + 1, is the disjoint union of the left-sibling subtrees along e's path (one for every
+// 1 bit of e), and the control bit of a subtree root reconstructs to 1 iff alpha lies in that subtree (the DPF
+// invariant t0 ^ t1 = [node on alpha's path], dpf.cuh:119-120) -- exactly what the parity of its leaves
+// reconstructs to.  So  share = XOR of the control bits of those left siblings  satisfies
+// share_0 ^ share_1 = 1[alpha <= x] like the reference, in O(n) PRG calls and no memory; per party the bit
+// differs from the reference's (the parity of pseudorandom leaf bits is not the root's bit): "reconstruction-equal,
+// share-parity unpinned".  Full range (e wraps to 0, or e == N): the root's control bit = the party index.
+// Blocks: both children at levels 0..n-2, only the left block (its control bit) at the last level.
+FSS_HD InVal in_succ(const InVal &x, int in_bytes) {
+  InVal e;
+  uint32_t c = 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    e.w[j] = x.w[j] + c;
+    c = (e.w[j] < c) ? 1u : 0u;
+  }
+  if (in_bytes == 1) e.w[0] &= 0xffu;
+  if (in_bytes == 2) e.w[0] &= 0xffffu;
+  if (in_bytes <= 4) e.w[1] = 0;
+  if (in_bytes <= 8) e.w[2] = e.w[3] = 0;
+  return e;
+}
+template <int PRG, class Cw>
+FSS_HD uint32_t grotto_walk_body(const PrgKeys &K, const typename Prg<PRG>::ctx_t &pc, int n, int in_bytes,
+    uint32_t party, blk s0, const InVal &x, const Cw &cw) {
+  const InVal e = in_succ(x, in_bytes);
+  // e == 0 (x + 1 overflowed In) or e == N: the whole domain (grotto_dcf.cuh:121)
+  bool full = (e.w[0] | e.w[1] | e.w[2] | e.w[3]) == 0u;
+  if (n < 8 * in_bytes) {
+    bool is_n = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) is_n = is_n && e.w[j] == ((n >> 5) == j ? (1u << (n & 31)) : 0u);
+    full = full || is_n;
+  }
+  blk st = clamp(s0);
+  st.w |= party;
+  uint32_t acc = 0;
+  cw.begin_level(0);
+  blk cs = cw.s(0);
+  uint32_t cf = cw.flag(0);
+  cw.done_level(0);
+#pragma unroll 1
+  for (int i = 0; i + 1 < n; ++i) {
+    cw.begin_level(i + 1);
+    const blk cs_next = cw.s(i + 1);
+    const uint32_t cf_next = cw.flag(i + 1);
+    cw.done_level(i + 1);
+    const uint32_t eb = in_bit(e, n - 1 - i);
+    blk cwr = cs;
+    cwr.w = (cs.w & ~1u) | cf;
+    blk l, r;
+    dpf_expand<PRG>(K, pc, st, cs, cwr, l, r);
+    acc ^= eb & lsb(l);                              // left sibling lies inside [0, e)
+    st = xor_masked(l, 0u - eb, l ^ r);              // eb ? r : l
+    cs = cs_next;
+    cf = cf_next;
+  }
+  {  // last level: only the left child's control bit can still count (the leaf e itself is outside [0, e))
+    const uint32_t tm = 0u - lsb(st);
+    const blk l = xor_masked(Prg<PRG>::gen_left(K, pc, clamp(st)), tm, cs);
+    acc ^= in_bit(e, 0) & lsb(l);
+  }
+  return full ? party : acc;
+}
+
 }  // namespace fssb200

@@ -9,9 +9,10 @@ explicit PRG key material (the reference's AES path does not compile and its Cha
 process-random), and the Half-Tree / Grotto schemes the reference binding
 does not expose.
 
-Every method evaluates on the GPU through libfssb200.so.  CPU tensors are accepted as in the
-reference (results come back on the inputs' device) and travel through the library's
-host-buffer entry points; there is no CPU evaluation path.
+Every method evaluates on the GPU through libfssb200.so.  gen / eval / eval_all accept CPU tensors as
+in the reference (results come back on the inputs' device) and travel through the library's
+host-buffer entry points; the Grotto preprocess / lookup / walk, relayout and VDPF prove / eval_all
+methods take CUDA tensors only and raise RuntimeError otherwise.  There is no CPU evaluation path.
 """
 from __future__ import annotations
 
@@ -216,3 +217,12 @@ class GrottoDcf:
 
     def eval(self, pt, x):
         return self._ctx.grotto_lookup(pt, x)
+
+    def eval_walk(self, party, s0, cws, x):
+        """O(n) point evaluation without a parity tree, any in_bits (e.g. BASELINE configs[4]: n = 32, 2^20 keys):
+        (N,) uint8 shares, share0 ^ share1 = 1[alpha <= x] as for eval(); the per-party bit is not the reference's
+        (include/fssb200.h: fssb200_grotto_eval_walk)."""
+        validate_party(party)
+        validate_batched("s0", s0, (4,))
+        validate_batched("cws", cws, (self.in_bits + 1, 8))
+        return self._ctx.grotto_walk(party, s0, cws, x)

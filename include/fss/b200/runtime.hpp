@@ -23,7 +23,9 @@ struct ParamsLess {
   bool operator()(const fssb200_params &a, const fssb200_params &b) const { return std::memcmp(&a, &b, sizeof(a)) < 0; }
 };
 
-// Contexts are immutable and shareable between threads / streams; they live until process exit.
+// Contexts are immutable (round keys + parameters, ~1.5 KB of host memory, no device or pinned memory: the staging
+// arenas of the host-array members belong to the library's per-device pool and are sized per call), so one cached
+// context per parameter set serves every thread and stream; they live until process exit.
 inline fssb200_ctx *ContextFor(fssb200_params p) {
   static std::mutex mu;
   static std::map<fssb200_params, fssb200_ctx *, ParamsLess> cache;
@@ -36,7 +38,6 @@ inline fssb200_ctx *ContextFor(fssb200_params p) {
   if (it != cache.end()) return it->second;
   fssb200_ctx *ctx = nullptr;
   Check(fssb200_ctx_create(&p, &ctx), "fssb200_ctx_create");
-  Check(fssb200_ctx_reserve_host(ctx, 0), "fssb200_ctx_reserve_host");
   cache.emplace(p, ctx);
   return ctx;
 }

@@ -26,14 +26,8 @@ cuda::std::array<int4, mul> GenOnDevice(int prg_tag, const uint8_t key64[64], in
   p.in_bytes = 1;
   p.prg = prg_tag;
   std::memcpy(p.prg_key, key64, 64);
-  fssb200_ctx *ctx = b200::ContextFor(p);
-  b200::DeviceBlock in(seed, nullptr);
-  int4 *out = nullptr;
-  if (cudaMallocAsync(reinterpret_cast<void **>(&out), sizeof(int4) * mul, nullptr) != cudaSuccess) throw std::bad_alloc();
-  b200::Check(fssb200_prg_gen(ctx, in.ptr, out, mul, 1, nullptr), "fssb200_prg_gen");
   cuda::std::array<int4, mul> r{};
-  cudaMemcpy(r.data(), out, sizeof(int4) * mul, cudaMemcpyDeviceToHost);
-  cudaFreeAsync(out, nullptr);
+  b200::Check(fssb200_prg_gen_host(b200::ContextFor(p), &seed, r.data(), mul, 1), "fssb200_prg_gen_host");
   return r;
 }
 }  // namespace b200_detail

@@ -24,8 +24,8 @@
  *
  * Ownership (dpf.cuh:86,225; eval_all_gpu.cuh:498): the caller allocates every
  * buffer; the library never allocates or frees device memory inside an eval /
- * gen call.  The `_host` variants stage through a per-context pinned/device
- * arena that is created once by fssb200_ctx_reserve_host().
+ * gen call.  The `_host` variants stage through arenas of a process-wide pool
+ * (see "host-buffer entry points").
  *
  * Errors: every function returns 0 on success, a negative FSSB200_E* code for an
  * invalid argument, or a positive `cudaError_t`.  Nothing throws or aborts.
@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FSSB200_VERSION 101 /* 0.1.1: fssb200_params grew hash_iv (VDPF) */
+#define FSSB200_VERSION 200 /* 0.2.0: re-entrant host entry points (arena pool), multi-device calls, Grotto walk */
 
 /* ---- enums --------------------------------------------------------------- */
 
@@ -89,7 +89,7 @@ enum {
   FSSB200_EALIGN = -5,     /* pointer not 16-byte aligned                         */
   FSSB200_ENODEVICE = -6,  /* no CUDA device / device index out of range          */
   FSSB200_ERANGE = -7,     /* leaf range not aligned / out of the domain          */
-  FSSB200_ENOARENA = -8    /* _host call without fssb200_ctx_reserve_host()       */
+  FSSB200_ENOARENA = -8    /* (0.1 only: _host call without a reserved arena)     */
 };
 
 /* ---- context --------------------------------------------------------------- */
@@ -214,6 +214,19 @@ int fssb200_grotto_preprocess(const fssb200_ctx *ctx, int party, const void *see
 int fssb200_grotto_eval(const fssb200_ctx *ctx, const void *pt, const void *xs, void *ys,
                         size_t nkeys, void *stream);
 
+/* O(n) Grotto point evaluation for domains where the parity tree cannot exist (BASELINE configs[4]:
+ * n = 32, 2^20 keys; the tree of grotto_dcf.cuh:78-81 would be 8 GiB per key -- SURVEY.md H6):
+ * ys[k] (1 byte) = XOR of the control bits of the left-sibling subtree roots along the path of
+ * e = xs[k] + 1, i.e. of the disjoint subtrees that tile [0, e).  ys0[k] ^ ys1[k] = 1[alpha_k <= xs[k]]
+ * exactly like `GrottoDcf::Eval` (grotto_dcf.cuh:116-135), with the same edge rule (e == 0 or
+ * e == N: the whole domain, share = party), but the per-party bit is NOT the reference's: that one
+ * is the parity of N pseudorandom leaf bits and cannot be had without expanding the tree.
+ * "Reconstruction-equal, share-parity unpinned": use fssb200_grotto_preprocess + fssb200_grotto_eval
+ * where per-share bit-exactness with the reference matters (n <= 31, 2N-1 bytes per key).
+ *   seeds : int4[nkeys]   cws : Cw[nkeys][n+1] (Dpf::Cw)   xs : In[nkeys]   ys : uint8[nkeys]  */
+int fssb200_grotto_eval_walk(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
+                             const void *xs, void *ys, size_t nkeys, void *stream);
+
 /* ---- VDPF (verifiable DPF) -----------------------------
  * Context scheme FSSB200_SCHEME_VDPF.  Key of party i = cws (n entries of Dpf-style
  * 32-byte Cw, vdpf.cuh:77-80) + cs (4 x int4 correction seed) + ocw + s0s[i].
@@ -278,15 +291,39 @@ int fssb200_eval_levelmajor(const fssb200_ctx *ctx, int party, const void *seeds
 /* ---- host-buffer entry points (what a CPU caller of the reference binds) -----
  * Same semantics with HOST pointers (pageable or pinned): inputs are staged to the
  * device in chunks, evaluated, and results copied back, with copies and kernels
- * overlapped on internal streams.  The call returns when ys is complete.
- * fssb200_ctx_reserve_host() creates the staging arena once (the only allocating
- * call); max_keys_per_chunk = 0 picks a default.  For DPF / Half-Tree contexts it also
- * starts the worker threads and pinned staging of the row-packing path (see "packed rows"
- * below) when this process is the only rank on the host (LOCAL_WORLD_SIZE unset or 1) and
- * has at least 6 usable cores; FSSB200_PACK_THREADS overrides the count (0 = off).
- * The _host calls of ONE context use its arena and are therefore not re-entrant: call them
- * from one thread at a time per context (different contexts are independent). */
+ * overlapped on internal streams.  The call returns when the outputs are complete.
+ *
+ * Re-entrant and thread-safe like the reference's members (dpf.cuh:170 is a const
+ * pure function; src/bench_cpu.cu:157-161 calls it under `#pragma omp parallel for`):
+ * a context owns no staging memory.  Each call checks an arena (device staging, pinned
+ * staging, streams, events) out of a process-wide per-device pool, sized from ITS batch
+ * (a 1-key call takes 1 MiB), and hands it back when it returns -- also on every error
+ * path, after its streams are drained.  The pool keeps up to 4 idle arenas per device for
+ * reuse; fssb200_host_trim() frees them.  fssb200_ctx_reserve_host() is kept from 0.1:
+ * it only records the preferred keys per pipeline chunk (0 = library default) and never
+ * allocates; no call returns FSSB200_ENOARENA any more.
+ *
+ * fssb200_eval_host, batches of >= 8192 keys on a host with >= 2 usable cores per rank
+ * (cores / LOCAL_WORLD_SIZE; FSSB200_PACK_THREADS overrides): adaptive pack / direct
+ * pipeline.  For DPF / Half-Tree keys worker threads strip the 15 padding bytes of every
+ * 32-byte Cw into pinned staging ("packed rows" below), chunk after chunk from the front
+ * of the batch, and the calling thread submits each finished chunk as one H2D copy +
+ * fssb200_eval_packed + D2H; whenever the link is about to run dry and no packed chunk is
+ * ready, a chunk from the back of the batch crosses in the reference layout straight from
+ * the caller's (pinned) buffer.  Pageable inputs are always staged by the workers (packed,
+ * or copied for schemes without padding).  fssb200_ctx_set_host_mode(): 0 = adaptive
+ * (default), 1 = reference layout only, 2 = staged chunks only.  A call that finds the
+ * worker threads lent to another call runs the plain chunked path instead. */
 int fssb200_ctx_reserve_host(fssb200_ctx *ctx, size_t max_keys_per_chunk);
+int fssb200_ctx_set_host_mode(fssb200_ctx *ctx, int mode);
+/* Keys of this context's last fssb200_eval_host call that crossed the link staged by the host
+ * threads (packed rows; plain copies for schemes without padding) / in the reference layout
+ * straight from the caller's buffers, and the host threads that call used (0: plain chunked path). */
+int fssb200_ctx_host_stats(const fssb200_ctx *ctx, uint64_t *packed_keys, uint64_t *direct_keys,
+                           int *threads);
+/* Frees the idle arenas of the pool; bytes they hold right now. */
+void fssb200_host_trim(void);
+int fssb200_host_cached_bytes(uint64_t *device_bytes, uint64_t *pinned_bytes);
 int fssb200_eval_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
                       const void *ocws, const void *xs, void *ys, size_t nkeys);
 int fssb200_eval_all_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
@@ -314,13 +351,13 @@ int fssb200_eval_levelmajor_host(fssb200_ctx *ctx, int party, const void *seeds,
  * `s` entries of a key followed by one 16-byte word of flag bits (bit i = the bool at byte 16
  * of entry i, i < 128): fssb200_packed_row_bytes() = ncw*16 + 16 (0 for schemes whose Cw has
  * no padding).  fssb200_pack_rows() converts HOST arrays (reference layout in, packed rows
- * out; multi-threaded on the worker threads of fssb200_ctx_reserve_host when they exist) --
+ * out; multi-threaded on the library's host worker threads when they are idle) --
  * a format conversion, no evaluation happens on the CPU.  fssb200_eval_packed() is
  * fssb200_eval() on packed rows in device memory (rows fetched by the TMA unit, four levels per
- * 64-byte chunk).  fssb200_eval_host() uses both internally when this process has enough cores
- * to strip the padding faster than the PCIe link would move it (see fssb200_ctx_reserve_host). */
+ * 64-byte chunk).  fssb200_eval_host() uses both internally (adaptive pipeline above). */
 size_t fssb200_packed_row_bytes(const fssb200_ctx *ctx);
-/* Threads fssb200_eval_host() packs with (0: it copies the reference layout as it is). */
+/* Threads a large fssb200_eval_host() call of this process stages rows with, the calling
+ * thread included (0: scheme without padding, or fewer than 2 cores per rank). */
 int fssb200_ctx_host_pack_threads(const fssb200_ctx *ctx);
 int fssb200_pack_rows(const fssb200_ctx *ctx, const void *cws, void *rows, size_t nkeys);
 int fssb200_eval_packed(const fssb200_ctx *ctx, int party, const void *seeds, const void *rows,
@@ -333,6 +370,8 @@ int fssb200_eval_packed(const fssb200_ctx *ctx, int party, const void *seeds, co
  * (prg/aes128_mmo.cuh:72-93, prg/chacha.cuh:95-127). */
 int fssb200_prg_gen(const fssb200_ctx *ctx, const void *seeds, void *out, int mul, size_t nseeds,
                     void *stream);
+/* The same with HOST arrays (arena pool; re-entrant): the `prg.Gen(seed)` member of the C++ shim. */
+int fssb200_prg_gen_host(fssb200_ctx *ctx, const void *seeds, void *out, int mul, size_t nseeds);
 /* Number of kernel launches this context has issued (bench.py's gpu_launches). */
 uint64_t fssb200_ctx_launch_count(const fssb200_ctx *ctx);
 /* Integer-pipe / shared-memory issue-rate microbenchmarks used for the roofline

@@ -306,6 +306,26 @@ int emul_evalall(const fssb200_params *p, int party, size_t nkeys, const void *s
   return 0;
 }
 
+// Grotto O(n) point walk (schemes.cuh: grotto_walk_body): ys[k] = one share bit
+int emul_grotto_walk(const fssb200_params *p, int party, size_t nkeys, const void *seeds, const void *cws,
+    const void *xs, void *ys) {
+  EmuCtx c;
+  make_ctx(*p, c);
+  if (p->scheme != FSSB200_SCHEME_GROTTO) return FSSB200_ESCHEME;
+  const blk *sd = static_cast<const blk *>(seeds);
+  for (size_t k = 0; k < nkeys; ++k) {
+    const InVal x = load_in(static_cast<const uint8_t *>(xs) + k * c.in_bytes, c.in_bytes);
+    const CwKeyMajor cw{static_cast<const uint8_t *>(cws) + k * uint64_t(c.ncw) * 32};
+    uint32_t bit;
+    if (p->prg == FSSB200_PRG_AES128_MMO)
+      bit = grotto_walk_body<kPrgAes>(c.keys, lane_ctx<kPrgAes>(k), c.n, c.in_bytes, uint32_t(party), sd[k], x, cw);
+    else
+      bit = grotto_walk_body<kPrgChaCha>(c.keys, NoCtx{}, c.n, c.in_bytes, uint32_t(party), sd[k], x, cw);
+    static_cast<uint8_t *>(ys)[k] = uint8_t(bit);
+  }
+  return 0;
+}
+
 int emul_hash(const fssb200_params *p, int which, size_t n, const void *msgs, void *out) {
   EmuCtx c;
   make_ctx(*p, c);

@@ -233,7 +233,7 @@ def test_host_entry_points(dev, orc):
     ("dpf", 64, "u128", "chacha", 8200), ("dpf", 128, "bytes", "aes128_mmo", 300), ("dpf", 5, "u32", "aes128_mmo", 33),
     ("halftree", 32, "bytes", "chacha", 1), ("dpf", 3, "bytes", "aes128_mmo", 8193), ("halftree", 1, "u32", "aes128_mmo", 70),
 ])
-def test_packed_rows(dev, orc, monkeypatch, scheme, n, group, prg, nkeys):
+def test_packed_rows(dev, orc, scheme, n, group, prg, nkeys):
     p = Params(scheme=scheme, in_bits=n, group=group, prg=prg, hash_key=HASH_KEY_BENCH)
     s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=7 * n + nkeys)
     xs[0] = (1 << n) - 1
@@ -259,14 +259,19 @@ def test_packed_rows(dev, orc, monkeypatch, scheme, n, group, prg, nkeys):
     for party in (0, 1):
         ys = ctx.eval_packed(party, T(s0s[:, party], dev), rows_d, xs, ocws_d)
         assert np.array_equal(N(ys), want[party]), party
-    # host entry point with the packing pipeline forced on (several chunks, three staging slots) and forced off
-    for threads in ("7", "0"):
-        monkeypatch.setenv("FSSB200_PACK_THREADS", threads)
-        ctx_h = mkctx(p)
-        ctx_h.reserve_host(2048)
-        ys = ctx_h.eval(1, torch.from_numpy(np.ascontiguousarray(s0s[:, 1]).view(np.int32)), cws_h, xs,
-                        None if ooc is None else torch.from_numpy(ooc.view(np.int32)))
-        assert ys.device.type == "cpu" and np.array_equal(N(ys), want[1]), threads
+    # host entry point: adaptive pipeline (0), reference layout only (1), staged chunks only (2); several chunks
+    seeds_h = torch.from_numpy(np.ascontiguousarray(s0s[:, 1]).view(np.int32))
+    ocws_h = None if ooc is None else torch.from_numpy(ooc.view(np.int32))
+    ctx_h = mkctx(p)
+    ctx_h.reserve_host(2048)
+    for mode in (0, 1, 2):
+        ctx_h.set_host_mode(mode)
+        for pin in (False, True):
+            a = [seeds_h, cws_h, ocws_h]
+            if pin:
+                a = [None if v is None else v.pin_memory() for v in a]
+            ys = ctx_h.eval(1, a[0], a[1], xs, a[2])
+            assert ys.device.type == "cpu" and np.array_equal(N(ys), want[1]), (mode, pin)
 
 
 def test_packed_rows_rejects_dcf(dev):
@@ -319,11 +324,11 @@ def _u127_add(a, b):
 
 
 def test_c3_full_size_reconstruction(dev, orc):
-    """BASELINE config 3: DCF, n = 64, Uint<u128, 2^127>, Aes128Mmo<4>, 2^20 keys here (8.7 GB of keys at 2^22):
+    """BASELINE config 3 at full size: DCF, n = 64, Uint<u128, 2^127>, Aes128Mmo<4>, 2^22 keys (8.7 GB of keys):
     y0 + y1 == (x < alpha ? beta : 0)."""
     p = Params(scheme="dcf", in_bits=64, group="u128")
     ctx = mkctx(p)
-    k = 1 << 20
+    k = 1 << 22
     g = torch.Generator(device=dev).manual_seed(43)
     s0s = torch.randint(-2 ** 31, 2 ** 31, (k, 2, 4), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
     betas = torch.randint(-2 ** 31, 2 ** 31, (k, 4), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
@@ -419,7 +424,11 @@ def test_error_codes_on_device(dev):
     hs = small.handle(0)
     assert L.lib.fssb200_eval_all(hs, 0, p, p, None, p, 1, 5, 0, None) == L.E_RANGE       # not unit aligned
     assert L.lib.fssb200_eval_all(hs, 0, p, p, None, p, 1, 1 << 20, 0, None) == L.E_RANGE  # outside the domain
-    assert L.lib.fssb200_eval_host(h, 0, p, p, None, p, p, 1) in (L.E_NOARENA, 0)
+    gr = 1 << 17                                                                            # begin + count wraps uint64
+    assert L.lib.fssb200_eval_all(hs, 0, p, p, None, p, 1, gr, 2 ** 64 - gr, None) == L.E_RANGE
+    assert L.lib.fssb200_eval_all_host(hs, 0, p, p, None, p, 1, gr, 2 ** 64 - gr) == L.E_RANGE
+    assert L.lib.fssb200_eval_host(h, 2, p, p, None, p, p, 1) == L.E_INVAL
+    assert L.lib.fssb200_ctx_set_host_mode(h, 3) == L.E_INVAL
     g = fss_b200.Context("grotto", 10)
     assert L.lib.fssb200_eval(g.handle(0), 0, p, p, None, p, p, 1, None) == L.E_SCHEME
 

@@ -126,3 +126,45 @@ def test_golden_through_kernel_bodies(emu, golden):
             assert np.array_equal(got, c[f"ys{party}"]), (c.name, party)
         ec, eoc = emul_gen(emu, p, c["s0s"], c.alphas, c.betas)
         assert np.array_equal(c.masked_cws(ec), c.masked_cws(c["cws"])), c.name
+
+
+def emul_walk(emu, p, party, seeds, cws, xs):
+    k = len(seeds)
+    ys, cp, xb = np.zeros(k, np.uint8), p.c(), pack_ints(xs, p.in_bytes)
+    rc = emu.emul_grotto_walk(C.byref(cp), party, C.c_size_t(k), _vp(np.ascontiguousarray(seeds)), _vp(cws), _vp(xb),
+                              _vp(ys))
+    assert rc == 0
+    return ys
+
+
+@pytest.mark.parametrize("prg", ["aes128_mmo", "chacha"])
+def test_grotto_walk_reconstructs_like_the_reference(emu, orc, prg):
+    """The O(n) Grotto walk (SURVEY.md H6) returns a different SHARE than GrottoDcf::Eval but the same SECRET:
+    share0 ^ share1 == 1[alpha <= x] == reference Preprocess + Eval reconstructed (grotto_dcf.cuh:94-135)."""
+    for n, in_bytes in ((1, 1), (2, 4), (5, 1), (8, 1), (8, 4), (10, 2), (16, 2), (32, 4), (33, 8), (64, 8), (100, 16),
+                        (128, 16)):
+        p = Params(scheme="grotto", in_bits=n, prg=prg, in_bytes=in_bytes)
+        k = 48
+        s0s, alphas, _, xs = synth_inputs(p, k, seed=100 + n)
+        top = (1 << n) - 1
+        xs[0], xs[1], alphas[2], xs[2], alphas[3], xs[3] = 0, top, 0, 0, top, top
+        xs[4], alphas[5], xs[5] = alphas[4], top, max(0, top - 1)
+        cws = orc.gen(p, s0s, alphas, None)
+        w0 = emul_walk(emu, p, 0, s0s[:, 0], cws, xs)
+        w1 = emul_walk(emu, p, 1, s0s[:, 1], cws, xs)
+        want = np.array([1 if int(a) <= int(x) else 0 for a, x in zip(alphas, xs)], np.uint8)
+        assert np.array_equal(w0 ^ w1, want), (n, in_bytes, prg)
+        if n <= 10:  # every point of the domain against the reference's parity-tree shares, reconstructed
+            m = min(k, 6)
+            for kk in range(m):
+                allx = list(range(1 << n))
+                rep = lambda a: np.repeat(a[kk:kk + 1], len(allx), axis=0)
+                a0 = emul_walk(emu, p, 0, rep(s0s[:, 0]), rep(cws), allx)
+                a1 = emul_walk(emu, p, 1, rep(s0s[:, 1]), rep(cws), allx)
+                r0 = orc.evalall(p, 0, s0s[kk:kk + 1, 0], cws[kk:kk + 1])[0]   # GrottoDcf::EvalAll
+                r1 = orc.evalall(p, 1, s0s[kk:kk + 1, 1], cws[kk:kk + 1])[0]
+                assert np.array_equal(a0 ^ a1, r0 ^ r1), (n, kk)
+            # GrottoDcf::Preprocess + Eval (the lookup, with its e == 0 / e == N rule) on the sampled points
+            l0 = orc.grotto_lookup(p, orc.grotto_preprocess(p, 0, s0s[:, 0], cws), xs)
+            l1 = orc.grotto_lookup(p, orc.grotto_preprocess(p, 1, s0s[:, 1], cws), xs)
+            assert np.array_equal(w0 ^ w1, l0 ^ l1), (n, in_bytes, prg)
