@@ -72,6 +72,13 @@ SYMBOLS = {
     "fssb200_eval_all_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _SZ, _U64, _U64]),
     "fssb200_gen_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
     "fssb200_eval_levelmajor_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ]),
+    "fssb200_eval_multi": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "fssb200_eval_all_multi": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "fssb200_gen_multi": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "fssb200_multi_sync": (_I, [_VP, _I, _VP, _VP]),
+    "fssb200_key_shard": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "fssb200_leaf_shard": (_I, [_VP, _I, _I, C.POINTER(_U64), C.POINTER(_U64)]),
+    "fssb200_eval_host_multi": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "fssb200_packed_row_bytes": (_SZ, [_VP]),
     "fssb200_ctx_host_pack_threads": (_I, [_VP]),
     "fssb200_pack_rows": (_I, [_VP, _VP, _VP, _SZ]),

@@ -132,10 +132,12 @@ int host_thread_budget() {
 // worker threads: one process-wide crew, lent to one call at a time
 // ---------------------------------------------------------------------------------------------------------------
 struct CrewJob {
-  virtual void run() = 0;  // called once by every worker; returns when the job has nothing left for it
+  virtual void run() = 0;  // called once by every worker lent to the job; returns when the job has nothing left for it
   virtual ~CrewJob() {}
 };
 
+// The crew can serve several calls at once (one process driving several GPUs: fssb200_eval_host_multi): a call
+// borrows up to `want` idle workers and gets whatever is idle (possibly none).
 class Crew {
  public:
   static Crew *get() {
@@ -145,52 +147,65 @@ class Crew {
     }();
     return crew;
   }
-  int workers() const { return int(th_.size()); }
-  // Lends the crew to `job` if it is idle.  The caller must call end() before `job` dies.
-  bool try_begin(CrewJob *job) {
+  int workers() const { return int(slot_.size()); }
+  // Lends up to `want` idle workers to `job`; returns how many (0: none idle).  The caller must call end(job) before
+  // `job` dies.
+  int begin(CrewJob *job, int want) {
     std::lock_guard<std::mutex> l(mu_);
-    if (job_) return false;
-    job_ = job;
-    running_ = int(th_.size());
-    ++gen_;
-    cv_start_.notify_all();
-    return true;
+    int got = 0;
+    for (auto &s : slot_) {
+      if (got >= want) break;
+      if (!s.job) {
+        s.job = job;
+        s.fresh = true;
+        ++got;
+      }
+    }
+    if (got) cv_start_.notify_all();
+    return got;
   }
-  // Blocks until every worker has left the job.
-  void end() {
+  // Blocks until every worker lent to `job` has left it.
+  void end(CrewJob *job) {
     std::unique_lock<std::mutex> l(mu_);
-    cv_done_.wait(l, [this] { return running_ == 0; });
-    job_ = nullptr;
+    cv_done_.wait(l, [&] {
+      for (auto &s : slot_)
+        if (s.job == job) return false;
+      return true;
+    });
   }
 
  private:
-  explicit Crew(int n) {
-    for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); }), th_.back().detach();
+  struct Slot {
+    CrewJob *job = nullptr;
+    bool fresh = false;
+  };
+  explicit Crew(int n) : slot_(size_t(n)) {
+    for (int i = 0; i < n; ++i) std::thread([this, i] { loop(i); }).detach();
   }
-  void loop() {
-    uint64_t seen = 0;
+  void loop(int i) {
     for (;;) {
       CrewJob *job;
       {
         std::unique_lock<std::mutex> l(mu_);
-        cv_start_.wait(l, [&] { return gen_ != seen; });
-        seen = gen_;
-        job = job_;
+        cv_start_.wait(l, [&] { return slot_[size_t(i)].fresh; });
+        slot_[size_t(i)].fresh = false;
+        job = slot_[size_t(i)].job;
       }
       job->run();
       {
         std::lock_guard<std::mutex> l(mu_);
-        if (--running_ == 0) cv_done_.notify_all();
+        slot_[size_t(i)].job = nullptr;
+        cv_done_.notify_all();
       }
     }
   }
-  std::vector<std::thread> th_;
+  std::vector<Slot> slot_;
   std::mutex mu_;
   std::condition_variable cv_start_, cv_done_;
-  CrewJob *job_ = nullptr;
-  uint64_t gen_ = 0;
-  int running_ = 0;
 };
+
+// Workers one call may borrow: all of them, or this thread's share when a multi-device call set one
+thread_local int t_crew_share = 0;  // 0 = no limit
 
 // ---------------------------------------------------------------------------------------------------------------
 // arena pool
@@ -503,10 +518,8 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
   P.tail.store(P.nchunks);
   P.free_upto.store(P.nslots);
 
-  const bool crewed = crew && crew->try_begin(&P);
-  if (!crewed && !allow_direct) {
-    // no workers right now and pageable inputs: the calling thread stages alone (still correct, just slower)
-  }
+  // (no idle worker and pageable inputs: the calling thread stages alone -- still correct, just slower)
+  const int lent = crew ? crew->begin(&P, t_crew_share > 0 ? t_crew_share : crew->workers()) : 0;
 
   struct Issue {
     size_t chunk;
@@ -631,7 +644,7 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
     }
   }
   P.stop.store(true, std::memory_order_release);
-  if (crewed) crew->end();
+  if (lent) crew->end(&P);
   // drain: results of every issued chunk
   for (size_t i = retired; i < issued; ++i) {
     const int first = rc;
@@ -642,7 +655,7 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
   rc = L.drain(rc);
   c->last_direct_keys.store(direct_keys, std::memory_order_relaxed);
   c->last_packed_keys.store(nkeys - direct_keys, std::memory_order_relaxed);  // staged: packed, or copied (no padding)
-  c->last_pack_threads.store(crewed ? crew->workers() + 1 : 1, std::memory_order_relaxed);
+  c->last_pack_threads.store(lent + 1, std::memory_order_relaxed);
   return rc;
 }
 
@@ -716,9 +729,9 @@ int fssb200_pack_rows(const fssb200_ctx *c, const void *cws, void *rows, size_t 
   job.ncw = c->ncw;
   job.nt = aligned16(rows);
   Crew *crew = nkeys >= 4096 ? Crew::get() : nullptr;
-  const bool crewed = crew && crew->try_begin(&job);
+  const int lent = crew ? crew->begin(&job, crew->workers()) : 0;
   job.run();  // the calling thread takes blocks too
-  if (crewed) crew->end();
+  if (lent) crew->end(&job);
   return 0;
 }
 
@@ -1018,6 +1031,46 @@ int fssb200_eval_all_host(fssb200_ctx *c, int party, const void *seeds, const vo
     }
   }
   return L.drain(rc);
+}
+
+// ---- one process, several GPUs: host arrays of the WHOLE batch -------------------------------------------------------
+// Keys are independent (dpf.cuh:170-214), so device d takes the contiguous key range [d*K/ndev .., (d+1)*K/ndev) of
+// the caller's arrays; one host thread per device runs the pipeline above on its range with its share of the worker
+// threads.  No collective, no peer traffic.
+int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const void *seeds, const void *cws,
+    const void *ocws, const void *xs, void *ys, size_t nkeys, int *rcs) {
+  if (!ctxs || ndev < 1 || ndev > 64) return FSSB200_EINVAL;
+  for (int d = 0; d < ndev; ++d) {
+    if (!ctxs[d]) return FSSB200_EINVAL;
+    const fssb200_params &a = ctxs[0]->p, &b = ctxs[d]->p;
+    if (a.scheme != b.scheme || a.in_bits != b.in_bits || a.in_bytes != b.in_bytes || a.group != b.group ||
+        a.prg != b.prg)
+      return FSSB200_EINVAL;  // one key batch = one parameter set
+  }
+  if (!seeds || !cws || !xs || !ys) return FSSB200_EINVAL;
+  const size_t cwb = size_t(ctxs[0]->ncw) * 32, ib = size_t(ctxs[0]->p.in_bytes);
+  Crew *crew = Crew::get();
+  const int share = crew ? std::max(1, crew->workers() / ndev) : 0;
+  std::vector<int> rc(size_t(ndev), 0);
+  std::vector<std::thread> th;
+  const size_t base = nkeys / size_t(ndev), rem = nkeys % size_t(ndev);
+  auto run = [&](int d) {
+    const size_t k0 = size_t(d) * base + std::min<size_t>(size_t(d), rem), k = base + (size_t(d) < rem ? 1 : 0);
+    t_crew_share = share;
+    rc[size_t(d)] = fssb200_eval_host(ctxs[d], party, static_cast<const uint8_t *>(seeds) + k0 * 16,
+        static_cast<const uint8_t *>(cws) + k0 * cwb, ocws ? static_cast<const uint8_t *>(ocws) + k0 * 16 : nullptr,
+        static_cast<const uint8_t *>(xs) + k0 * ib, static_cast<uint8_t *>(ys) + k0 * 16, k);
+    t_crew_share = 0;
+  };
+  for (int d = 1; d < ndev; ++d) th.emplace_back(run, d);
+  run(0);
+  for (auto &t : th) t.join();
+  int first = 0;
+  for (int d = 0; d < ndev; ++d) {
+    if (rcs) rcs[d] = rc[size_t(d)];
+    if (!first && rc[size_t(d)]) first = rc[size_t(d)];
+  }
+  return first;
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "../../fssb200.h"
@@ -26,11 +27,11 @@ struct ParamsLess {
 // Contexts are immutable (round keys + parameters, ~1.5 KB of host memory, no device or pinned memory: the staging
 // arenas of the host-array members belong to the library's per-device pool and are sized per call), so one cached
 // context per parameter set serves every thread and stream; they live until process exit.
-inline fssb200_ctx *ContextFor(fssb200_params p) {
+inline fssb200_ctx *ContextFor(fssb200_params p, int device = -1) {  // device < 0: the current device
   static std::mutex mu;
   static std::map<fssb200_params, fssb200_ctx *, ParamsLess> cache;
-  int dev = 0;
-  cudaGetDevice(&dev);
+  int dev = device;
+  if (dev < 0) cudaGetDevice(&dev);
   p.device = dev;
   p.reserved = 0;
   std::lock_guard<std::mutex> lock(mu);
@@ -59,6 +60,23 @@ fssb200_params MakeParams(int scheme, const Prg &prg, int pred = FSSB200_PRED_LT
   if (hash_key) std::memcpy(p.hash_key, hash_key, 16);
   return p;
 }
+
+// Multi-device members (`EvalBatchMulti`): contexts of one parameter set on `ndev` devices + the per-device error
+// codes folded into one exception.
+struct MultiCall {
+  std::vector<fssb200_ctx *> ctxs;
+  std::vector<int> rcs;
+  MultiCall(const fssb200_params &p, int ndev, const int *devices) : rcs(size_t(ndev), 0) {
+    for (int d = 0; d < ndev; ++d) ctxs.push_back(ContextFor(p, devices ? devices[d] : d));
+  }
+  void Check(int rc, const char *what) const {
+    if (rc == 0) return;
+    std::string msg = std::string(what) + ":";
+    for (size_t d = 0; d < rcs.size(); ++d)
+      if (rcs[d]) msg += " device " + std::to_string(d) + ": " + fssb200_strerror(rcs[d]) + ";";
+    throw std::runtime_error(msg);
+  }
+};
 
 // A 16-byte value the reference passes by value (a seed, an output CW) as a stream-ordered device temp.
 struct DeviceBlock {

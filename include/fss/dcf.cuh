@@ -62,6 +62,26 @@ public:
   void EvalBatchHost(bool b, const int4 *seeds, const Cw *cws, const In *xs, int4 *ys, size_t nkeys) const {
     b200::Check(fssb200_eval_host(Context(), b, seeds, cws, nullptr, xs, ys, nkeys), "Dcf::EvalBatchHost");
   }
+  // one process, ndev GPUs: per-device arrays, one stream per device, no collective (see Dpf::EvalBatchMulti)
+  fssb200_params Params() const {
+    return b200::MakeParams<in_bits, Group, Prg, In>(FSSB200_SCHEME_DCF, prg,
+                                                     pred == DcfPred::kLt ? FSSB200_PRED_LT : FSSB200_PRED_GT);
+  }
+  void EvalBatchMulti(bool b, int ndev, const int *devices, const int4 *const *seeds, const Cw *const *cws,
+                      const In *const *xs, int4 *const *ys, const size_t *nkeys,
+                      const cudaStream_t *streams = nullptr) const {
+    b200::MultiCall m(Params(), ndev, devices);
+    m.Check(fssb200_eval_multi(m.ctxs.data(), ndev, b, reinterpret_cast<const void *const *>(seeds),
+                               reinterpret_cast<const void *const *>(cws), nullptr,
+                               reinterpret_cast<const void *const *>(xs), reinterpret_cast<void *const *>(ys), nkeys,
+                               reinterpret_cast<void *const *>(streams), m.rcs.data()),
+            "Dcf::EvalBatchMulti");
+  }
+  void SyncMulti(int ndev, const int *devices, const cudaStream_t *streams = nullptr) const {
+    b200::MultiCall m(Params(), ndev, devices);
+    m.Check(fssb200_multi_sync(m.ctxs.data(), ndev, reinterpret_cast<void *const *>(streams), m.rcs.data()),
+            "Dcf::SyncMulti");
+  }
 };
 
 }  // namespace fss

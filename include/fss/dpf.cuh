@@ -63,6 +63,41 @@ public:
   void EvalBatchHost(bool b, const int4 *seeds, const Cw *cws, const In *xs, int4 *ys, size_t nkeys) const {
     b200::Check(fssb200_eval_host(Context(), b, seeds, cws, nullptr, xs, ys, nkeys), "Dpf::EvalBatchHost");
   }
+  // ---- one process, ndev GPUs: per-device arrays, one stream per device, no collective ----
+  // devices == nullptr: ordinals 0..ndev-1.  Stream ordered; SyncMulti waits and surfaces each device's error.
+  void EvalBatchMulti(bool b, int ndev, const int *devices, const int4 *const *seeds, const Cw *const *cws,
+                      const In *const *xs, int4 *const *ys, const size_t *nkeys,
+                      const cudaStream_t *streams = nullptr) const {
+    b200::MultiCall m(b200::MakeParams<in_bits, Group, Prg, In>(FSSB200_SCHEME_DPF, prg), ndev, devices);
+    m.Check(fssb200_eval_multi(m.ctxs.data(), ndev, b, reinterpret_cast<const void *const *>(seeds),
+                               reinterpret_cast<const void *const *>(cws), nullptr,
+                               reinterpret_cast<const void *const *>(xs), reinterpret_cast<void *const *>(ys), nkeys,
+                               reinterpret_cast<void *const *>(streams), m.rcs.data()),
+            "Dpf::EvalBatchMulti");
+  }
+  // leaves [leaf_begin[d], +leaf_count[d]) of device d's keys (subtrees sharded: fssb200_leaf_shard)
+  void EvalAllBatchMulti(bool b, int ndev, const int *devices, const int4 *const *seeds, const Cw *const *cws,
+                         int4 *const *ys, const size_t *nkeys, const uint64_t *leaf_begin, const uint64_t *leaf_count,
+                         const cudaStream_t *streams = nullptr) const {
+    b200::MultiCall m(b200::MakeParams<in_bits, Group, Prg, In>(FSSB200_SCHEME_DPF, prg), ndev, devices);
+    m.Check(fssb200_eval_all_multi(m.ctxs.data(), ndev, b, reinterpret_cast<const void *const *>(seeds),
+                                   reinterpret_cast<const void *const *>(cws), nullptr,
+                                   reinterpret_cast<void *const *>(ys), nkeys, leaf_begin, leaf_count,
+                                   reinterpret_cast<void *const *>(streams), m.rcs.data()),
+            "Dpf::EvalAllBatchMulti");
+  }
+  void SyncMulti(int ndev, const int *devices, const cudaStream_t *streams = nullptr) const {
+    b200::MultiCall m(b200::MakeParams<in_bits, Group, Prg, In>(FSSB200_SCHEME_DPF, prg), ndev, devices);
+    m.Check(fssb200_multi_sync(m.ctxs.data(), ndev, reinterpret_cast<void *const *>(streams), m.rcs.data()),
+            "Dpf::SyncMulti");
+  }
+  // host arrays of the whole batch over ndev GPUs (key ranges of fssb200_key_shard)
+  void EvalBatchHostMulti(bool b, int ndev, const int *devices, const int4 *seeds, const Cw *cws, const In *xs,
+                          int4 *ys, size_t nkeys) const {
+    b200::MultiCall m(b200::MakeParams<in_bits, Group, Prg, In>(FSSB200_SCHEME_DPF, prg), ndev, devices);
+    m.Check(fssb200_eval_host_multi(m.ctxs.data(), ndev, b, seeds, cws, nullptr, xs, ys, nkeys, m.rcs.data()),
+            "Dpf::EvalBatchHostMulti");
+  }
 };
 
 }  // namespace fss

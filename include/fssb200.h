@@ -345,6 +345,44 @@ int fssb200_eval_levelmajor_host(fssb200_ctx *ctx, int party, const void *seeds,
                                  const void *cw_v, const void *extra, const void *out_cw,
                                  const void *ocws, const void *xs, void *ys, size_t nkeys);
 
+/* ---- multi-device entry points (one process, ndev GPUs) ----------
+ * The path shards with no exchange step: keys are independent (dpf.cuh:170-214) and an EvalAll
+ * subtree depends only on its root (dpf.cuh:291-301).  A multi-device call is ndev independent,
+ * stream-ordered launches; nothing moves between devices, there is no collective (the reference
+ * has no multi-GPU code at all).  ctxs[d] is a context created for device d' = its params.device
+ * with the SAME parameter set and key material; every array argument is an array of ndev
+ * per-device pointers (device memory of ctxs[d]'s device); streams[d] is a stream of that device
+ * (streams == NULL: default streams).  Returns the first non-zero per-device code; rcs (may be
+ * NULL) receives all ndev codes.  The calls do not synchronise: fssb200_multi_sync() waits for
+ * every device's stream and surfaces each device's cudaError_t.
+ *   fssb200_eval_multi      device d: ys[d][k] = Eval(party, seeds[d][k], cws[d][k], xs[d][k]), k < nkeys[d]
+ *   fssb200_eval_all_multi  device d: leaves [leaf_begin[d], +leaf_count[d]) of its nkeys[d] keys
+ *                           (BASELINE configs[3] "subtrees sharded": same keys on every device,
+ *                           ranges from fssb200_leaf_shard; or a key range per device)
+ *   fssb200_gen_multi       device d: Gen of its nkeys[d] keys
+ * fssb200_key_shard / fssb200_leaf_shard: the contiguous split (sizes differ by at most one key /
+ * work unit) the multi-device calls, bench.py and fss_b200/sharding.py use. */
+int fssb200_eval_multi(const fssb200_ctx *const *ctxs, int ndev, int party, const void *const *seeds,
+                       const void *const *cws, const void *const *ocws, const void *const *xs,
+                       void *const *ys, const size_t *nkeys, void *const *streams, int *rcs);
+int fssb200_eval_all_multi(const fssb200_ctx *const *ctxs, int ndev, int party,
+                           const void *const *seeds, const void *const *cws, const void *const *ocws,
+                           void *const *ys, const size_t *nkeys, const uint64_t *leaf_begin,
+                           const uint64_t *leaf_count, void *const *streams, int *rcs);
+int fssb200_gen_multi(const fssb200_ctx *const *ctxs, int ndev, const void *const *s0s,
+                      const void *const *alphas, const void *const *betas, void *const *cws,
+                      void *const *ocws, const size_t *nkeys, void *const *streams, int *rcs);
+int fssb200_multi_sync(const fssb200_ctx *const *ctxs, int ndev, void *const *streams, int *rcs);
+int fssb200_key_shard(size_t nkeys, int d, int n, size_t *begin, size_t *end);
+int fssb200_leaf_shard(const fssb200_ctx *ctx, int d, int n, uint64_t *begin, uint64_t *count);
+/* Host arrays of the WHOLE batch, evaluated on ndev GPUs: device d takes key range
+ * fssb200_key_shard(nkeys, d, ndev) of the caller's arrays; one host thread per device runs the
+ * fssb200_eval_host pipeline on its range with its share of the worker threads.  Returns when ys
+ * is complete. */
+int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const void *seeds,
+                            const void *cws, const void *ocws, const void *xs, void *ys, size_t nkeys,
+                            int *rcs);
+
 /* ---- packed rows: compact key format for DPF / Half-Tree keys ---------------------------
  * Dpf::Cw (dpf.cuh:76-81) and HalfTreeDpf::Cw (half_tree_dpf.cuh:53-57) are {int4 s; bool flag}
  * padded to 32 bytes: 15 of every 32 bytes carry nothing.  A packed row holds the ncw 16-byte

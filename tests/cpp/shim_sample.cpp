@@ -197,6 +197,40 @@ static void BatchedChaCha() {
   std::vector<Dpf::Cw> h_cws(33);
   cudaMemcpy(h_cws.data(), d_cws + 33 * 7, sizeof(Dpf::Cw) * 33, cudaMemcpyDeviceToHost);
   EXPECT(Eq(dpf.Eval(false, seeds0[7], h_cws.data(), xs[7]), y0[7]), "Dpf::Eval == EvalBatch");
+  // multi-device members: two shards of the key batch, here both on the current device so that
+  // the sample runs on a one-GPU box -- per-device pointer arrays, one stream per shard, no collective
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int devices[2] = {dev, dev};
+    size_t b0, e0, b1, e1;
+    fssb200_key_shard(size_t(n), 0, 2, &b0, &e0);
+    fssb200_key_shard(size_t(n), 1, 2, &b1, &e1);
+    EXPECT(b0 == 0 && e0 == b1 && e1 == size_t(n), "key_shard covers the batch");
+    cudaStream_t st[2];
+    cudaStreamCreate(&st[0]);
+    cudaStreamCreate(&st[1]);
+    int4 *d_ym;
+    cudaMalloc(&d_ym, 16 * n);
+    const int4 *sd[2] = {d_seeds0 + b0, d_seeds0 + b1};
+    const Dpf::Cw *cw[2] = {d_cws + 33 * b0, d_cws + 33 * b1};
+    const uint32_t *xx[2] = {d_xs + b0, d_xs + b1};
+    int4 *yy[2] = {d_ym + b0, d_ym + b1};
+    const size_t nk[2] = {e0 - b0, e1 - b1};
+    dpf.EvalBatchMulti(false, 2, devices, sd, cw, xx, yy, nk, st);
+    dpf.SyncMulti(2, devices, st);
+    std::vector<int4> ym(n), yh(n);
+    cudaMemcpy(ym.data(), d_ym, 16 * n, cudaMemcpyDeviceToHost);
+    EXPECT(std::memcmp(ym.data(), y0.data(), 16 * size_t(n)) == 0, "EvalBatchMulti (2 shards) == EvalBatch");
+    // host arrays of the whole batch over the same two shards
+    std::vector<Dpf::Cw> all_cws(33 * size_t(n));
+    cudaMemcpy(all_cws.data(), d_cws, sizeof(Dpf::Cw) * all_cws.size(), cudaMemcpyDeviceToHost);
+    dpf.EvalBatchHostMulti(false, 2, devices, seeds0.data(), all_cws.data(), xs.data(), yh.data(), size_t(n));
+    EXPECT(std::memcmp(yh.data(), y0.data(), 16 * size_t(n)) == 0, "EvalBatchHostMulti (2 shards) == EvalBatch");
+    cudaStreamDestroy(st[0]);
+    cudaStreamDestroy(st[1]);
+    cudaFree(d_ym);
+  }
   // full-domain on the device for a small domain
   using Dpf12 = fss::Dpf<12, Group, Prg, uint32_t>;
   Dpf12 d12{prg};

@@ -1,0 +1,46 @@
+#!/bin/bash
+# One parameterised GPU session (replaces the per-session scripts of round 1).  Run under gpurun from the repo root:
+#   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh tests bench sweep'
+# Steps (any subset, in the order given):
+#   newtests  the round-2 test files only (fast feedback)        -> gpurun_out/pytest_new.log
+#   tests     the whole -m gpu suite                             -> gpurun_out/pytest_gpu.log
+#   bench     bench.py own arm, N = 1 ($BENCH_ARGS)               -> gpurun_out/bench.json
+#   refarm    bench.py --impl reference                          -> gpurun_out/bench_ref.json
+#   sweep     tools/e2e_sweep.py ($SWEEP_ARGS)                    -> gpurun_out/e2e_sweep.jsonl
+#   launches  ncu launch list of the bench command               -> gpurun_out/launches.csv
+#   ncu       ncu --set full of the kernels in $NCU_KERNELS      -> gpurun_out/prof_<name>.ncu-rep
+#   host      lscpu / numactl / nvidia-smi topo of the box       -> gpurun_out/host.txt
+set -u
+mkdir -p gpurun_out
+for step in "$@"; do
+  case "$step" in
+    host)
+      { lscpu; echo; numactl -H 2>/dev/null || cat /sys/devices/system/node/node*/cpulist; echo; nvidia-smi topo -m; echo; free -g; nproc; } > gpurun_out/host.txt 2>&1 ;;
+    newtests)
+      ( timeout 1200 python -m pytest tests/test_host_pipeline.py tests/test_multi.py -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_new.log
+      tail -5 gpurun_out/pytest_new.log ;;
+    tests)
+      ( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_gpu.log
+      tail -5 gpurun_out/pytest_gpu.log ;;
+    bench)
+      timeout 900 python bench.py ${BENCH_ARGS:---steps 20 --warmup 5} > gpurun_out/bench.json 2> gpurun_out/bench.err
+      echo "bench rc=$?"; tail -c 600 gpurun_out/bench.err ;;
+    refarm)
+      timeout 900 python bench.py --impl reference ${REF_ARGS:---steps 5 --warmup 3} > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+      echo "refarm rc=$?" ;;
+    sweep)
+      timeout 900 python tools/e2e_sweep.py ${SWEEP_ARGS:-} > gpurun_out/e2e_sweep.log 2>&1
+      echo "sweep rc=$?"; tail -40 gpurun_out/e2e_sweep.log ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu --no-check > gpurun_out/launches_bench.log 2>&1
+      echo "launches rc=$?" ;;
+    ncu)
+      for k in ${NCU_KERNELS:-c2}; do
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:${NCU_REGEX:-.} -s ${NCU_SKIP:-2} -c 1 \
+          -f -o gpurun_out/prof_$k python tools/prof_one.py $k > gpurun_out/prof_$k.log 2>&1
+        echo "ncu $k rc=$?"
+      done ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
