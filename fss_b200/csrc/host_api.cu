@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -128,6 +129,31 @@ int host_thread_budget() {
   return t < 0 ? 0 : t;
 }
 
+// Last-level cache of the host divided by the ranks that share it (0 if unknown).
+size_t llc_bytes_per_rank() {
+  static const size_t v = [] {
+    size_t best = 0;
+#if defined(__linux__)
+    for (int idx = 2; idx <= 4; ++idx) {
+      char path[96];
+      std::snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu0/cache/index%d/size", idx);
+      if (FILE *f = std::fopen(path, "r")) {
+        unsigned long n = 0;
+        char unit = 0;
+        if (std::fscanf(f, "%lu%c", &n, &unit) >= 1) {
+          size_t b = size_t(n) * (unit == 'K' ? 1024u : (unit == 'M' ? 1048576u : 1u));
+          if (b > best) best = b;
+        }
+        std::fclose(f);
+      }
+    }
+#endif
+    int lws = env_int("LOCAL_WORLD_SIZE", 1);
+    return best / size_t(lws < 1 ? 1 : lws);
+  }();
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // worker threads: one process-wide crew, lent to one call at a time
 // ---------------------------------------------------------------------------------------------------------------
@@ -206,6 +232,8 @@ class Crew {
 
 // Workers one call may borrow: all of them, or this thread's share when a multi-device call set one
 thread_local int t_crew_share = 0;  // 0 = no limit
+// ... and the devices this process drives at once (they share the last-level cache)
+thread_local int t_devices_sharing_host = 1;
 
 // ---------------------------------------------------------------------------------------------------------------
 // arena pool
@@ -495,10 +523,18 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
   P.rowb = fssb200_packed_row_bytes(c);
   P.ib = size_t(c->p.in_bytes);
   P.pack = P.rowb != 0;
-  P.nt_stores = env_int("FSSB200_PACK_NT", 1) != 0;
-  P.ck = chunk_pref(c, nkeys, size_t(1) << env_int("FSSB200_PIPE_CHUNK_BITS", 16));
+  // Staging ring, two regimes (measured on the 16-core / 60 MiB-L3 host of a 1-GPU box, profiles/r02_host_pipeline.md):
+  //  * cache-resident: 4 slots of 2^14 keys (36 MB) written with ordinary stores -- the ring lives in the last-level
+  //    cache, the copy engine's reads are served from it, and the only DRAM traffic of a packed chunk is the read of
+  //    the caller's rows: 46.4 ms per 2^22 keys;
+  //  * streaming: 6 slots of 2^16 keys written with non-temporal stores when this rank's share of the cache cannot
+  //    hold a ring (several ranks per host): 51.4 ms.  (Ordinary stores into a ring that does NOT fit pay a
+  //    read-for-ownership per line: 56.9 ms.)
+  const bool cached_ring = llc_bytes_per_rank() / size_t(t_devices_sharing_host) >= (size_t(48) << 20);
+  P.nt_stores = env_int("FSSB200_PACK_NT", cached_ring ? 0 : 1) != 0;
+  P.ck = chunk_pref(c, nkeys, size_t(1) << env_int("FSSB200_PIPE_CHUNK_BITS", cached_ring ? 14 : 16));
   P.nchunks = (nkeys + P.ck - 1) / P.ck;
-  P.nslots = size_t(std::max(2, std::min(16, env_int("FSSB200_PIPE_SLOTS", 6))));
+  P.nslots = size_t(std::max(2, std::min(16, env_int("FSSB200_PIPE_SLOTS", cached_ring ? 4 : 6))));
   if (P.nslots > P.nchunks) P.nslots = P.nchunks;
   P.slot_bytes = align_up(P.staged_bytes(P.ck), 4096);
   const int nsets = int(std::min<size_t>(kMaxSets, std::max<size_t>(2, std::min<size_t>(P.nchunks, 4))));
@@ -789,7 +825,7 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
     const bool packable = fssb200_packed_row_bytes(c) != 0;
     // pinned inputs of a scheme without padding: nothing to gain from staging, the link takes the rows as they are
     const int mode = c->host_mode.load(std::memory_order_relaxed);
-    if ((packable && mode != 1) || !in_pinned)
+    if (mode != 1 && (packable || !in_pinned))
       return eval_host_pipelined(c, party, seeds, cws, ocws, xs, ys, nkeys, crew, in_pinned && mode != 2,
           is_pinned_or_device(ys));
   }
@@ -1057,10 +1093,12 @@ int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const
   auto run = [&](int d) {
     const size_t k0 = size_t(d) * base + std::min<size_t>(size_t(d), rem), k = base + (size_t(d) < rem ? 1 : 0);
     t_crew_share = share;
+    t_devices_sharing_host = ndev;
     rc[size_t(d)] = fssb200_eval_host(ctxs[d], party, static_cast<const uint8_t *>(seeds) + k0 * 16,
         static_cast<const uint8_t *>(cws) + k0 * cwb, ocws ? static_cast<const uint8_t *>(ocws) + k0 * 16 : nullptr,
         static_cast<const uint8_t *>(xs) + k0 * ib, static_cast<uint8_t *>(ys) + k0 * 16, k);
     t_crew_share = 0;
+    t_devices_sharing_host = 1;
   };
   for (int d = 1; d < ndev; ++d) th.emplace_back(run, d);
   run(0);

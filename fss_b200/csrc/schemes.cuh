@@ -649,6 +649,8 @@ FSS_HD uint32_t grotto_walk_body(const PrgKeys &K, const typename Prg<PRG>::ctx_
     cs = cs_next;
     cf = cf_next;
   }
+  cw.begin_level(n);  // (entry n, the output CW, is not used: Grotto has beta = 0 -- but a staged accessor must be
+  cw.done_level(n);   //  walked to the end of the row so that its prefetch pipeline stays in step with the next tile)
   {  // last level: only the left child's control bit can still count (the leaf e itself is outside [0, e))
     const uint32_t tm = 0u - lsb(st);
     const blk l = xor_masked(Prg<PRG>::gen_left(K, pc, clamp(st)), tm, cs);

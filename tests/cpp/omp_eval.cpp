@@ -72,7 +72,7 @@ static void Run(Scheme &sch, const char *name, bool lt_pred) {
     if (!Eq(y0[i], z0[i]) || !Eq(y1[i], z1[i])) ++bad;
     const int4 sum = (Group::From(y0[i]) + Group::From(y1[i])).Into();
     const bool hit = lt_pred ? (x[i] < alpha[i]) : (x[i] == alpha[i]);
-    const int4 want = hit ? beta[i] : int4{0, 0, 0, 0};
+    const int4 want = hit ? Group::From(beta[i]).Into() : int4{0, 0, 0, 0};  // (Uint<u64>: words 2, 3 of beta do not count)
     if (!Eq(sum, want)) ++bad_rec;
   }
   std::printf("%s: %d keys, %d OpenMP threads, %d mismatches vs single-threaded, %d reconstruction failures\n", name, kKeys,

@@ -67,12 +67,10 @@ def main():
         child(args)
         return
     base = [{"mode": 0}, {"mode": 1}, {"mode": 2}]
-    tune = [{"mode": 0, "env": {"FSSB200_PIPE_CHUNK_BITS": b}} for b in (14, 15, 17, 18)] + \
-           [{"mode": 0, "env": {"FSSB200_PIPE_SLOTS": s}} for s in (3, 12)] + \
-           [{"mode": 0, "env": {"FSSB200_PACK_NT": 0}}, {"mode": 2, "env": {"FSSB200_PACK_NT": 0}},
-            {"mode": 0, "env": {"FSSB200_PACK_NT": 0, "FSSB200_PIPE_CHUNK_BITS": 14, "FSSB200_PIPE_SLOTS": 4}},
-            {"mode": 2, "env": {"FSSB200_PACK_NT": 0, "FSSB200_PIPE_CHUNK_BITS": 14, "FSSB200_PIPE_SLOTS": 4}},
-            {"mode": 0, "env": {"FSSB200_PACK_NT": 0, "FSSB200_PIPE_CHUNK_BITS": 13, "FSSB200_PIPE_SLOTS": 6}}]
+    nt0 = lambda b, s, m=0: {"mode": m, "env": {"FSSB200_PACK_NT": 0, "FSSB200_PIPE_CHUNK_BITS": b, "FSSB200_PIPE_SLOTS": s}}  # noqa: E731
+    nt1 = lambda b, s, m=0: {"mode": m, "env": {"FSSB200_PACK_NT": 1, "FSSB200_PIPE_CHUNK_BITS": b, "FSSB200_PIPE_SLOTS": s}}  # noqa: E731
+    tune = [nt0(14, 3), nt0(14, 5), nt0(14, 6), nt0(14, 8), nt0(15, 2), nt0(15, 3), nt0(15, 4), nt0(13, 8), nt0(13, 12),
+            nt1(16, 6), nt1(15, 6), nt1(14, 4)]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         for i, t in enumerate(args.threads.split(",")):
