@@ -250,6 +250,8 @@ struct Arena {
   cudaStream_t stream[kArenaStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t h2d_ev[kMaxSets] = {};
   cudaEvent_t set_ev[kMaxSets] = {};
+  cudaEvent_t slot_ev[32] = {};  // one per staging-ring slot (kMaxSlots)
+  cudaEvent_t dir_ev[32] = {};   // link events of the direct pieces in flight (at most 24 at a time)
 };
 
 size_t round_arena(size_t b) {
@@ -295,6 +297,10 @@ class ArenaPool {
       for (int i = 0; i < kMaxSets && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&a->h2d_ev[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->set_ev[i], cudaEventDisableTiming);
+      }
+      for (int i = 0; i < 32 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&a->slot_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->dir_ev[i], cudaEventDisableTiming);
       }
       if (e != cudaSuccess) { destroy(a); *rc = int(e); return nullptr; }
     }
@@ -370,6 +376,10 @@ class ArenaPool {
       if (a->h2d_ev[i]) cudaEventDestroy(a->h2d_ev[i]);
       if (a->set_ev[i]) cudaEventDestroy(a->set_ev[i]);
     }
+    for (int i = 0; i < 32; ++i) {
+      if (a->slot_ev[i]) cudaEventDestroy(a->slot_ev[i]);
+      if (a->dir_ev[i]) cudaEventDestroy(a->dir_ev[i]);
+    }
     delete a;
   }
   std::mutex mu_;
@@ -433,68 +443,77 @@ bool is_pinned_or_device(const void *p) {
 // ---------------------------------------------------------------------------------------------------------------
 // the adaptive pipeline of fssb200_eval_host
 // ---------------------------------------------------------------------------------------------------------------
-constexpr size_t kPackBlock = 512;  // keys a worker claims at a time
+// Two granularities (measured, profiles/r02_host_pipeline.md):
+//   CHUNK  = the keys of one kernel launch + one D2H (default 2^16): large enough that the launch is not latency-bound;
+//   PIECE  = the keys of one staging-ring slot + one H2D copy (default 2^12, 2.2 MB packed): small enough that a ring
+//            of a few slots stays in the last-level cache between the workers' stores and the copy engine's reads, so
+//            the only DRAM traffic of a packed key is the 1056-byte read of the caller's row (the host's DRAM
+//            bandwidth, ~185 GB/s on the boxes measured, is what bounds the call once more than one GPU shares it).
+// Chunks [0, tail) are staged piece by piece from the front of the batch; chunks [tail, nchunks) were sent in the
+// reference layout, taken one at a time from the back whenever the link was about to run dry.
+constexpr size_t kPackBlock = 256;  // keys a worker claims at a time
+constexpr int kMaxSlots = 32;
 
 struct EvalPipe : CrewJob {
   // the call
   fssb200_ctx *c;
-  int party;
-  const uint8_t *seeds, *cws, *ocws, *xs;
-  uint8_t *ys;
+  const uint8_t *cws;
   size_t nkeys;
   // geometry
-  size_t ck, nchunks, cwb, rowb, ib;
+  size_t ck, nchunks, pk, ppc;  // keys per chunk, chunks, keys per piece, pieces per chunk
+  size_t cwb, rowb;
   bool pack;        // staged rows are packed rows (else: a plain copy of the reference layout)
   bool nt_stores;
-  uint8_t *stage;   // ring of pinned slots
+  uint8_t *stage;   // ring of pinned slots, one piece each
   size_t slot_bytes, nslots;
   // shared state
-  struct ChunkState {
-    std::atomic<uint32_t> next{0};  // next 512-key block to claim
+  struct PieceState {
+    std::atomic<uint32_t> next{0};  // next block to claim
     std::atomic<uint32_t> done{0};  // keys staged so far
   };
-  std::unique_ptr<ChunkState[]> st;
-  std::atomic<size_t> cur{0};        // chunk the workers are staging
-  std::atomic<size_t> tail{0};       // chunks [tail, nchunks) were sent in the reference layout
-  std::atomic<size_t> free_upto{0};  // staging may write chunk c iff c < free_upto
+  std::unique_ptr<PieceState[]> st;  // indexed by global piece number q = chunk * ppc + piece
+  std::atomic<size_t> cur{0};        // piece the workers are staging
+  std::atomic<size_t> tail{0};       // chunks [tail, nchunks) go in the reference layout
+  std::atomic<size_t> free_upto{0};  // staging may write staged-piece ordinal o iff o < free_upto
   std::atomic<bool> stop{false};
   std::mutex claim_mu;
 
-  size_t keys_of(size_t ch) const { return ch + 1 < nchunks ? ck : nkeys - ch * ck; }
-  // staged chunk layout in a slot (and, identically, in its device set): rows | seeds | xs | ocws
+  size_t keys_of_chunk(size_t ch) const { return ch + 1 < nchunks ? ck : nkeys - ch * ck; }
+  size_t pieces_of_chunk(size_t ch) const { return (keys_of_chunk(ch) + pk - 1) / pk; }
+  size_t keys_of_piece(size_t q) const {
+    const size_t ch = q / ppc, pi = q % ppc, kc = keys_of_chunk(ch);
+    return pi * pk >= kc ? 0 : std::min(pk, kc - pi * pk);
+  }
   size_t staged_row_bytes() const { return pack ? rowb : cwb; }
-  size_t off_seeds(size_t k) const { return align_up(k * staged_row_bytes(), 256); }
-  size_t off_xs(size_t k) const { return off_seeds(k) + align_up(k * 16, 256); }
-  size_t off_ocws(size_t k) const { return off_xs(k) + align_up(k * ib, 256); }
-  size_t staged_bytes(size_t k) const { return off_ocws(k) + (ocws ? align_up(k * 16, 256) : 0); }
+  // Ordinal of piece q among the NON-EMPTY staged pieces (only the batch's last chunk can have empty pieces, and they
+  // trail): ring slot = ordinal % nslots.  All chunks before q's are full, so the ordinal is q itself.
+  uint8_t *slot_of(size_t q) const { return stage + (q % nslots) * slot_bytes; }
 
   // Stages one block if there is one.  Returns false when there is nothing to do right now.
   bool stage_step() {
-    const size_t ch = cur.load(std::memory_order_acquire);
-    if (ch >= tail.load(std::memory_order_acquire)) return false;
-    if (ch >= free_upto.load(std::memory_order_acquire)) return false;
-    const size_t k = keys_of(ch);
+    const size_t q = cur.load(std::memory_order_acquire);
+    if (q / ppc >= tail.load(std::memory_order_acquire)) return false;
+    const size_t k = keys_of_piece(q);
+    if (k && q >= free_upto.load(std::memory_order_acquire)) return false;
     const uint32_t nblocks = uint32_t((k + kPackBlock - 1) / kPackBlock);
-    const uint32_t b = st[ch].next.fetch_add(1, std::memory_order_relaxed);
+    const uint32_t b = st[q].next.fetch_add(1, std::memory_order_relaxed);
     if (b >= nblocks) {
       std::lock_guard<std::mutex> l(claim_mu);
-      if (cur.load(std::memory_order_relaxed) == ch) cur.store(ch + 1, std::memory_order_release);
+      if (cur.load(std::memory_order_relaxed) == q) cur.store(q + 1, std::memory_order_release);
       return true;
     }
-    const size_t k0 = size_t(b) * kPackBlock, k1 = std::min(k, k0 + kPackBlock), g0 = ch * ck;
-    uint8_t *slot = stage + (ch % nslots) * slot_bytes;
+    const size_t k0 = size_t(b) * kPackBlock, k1 = std::min(k, k0 + kPackBlock);
+    const size_t g0 = (q / ppc) * ck + (q % ppc) * pk;  // first key of the piece
+    uint8_t *slot = slot_of(q);
     if (pack) pack_rows_range(cws + g0 * cwb, slot, k0, k1, c->ncw, nt_stores);
     else stage_copy(cws + (g0 + k0) * cwb, slot + k0 * cwb, (k1 - k0) * cwb, nt_stores);
-    stage_copy(seeds + (g0 + k0) * 16, slot + off_seeds(k) + k0 * 16, (k1 - k0) * 16, nt_stores);
-    stage_copy(xs + (g0 + k0) * ib, slot + off_xs(k) + k0 * ib, (k1 - k0) * ib, false);
-    if (ocws) stage_copy(ocws + (g0 + k0) * 16, slot + off_ocws(k) + k0 * 16, (k1 - k0) * 16, nt_stores);
-    st[ch].done.fetch_add(uint32_t(k1 - k0), std::memory_order_release);
+    st[q].done.fetch_add(uint32_t(k1 - k0), std::memory_order_release);
     return true;
   }
   void run() override {
     int idle = 0;
     while (!stop.load(std::memory_order_acquire)) {
-      if (cur.load(std::memory_order_acquire) >= tail.load(std::memory_order_acquire)) break;
+      if (cur.load(std::memory_order_acquire) / ppc >= tail.load(std::memory_order_acquire)) break;
       if (stage_step()) {
         idle = 0;
       } else if (++idle < 64) {
@@ -506,50 +525,51 @@ struct EvalPipe : CrewJob {
   }
 };
 
-// Large batches with worker threads available.  `allow_direct`: the caller's buffers are pinned, so chunks may also
+// Large batches with worker threads available.  `allow_direct`: the caller's rows are pinned, so chunks may also
 // cross the link straight from them.
-int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws,
-    const void *xs, void *ys, size_t nkeys, Crew *crew, bool allow_direct, bool ys_pinned) {
+int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const void *cws, const void *ocws_v,
+    const void *xs_v, void *ys_v, size_t nkeys, Crew *crew, bool allow_direct, bool ys_pinned) {
+  const uint8_t *seeds = static_cast<const uint8_t *>(seeds_v), *ocws = static_cast<const uint8_t *>(ocws_v),
+                *xs = static_cast<const uint8_t *>(xs_v);
+  uint8_t *ys = static_cast<uint8_t *>(ys_v);
   EvalPipe P;
   P.c = c;
-  P.party = party;
-  P.seeds = static_cast<const uint8_t *>(seeds);
   P.cws = static_cast<const uint8_t *>(cws);
-  P.ocws = static_cast<const uint8_t *>(ocws);
-  P.xs = static_cast<const uint8_t *>(xs);
-  P.ys = static_cast<uint8_t *>(ys);
   P.nkeys = nkeys;
   P.cwb = size_t(c->ncw) * 32;
   P.rowb = fssb200_packed_row_bytes(c);
-  P.ib = size_t(c->p.in_bytes);
+  const size_t ib = size_t(c->p.in_bytes);
   P.pack = P.rowb != 0;
-  // Staging ring, two regimes (measured on the 16-core / 60 MiB-L3 host of a 1-GPU box, profiles/r02_host_pipeline.md):
-  //  * cache-resident: 4 slots of 2^14 keys (36 MB) written with ordinary stores -- the ring lives in the last-level
-  //    cache, the copy engine's reads are served from it, and the only DRAM traffic of a packed chunk is the read of
-  //    the caller's rows: 46.4 ms per 2^22 keys;
-  //  * streaming: 6 slots of 2^16 keys written with non-temporal stores when this rank's share of the cache cannot
-  //    hold a ring (several ranks per host): 51.4 ms.  (Ordinary stores into a ring that does NOT fit pay a
-  //    read-for-ownership per line: 56.9 ms.)
-  const bool cached_ring = llc_bytes_per_rank() / size_t(t_devices_sharing_host) >= (size_t(48) << 20);
+  // ring: cache-resident (ordinary stores) when this rank's share of the last-level cache can hold it together with
+  // the rows streaming through; else non-temporal stores into a ring that lives in DRAM
+  const size_t llc = llc_bytes_per_rank() / size_t(t_devices_sharing_host);
+  const bool cached_ring = llc >= (size_t(6) << 20);
   P.nt_stores = env_int("FSSB200_PACK_NT", cached_ring ? 0 : 1) != 0;
-  P.ck = chunk_pref(c, nkeys, size_t(1) << env_int("FSSB200_PIPE_CHUNK_BITS", cached_ring ? 14 : 16));
+  P.ck = chunk_pref(c, nkeys, size_t(1) << env_int("FSSB200_PIPE_CHUNK_BITS", 16));
   P.nchunks = (nkeys + P.ck - 1) / P.ck;
-  P.nslots = size_t(std::max(2, std::min(16, env_int("FSSB200_PIPE_SLOTS", cached_ring ? 4 : 6))));
-  if (P.nslots > P.nchunks) P.nslots = P.nchunks;
-  P.slot_bytes = align_up(P.staged_bytes(P.ck), 4096);
+  // piece: 2^14 keys (8.9 MB packed) when the ring of 4 has the cache to itself, 2^13 when ranks share it; smaller
+  // pieces lose more to their hand-offs than they gain in residency (2 ranks: 2^13 -> 66-69 ms, 2^12 -> 84-87 ms)
+  const int piece_bits = llc >= (size_t(48) << 20) ? 14 : 13;
+  P.pk = std::min(P.ck, size_t(1) << env_int("FSSB200_PIPE_PIECE_BITS", piece_bits));
+  P.ppc = (P.ck + P.pk - 1) / P.pk;
+  P.slot_bytes = align_up(P.pk * P.staged_row_bytes(), 4096);
+  {
+    size_t want = cached_ring ? 4 : 6;
+    want = size_t(std::max(2, std::min(kMaxSlots, env_int("FSSB200_PIPE_SLOTS", int(want)))));
+    P.nslots = std::min(want, P.nchunks * P.ppc);
+  }
   const int nsets = int(std::min<size_t>(kMaxSets, std::max<size_t>(2, std::min<size_t>(P.nchunks, 4))));
-  // device set: a staged chunk or a reference-layout chunk (rows | seeds | xs | ocws), then ys
-  const size_t direct_bytes = align_up(P.ck * P.cwb, 256) + align_up(P.ck * 16, 256) + align_up(P.ck * P.ib, 256) +
-      (ocws ? align_up(P.ck * 16, 256) : 0);
-  const size_t set_in = std::max(direct_bytes, P.staged_bytes(P.ck));
-  const size_t set_bytes = align_up(set_in + P.ck * 16, 4096);
+  // device set: rows (reference layout: the larger of the two formats) | seeds | xs | ocws | ys
+  const size_t off_seeds = align_up(P.ck * P.cwb, 256), off_xs = off_seeds + align_up(P.ck * 16, 256),
+               off_ocws = off_xs + align_up(P.ck * ib, 256), off_ys = off_ocws + (ocws ? align_up(P.ck * 16, 256) : 0);
+  const size_t set_bytes = align_up(off_ys + P.ck * 16, 4096);
   const size_t ys_stage = ys_pinned ? 0 : align_up(P.ck * 16, 4096);  // pageable ys: results land in pinned memory first
   ArenaLease L(c->p.device, set_bytes * nsets, P.nslots * P.slot_bytes + ys_stage * nsets);
   if (!L.a) return L.rc;
   Arena &A = *L.a;
   P.stage = A.pin;
   uint8_t *ys_pin = A.pin + P.nslots * P.slot_bytes;
-  P.st.reset(new (std::nothrow) EvalPipe::ChunkState[P.nchunks]);
+  P.st.reset(new (std::nothrow) EvalPipe::PieceState[P.nchunks * P.ppc]);
   if (!P.st) return FSSB200_EINVAL;
   P.tail.store(P.nchunks);
   P.free_upto.store(P.nslots);
@@ -557,82 +577,104 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
   // (no idle worker and pageable inputs: the calling thread stages alone -- still correct, just slower)
   const int lent = crew ? crew->begin(&P, t_crew_share > 0 ? t_crew_share : crew->workers()) : 0;
 
-  struct Issue {
-    size_t chunk;
-    bool staged;
+  struct SetUse {
+    bool busy = false;      // holds a chunk
+    bool launched = false;  // ... whose kernel + D2H are queued (set_ev recorded)
+    size_t chunk = 0;
   };
-  std::deque<Issue> link_fifo;           // H2D copies not yet known to be complete, in issue order
-  Issue set_use[kMaxSets];
-  bool set_busy[kMaxSets] = {};
-  size_t issued = 0, retired = 0;        // issue i uses device set i % nsets
-  size_t next_staged = 0, staged_copied = 0;
+  SetUse sets[kMaxSets];
+  struct LinkOp {
+    cudaEvent_t ev;
+    size_t bytes;
+    bool piece;
+  };
+  std::deque<LinkOp> link;   // row copies not yet known to be complete, in issue order
+  size_t link_bytes = 0;     // ... and their bytes: how much work the link has queued
+  size_t pieces_copied = 0;  // staged pieces whose copy has completed (they complete in order)
+  size_t next_piece = 0;     // next staged piece to submit
+  int cur_set = -1;          // device set of the staged chunk in progress
+  size_t issue_seq = 0;      // chunks started so far (stream round-robin)
+  cudaStream_t cur_stream = nullptr;
   uint64_t direct_keys = 0;
   int rc = 0;
+  // the link should always have about two pieces queued; below that, rows from the back of the batch go as they are
+  const size_t low_water = env_int("FSSB200_PIPE_LOW_WATER_MB", 0) > 0 ? size_t(env_int("FSSB200_PIPE_LOW_WATER_MB", 0)) << 20
+                                                                         : P.pk * P.staged_row_bytes() * 7 / 4;
 
-  auto retire_set = [&](int s, bool wait) -> bool {  // results of the issue in set s are on the host
-    if (!set_busy[s]) return true;
-    if (wait) {
-      const cudaError_t e = cudaEventSynchronize(A.set_ev[s]);
-      if (e != cudaSuccess) { rc = int(e); return false; }
-    } else {
-      const cudaError_t e = cudaEventQuery(A.set_ev[s]);
-      if (e == cudaErrorNotReady) return false;
-      if (e != cudaSuccess) { rc = int(e); return false; }
-    }
-    if (ys_stage) {
-      const size_t ch = set_use[s].chunk;
-      std::memcpy(P.ys + ch * P.ck * 16, ys_pin + size_t(s) * ys_stage, P.keys_of(ch) * 16);
-    }
-    set_busy[s] = false;
-    ++retired;
+  auto retire_set = [&](int s, bool wait) -> bool {  // results of the chunk in set s are on the host
+    if (!sets[s].busy) return true;
+    if (!sets[s].launched) return false;  // the staged chunk still being filled
+    const cudaError_t e = wait ? cudaEventSynchronize(A.set_ev[s]) : cudaEventQuery(A.set_ev[s]);
+    if (e == cudaErrorNotReady) return false;
+    if (e != cudaSuccess) { rc = int(e); return false; }
+    if (ys_stage)
+      std::memcpy(ys + sets[s].chunk * P.ck * 16, ys_pin + size_t(s) * ys_stage, P.keys_of_chunk(sets[s].chunk) * 16);
+    sets[s].busy = sets[s].launched = false;
     return true;
   };
+  auto acquire_set = [&]() -> int {
+    for (int s = 0; s < nsets; ++s)
+      if (!sets[s].busy) return s;
+    for (int s = 0; s < nsets; ++s)
+      if (retire_set(s, false)) return s;
+    return -1;
+  };
   auto poll_link = [&]() {
-    while (!link_fifo.empty()) {
-      const int s = int((issued - link_fifo.size()) % size_t(nsets));
-      const cudaError_t e = cudaEventQuery(A.h2d_ev[s]);
+    while (!link.empty()) {
+      const cudaError_t e = cudaEventQuery(link.front().ev);
       if (e == cudaErrorNotReady) break;
       if (e != cudaSuccess) { rc = int(e); break; }
-      if (link_fifo.front().staged) {
-        ++staged_copied;
-        P.free_upto.store(staged_copied + P.nslots, std::memory_order_release);
-      }
-      link_fifo.pop_front();
+      link_bytes -= link.front().bytes;
+      if (link.front().piece) P.free_upto.store(++pieces_copied + P.nslots, std::memory_order_release);
+      link.pop_front();
     }
   };
-  auto issue = [&](size_t ch, bool staged) {
-    const int s = int(issued % size_t(nsets));
-    cudaStream_t str = A.stream[issued % kArenaStreams];
-    const size_t k = P.keys_of(ch), g0 = ch * P.ck;
-    uint8_t *d = A.dev + size_t(s) * set_bytes;
-    uint8_t *d_rows = d, *d_seeds, *d_xs, *d_ocws, *d_ys = d + set_in;
+  // small arrays of a chunk straight from the caller's memory (pageable: the driver stages them, they are 36 B per key)
+  auto copy_small = [&](uint8_t *d, size_t ch, cudaStream_t str) -> int {
+    const size_t k = P.keys_of_chunk(ch), g0 = ch * P.ck;
+    int rc2 = 0;
     do {
-      if (staged) {
-        d_seeds = d + P.off_seeds(k);
-        d_xs = d + P.off_xs(k);
-        d_ocws = d + P.off_ocws(k);
-        TRY_BREAK(H2D(d, P.stage + (ch % P.nslots) * P.slot_bytes, P.staged_bytes(k), str));
-      } else {
-        d_seeds = d + align_up(k * P.cwb, 256);
-        d_xs = d_seeds + align_up(k * 16, 256);
-        d_ocws = d_xs + align_up(k * P.ib, 256);
-        TRY_BREAK(H2D(d_rows, P.cws + g0 * P.cwb, k * P.cwb, str));
-        TRY_BREAK(H2D(d_seeds, P.seeds + g0 * 16, k * 16, str));
-        TRY_BREAK(H2D(d_xs, P.xs + g0 * P.ib, k * P.ib, str));
-        if (P.ocws) TRY_BREAK(H2D(d_ocws, P.ocws + g0 * 16, k * 16, str));
-        direct_keys += k;
+      const cudaError_t e1 = H2D(d + off_seeds, seeds + g0 * 16, k * 16, str);
+      if (e1 != cudaSuccess) { rc2 = int(e1); break; }
+      const cudaError_t e2 = H2D(d + off_xs, xs + g0 * ib, k * ib, str);
+      if (e2 != cudaSuccess) { rc2 = int(e2); break; }
+      if (ocws) {
+        const cudaError_t e3 = H2D(d + off_ocws, ocws + g0 * 16, k * 16, str);
+        if (e3 != cudaSuccess) { rc2 = int(e3); break; }
       }
-      TRY_BREAK(cudaEventRecord(A.h2d_ev[s], str));
-      rc = (staged && P.pack) ? fssb200_eval_packed(c, party, d_seeds, d_rows, P.ocws ? d_ocws : nullptr, d_xs, d_ys, k, str)
-                              : fssb200_eval(c, party, d_seeds, d_rows, P.ocws ? d_ocws : nullptr, d_xs, d_ys, k, str);
+    } while (0);
+    return rc2;
+  };
+  auto launch_chunk = [&](int s, size_t ch, bool packed_rows, cudaStream_t str) {
+    const size_t k = P.keys_of_chunk(ch);
+    uint8_t *d = A.dev + size_t(s) * set_bytes;
+    do {
+      rc = packed_rows ? fssb200_eval_packed(c, party, d + off_seeds, d, ocws ? d + off_ocws : nullptr, d + off_xs, d + off_ys, k, str)
+                       : fssb200_eval(c, party, d + off_seeds, d, ocws ? d + off_ocws : nullptr, d + off_xs, d + off_ys, k, str);
       if (rc) break;
-      TRY_BREAK(D2H(ys_stage ? ys_pin + size_t(s) * ys_stage : P.ys + g0 * 16, d_ys, k * 16, str));
+      TRY_BREAK(D2H(ys_stage ? ys_pin + size_t(s) * ys_stage : ys + ch * P.ck * 16, d + off_ys, k * 16, str));
       TRY_BREAK(cudaEventRecord(A.set_ev[s], str));
     } while (0);
-    set_busy[s] = true;
-    set_use[s] = Issue{ch, staged};
-    link_fifo.push_back(Issue{ch, staged});
-    ++issued;
+    sets[s].busy = sets[s].launched = true;
+    sets[s].chunk = ch;
+  };
+
+  // An OPEN chunk is being filled on the device piece by piece; its kernel is launched behind its last piece.
+  struct Open {
+    int set = -1;
+    size_t chunk = 0, next_pi = 0;
+    cudaStream_t str = nullptr;
+  };
+  Open so, dio;              // the staged chunk (front of the batch) and the direct chunk (back) in progress
+  int dir_ev_next = 0;       // direct pieces take their link events from a small ring
+  auto open_chunk = [&](Open &o, int s, size_t ch) {  // s: a free device set
+    o.set = s;
+    o.chunk = ch;
+    o.next_pi = 0;
+    o.str = A.stream[issue_seq++ % kArenaStreams];
+    sets[s].busy = true;  // (held from the first piece on; `launched` once its kernel is queued)
+    sets[s].chunk = ch;
+    rc = copy_small(A.dev + size_t(s) * set_bytes, ch, o.str);
   };
 
   int idle = 0;
@@ -640,31 +682,80 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
     poll_link();
     if (rc) break;
     const size_t tl = P.tail.load(std::memory_order_acquire);
-    if (next_staged >= tl) break;  // every chunk has been issued
+    const bool staged_left = next_piece / P.ppc < tl;
+    if (!staged_left && dio.set < 0) break;  // every chunk has been issued
     bool progressed = false;
-    const int s = int(issued % size_t(nsets));
-    const bool set_free = retire_set(s, false);
-    if (rc) break;
-    if (set_free) {
-      poll_link();  // (the set's previous H2D event is about to be re-recorded)
-      if (P.st[next_staged].done.load(std::memory_order_acquire) == uint32_t(P.keys_of(next_staged))) {
-        issue(next_staged++, true);
+    if (staged_left) {
+      const size_t ch = next_piece / P.ppc, pi = next_piece % P.ppc, kp = P.keys_of_piece(next_piece);
+      if (kp == 0) {  // trailing empty piece of the batch's last chunk
+        ++next_piece;
+        continue;
+      }
+      if (so.set < 0 && P.st[next_piece].done.load(std::memory_order_acquire) == uint32_t(kp)) {
+        const int s = acquire_set();  // a staged chunk starts: it needs a device set
+        if (rc) break;
+        if (s >= 0) open_chunk(so, s, ch);
+        if (rc) break;
+      }
+      if (so.set >= 0 && P.st[next_piece].done.load(std::memory_order_acquire) == uint32_t(kp)) {
+        // submit the piece: its rows go behind the chunk's earlier pieces in the set
+        const size_t bytes = kp * P.staged_row_bytes();
+        const int slot = int(next_piece % P.nslots);
+        do {
+          TRY_BREAK(H2D(A.dev + size_t(so.set) * set_bytes + pi * P.pk * P.staged_row_bytes(), P.slot_of(next_piece), bytes, so.str));
+          TRY_BREAK(cudaEventRecord(A.slot_ev[slot], so.str));
+        } while (0);
+        if (rc) break;
+        link.push_back(LinkOp{A.slot_ev[slot], bytes, true});
+        link_bytes += bytes;
+        ++next_piece;
+        if (pi + 1 == P.pieces_of_chunk(ch)) {  // the chunk is complete on the device side: evaluate it
+          launch_chunk(so.set, ch, P.pack, so.str);
+          so.set = -1;
+          next_piece = (ch + 1) * P.ppc;
+        }
         progressed = true;
-      } else if (allow_direct && link_fifo.size() < 2) {
-        // the link is about to run dry and no staged chunk is ready: send one from the back as it is
-        size_t take = ~size_t(0);
-        {
-          std::lock_guard<std::mutex> l(P.claim_mu);
-          const size_t t = P.tail.load(std::memory_order_relaxed);
-          if (t > 0 && t - 1 > P.cur.load(std::memory_order_relaxed)) {
-            take = t - 1;
-            P.tail.store(take, std::memory_order_release);
+      }
+    }
+    // The link is about to run dry and no staged piece is ready (or nothing is left to stage): rows from the back of
+    // the batch cross as they are, one piece at a time so that a staged piece never waits long behind them.
+    if (!progressed && allow_direct && (link_bytes < low_water || !staged_left) && link.size() < 24) {
+      if (dio.set < 0 && staged_left) {
+        const int s = acquire_set();  // (before the claim: a chunk taken from the back is never given back)
+        if (rc) break;
+        if (s >= 0) {
+          size_t take = ~size_t(0);
+          {
+            std::lock_guard<std::mutex> l(P.claim_mu);
+            const size_t t = P.tail.load(std::memory_order_relaxed);
+            if (t > 0 && t - 1 > P.cur.load(std::memory_order_relaxed) / P.ppc && t - 1 > next_piece / P.ppc) {
+              take = t - 1;
+              P.tail.store(take, std::memory_order_release);
+            }
           }
+          if (take != ~size_t(0)) open_chunk(dio, s, take);
+          if (rc) break;
         }
-        if (take != ~size_t(0)) {
-          issue(take, false);
-          progressed = true;
+      }
+      if (dio.set >= 0) {
+        const size_t kc = P.keys_of_chunk(dio.chunk), k0 = dio.next_pi * P.pk, kp = std::min(P.pk, kc - k0);
+        cudaEvent_t ev = A.dir_ev[dir_ev_next];
+        dir_ev_next = (dir_ev_next + 1) % 32;
+        do {
+          TRY_BREAK(H2D(A.dev + size_t(dio.set) * set_bytes + k0 * P.cwb, P.cws + (dio.chunk * P.ck + k0) * P.cwb, kp * P.cwb, dio.str));
+          TRY_BREAK(cudaEventRecord(ev, dio.str));
+        } while (0);
+        if (rc) break;
+        link.push_back(LinkOp{ev, kp * P.cwb, false});
+        link_bytes += kp * P.cwb;
+        direct_keys += kp;
+        if (k0 + kp == kc) {
+          launch_chunk(dio.set, dio.chunk, false, dio.str);
+          dio.set = -1;
+        } else {
+          ++dio.next_pi;
         }
+        progressed = true;
       }
     }
     if (progressed) {
@@ -682,10 +773,10 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds, const void
   P.stop.store(true, std::memory_order_release);
   if (lent) crew->end(&P);
   // drain: results of every issued chunk
-  for (size_t i = retired; i < issued; ++i) {
+  for (int s = 0; s < nsets; ++s) {
     const int first = rc;
     rc = 0;
-    retire_set(int(i % size_t(nsets)), true);
+    if (sets[s].busy && sets[s].launched) retire_set(s, true);
     if (first) rc = first;
   }
   rc = L.drain(rc);

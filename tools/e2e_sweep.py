@@ -33,7 +33,7 @@ def child(args):
     del cws, s0s
     rows = []
     for cfg in json.loads(args.configs):
-        for key in ("FSSB200_PIPE_CHUNK_BITS", "FSSB200_PIPE_SLOTS", "FSSB200_PACK_NT"):
+        for key in ("FSSB200_PIPE_CHUNK_BITS", "FSSB200_PIPE_SLOTS", "FSSB200_PACK_NT", "FSSB200_PIPE_PIECE_BITS", "FSSB200_PIPE_LOW_WATER_MB"):
             os.environ.pop(key, None)
         for key, v in cfg.get("env", {}).items():
             os.environ[key] = str(v)
@@ -61,16 +61,25 @@ def main():
     ap.add_argument("--keys", type=int, default=1 << 22)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--threads", default="0,4,8,16", help="FSSB200_PACK_THREADS values (0 = library default for the box)")
+    ap.add_argument("--tune", default="single")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "e2e_sweep.jsonl"))
     args = ap.parse_args()
     if args.child:
         child(args)
         return
     base = [{"mode": 0}, {"mode": 1}, {"mode": 2}]
-    nt0 = lambda b, s, m=0: {"mode": m, "env": {"FSSB200_PACK_NT": 0, "FSSB200_PIPE_CHUNK_BITS": b, "FSSB200_PIPE_SLOTS": s}}  # noqa: E731
-    nt1 = lambda b, s, m=0: {"mode": m, "env": {"FSSB200_PACK_NT": 1, "FSSB200_PIPE_CHUNK_BITS": b, "FSSB200_PIPE_SLOTS": s}}  # noqa: E731
-    tune = [nt0(14, 3), nt0(14, 5), nt0(14, 6), nt0(14, 8), nt0(15, 2), nt0(15, 3), nt0(15, 4), nt0(13, 8), nt0(13, 12),
-            nt1(16, 6), nt1(15, 6), nt1(14, 4)]
+
+    def cfg(piece, slots, nt, chunk=16, mode=0, low=None):
+        env = {"FSSB200_PACK_NT": nt, "FSSB200_PIPE_PIECE_BITS": piece, "FSSB200_PIPE_SLOTS": slots,
+               "FSSB200_PIPE_CHUNK_BITS": chunk}
+        if low is not None:
+            env["FSSB200_PIPE_LOW_WATER_MB"] = low
+        return {"mode": mode, "env": env}
+    tune = [cfg(14, 4, 0), cfg(14, 5, 0), cfg(14, 6, 0), cfg(13, 6, 0), cfg(13, 8, 0), cfg(13, 10, 0), cfg(12, 8, 0), cfg(12, 12, 0),
+            cfg(12, 16, 0), cfg(14, 4, 0, 17), cfg(14, 4, 0, 15), cfg(14, 4, 0, low=8), cfg(14, 4, 0, low=32), cfg(14, 4, 0, mode=2),
+            cfg(14, 8, 1), cfg(15, 6, 1), cfg(16, 6, 1)]
+    if args.tune == "multi":   # several ranks share the host: small cache-resident rings vs streaming rings
+        tune = [cfg(13, 4, 0), cfg(12, 4, 0), cfg(12, 8, 0), cfg(11, 8, 0), cfg(14, 4, 0), cfg(14, 6, 1), cfg(16, 6, 1), cfg(12, 16, 1)]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         for i, t in enumerate(args.threads.split(",")):
