@@ -23,13 +23,16 @@ struct Uint {
 
   Uint() = default;
   FSS_SHIM_HD Uint operator+(Uint rhs) const {
-    if constexpr (mod == 0) return Uint(static_cast<T>(val + rhs.val));
-    const unsigned __int128 s = static_cast<unsigned __int128>(val) + rhs.val;  // both < mod <= 2^127
-    return Uint(static_cast<T>(s >= mod ? s - mod : s));
+    if constexpr (mod == 0) {
+      return Uint(static_cast<T>(val + rhs.val));
+    } else {
+      const unsigned __int128 s = static_cast<unsigned __int128>(val) + rhs.val;  // both < mod <= 2^127
+      return Uint(static_cast<T>(s >= mod ? s - mod : s));
+    }
   }
   FSS_SHIM_HD Uint operator-() const {
     if constexpr (mod == 0) return Uint(static_cast<T>(T(0) - val));
-    return Uint(val == 0 ? T(0) : static_cast<T>(mod - val));
+    else return Uint(val == 0 ? T(0) : static_cast<T>(mod - val));
   }
   // Little-endian words; a 16-byte T drops the clamp bit with `.w >> 1` (uint.cuh:49-68).
   FSS_SHIM_HD static Uint From(int4 buf) {
