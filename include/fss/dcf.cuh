@@ -46,6 +46,7 @@ public:
   }
 
   FSS_SHIM_HD void Gen(Cw cws[], const int4 s0s[2], In a, int4 b_buf) const {          // dcf.cuh:108
+    KeepGenericKernels();
 #if defined(__CUDA_ARCH__)
     b200::generic::DcfGen<in_bits, Group, In>(const_cast<Prg &>(prg), pred == DcfPred::kLt, cws, s0s, a, b_buf);
 #else
@@ -64,6 +65,7 @@ public:
 #endif
   }
   FSS_SHIM_HD int4 Eval(bool b, int4 s0, const Cw cws[], In x) const {                  // dcf.cuh:205
+    KeepGenericKernels();
 #if defined(__CUDA_ARCH__)
     return b200::generic::DcfEval<in_bits, Group, In>(const_cast<Prg &>(prg), b, s0, cws, x);
 #else
@@ -167,6 +169,18 @@ public:
   }
 
 private:
+  // The single-key members above reach the batched members (and through them the generic kernels) only in their HOST
+  // branch.  nvcc instantiates a __global__ template for the device only if the instantiation is also seen while
+  // __CUDA_ARCH__ is defined, so the members name the kernels once outside the branch.
+  FSS_SHIM_HD static void KeepGenericKernels() {
+#if defined(__CUDACC__)
+    if constexpr (!kPrebuilt) {
+      [[maybe_unused]] auto g = &b200::generic::GenKernel<Dcf, In>;
+      [[maybe_unused]] auto e = &b200::generic::EvalKernel<Dcf, In>;
+      [[maybe_unused]] auto a = &b200::generic::EvalAllKernel<Dcf, In>;
+    }
+#endif
+  }
   static void UserPluginNeedsNvcc() {
 #if !defined(__CUDACC__)
     static_assert(kPrebuilt, "a user-defined Group / Prg plugin is compiled for the GPU in YOUR translation unit: "

@@ -48,6 +48,7 @@ public:
 
   // ---- the reference's single-key members ----
   FSS_SHIM_HD void Gen(Cw cws[], const int4 s0s[2], In a, int4 b_buf) const {          // dpf.cuh:93
+    KeepGenericKernels();
 #if defined(__CUDA_ARCH__)
     b200::generic::DpfGen<in_bits, Group, In>(const_cast<Prg &>(prg), cws, s0s, a, b_buf);
 #else
@@ -66,6 +67,7 @@ public:
 #endif
   }
   FSS_SHIM_HD int4 Eval(bool b, int4 s0, const Cw cws[], In x) const {                  // dpf.cuh:170
+    KeepGenericKernels();
 #if defined(__CUDA_ARCH__)
     return b200::generic::DpfEval<in_bits, Group, In>(const_cast<Prg &>(prg), b, s0, cws, x);
 #else
@@ -195,6 +197,18 @@ public:
   }
 
 private:
+  // The single-key members above reach the batched members (and through them the generic kernels) only in their HOST
+  // branch.  nvcc instantiates a __global__ template for the device only if the instantiation is also seen while
+  // __CUDA_ARCH__ is defined, so the members name the kernels once outside the branch.
+  FSS_SHIM_HD static void KeepGenericKernels() {
+#if defined(__CUDACC__)
+    if constexpr (!kPrebuilt) {
+      [[maybe_unused]] auto g = &b200::generic::GenKernel<Dpf, In>;
+      [[maybe_unused]] auto e = &b200::generic::EvalKernel<Dpf, In>;
+      [[maybe_unused]] auto a = &b200::generic::EvalAllKernel<Dpf, In>;
+    }
+#endif
+  }
   static void UserPluginNeedsNvcc() {
 #if !defined(__CUDACC__)
     static_assert(kPrebuilt, "a user-defined Group / Prg plugin is compiled for the GPU in YOUR translation unit: "

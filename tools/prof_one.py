@@ -1,6 +1,6 @@
 """One small workload per invocation, for `ncu -k regex:<kernel> -s 2 -c 1` captures (profiles/).
 
-  python tools/prof_one.py evalall_dpf|evalall_ht|evalall_dcf|gen_dcf|gen_dpf|grotto
+  python tools/prof_one.py evalall_dpf|evalall_ht|evalall_dcf|gen_dcf|gen_dpf|grotto|c2|c3|ht|packed|vdpf|walk
 """
 import os
 import sys
@@ -28,7 +28,36 @@ def main():
         alphas = torch.randint(0, 1 << min(n, 62), (k,), dtype=torch.int64, device=dev, generator=g)
         return s0s, alphas, betas
 
-    if which.startswith("evalall") or which == "grotto":
+    if which in ("c2", "c3", "ht", "packed", "vdpf", "walk"):
+        scheme, n, k, group = {"c2": ("dpf", 32, 1 << 22, "bytes"), "c3": ("dcf", 64, 1 << 21, "u128"),
+                               "ht": ("halftree", 32, 1 << 20, "bytes"), "packed": ("dpf", 32, 1 << 21, "bytes"),
+                               "vdpf": ("vdpf", 32, 1 << 20, "bytes"), "walk": ("grotto", 32, 1 << 20, "bytes")}[which]
+        ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
+        s0s, alphas, betas = inputs(k, n)
+        xs = torch.randint(0, 1 << min(n, 62), (k,), dtype=torch.int64, device=dev, generator=g)
+        if n <= 32:
+            alphas, xs = alphas.to(torch.int32), xs.to(torch.int32)
+        seeds0 = s0s[:, 0].contiguous()
+        if scheme == "vdpf":
+            cws, cs, ocws, _ = ctx.vdpf_gen(s0s, alphas, betas)
+            for _ in range(3):
+                ctx.vdpf_eval(0, seeds0, cws, cs, ocws, xs)
+        elif scheme == "grotto":
+            cws = ctx.gen(s0s, alphas)
+            for _ in range(3):
+                ctx.grotto_walk(0, seeds0, cws, xs)
+        else:
+            r = ctx.gen(s0s, alphas, betas)
+            cws, ocws = r if scheme == "halftree" else (r, None)
+            ys = torch.empty((k, 4), dtype=torch.int32, device=dev)
+            if which == "packed":
+                rows = ctx.pack_rows(cws.cpu()).to(dev)
+                for _ in range(3):
+                    ctx.eval_packed(0, seeds0, rows, xs, out=ys)
+            else:
+                for _ in range(3):
+                    ctx.eval(0, seeds0, cws, xs, ocws, out=ys)
+    elif which.startswith("evalall") or which == "grotto":
         scheme, n, k, group = {"evalall_dpf": ("dpf", 26, 2, "bytes"), "evalall_ht": ("halftree", 26, 2, "bytes"),
                                "evalall_dcf": ("dcf", 24, 2, "u128"), "grotto": ("grotto", 26, 2, "bytes")}[which]
         ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
