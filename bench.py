@@ -507,11 +507,14 @@ def run_own_arm(args) -> None:
         del d_probe
         e2e = e2e_leg(0)
         e2e["api"] = ("fssb200_eval_host: reference-layout keys (32-byte Dpf::Cw) in pinned host buffers, results back in "
-                      "pinned host memory, wall clock around the blocking call; adaptive pipeline: host threads strip the "
-                      "15 padding bytes of each Cw for chunks taken from the front of the batch while chunks from the back "
-                      "cross the link as they are whenever it would otherwise idle")
+                      "pinned host memory, wall clock around the blocking call; automatic mode: with 1-2 ranks per host the "
+                      "adaptive pipeline (host threads strip the 15 padding bytes of each Cw for chunks taken from the front of "
+                      "the batch while rows from the back cross the link as they are whenever it would otherwise idle), with "
+                      ">= 3 ranks the rows cross as they are (the host memory system, not the links, is the bound)")
         e2e["direct_copy"] = e2e_leg(1)     # reference layout crosses the link as it is
         e2e["staged_only"] = e2e_leg(2)     # every chunk packed by the host threads
+        if world >= 3:                      # automatic mode = direct from three ranks on: show what it is chosen over
+            e2e["adaptive_forced"] = e2e_leg(3)
         ctx.set_host_mode(0)
         # link utilisation and the ceiling a plain copy of the reference layout could reach on this box
         agg_h2d_gbs = world * e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9

@@ -528,7 +528,7 @@ struct EvalPipe : CrewJob {
 // Large batches with worker threads available.  `allow_direct`: the caller's rows are pinned, so chunks may also
 // cross the link straight from them.
 int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const void *cws, const void *ocws_v,
-    const void *xs_v, void *ys_v, size_t nkeys, Crew *crew, bool allow_direct, bool ys_pinned) {
+    const void *xs_v, void *ys_v, size_t nkeys, Crew *crew, bool allow_direct, bool ys_pinned, bool stage_nothing = false) {
   const uint8_t *seeds = static_cast<const uint8_t *>(seeds_v), *ocws = static_cast<const uint8_t *>(ocws_v),
                 *xs = static_cast<const uint8_t *>(xs_v);
   uint8_t *ys = static_cast<uint8_t *>(ys_v);
@@ -556,7 +556,7 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
   {
     size_t want = cached_ring ? 4 : 6;
     want = size_t(std::max(2, std::min(kMaxSlots, env_int("FSSB200_PIPE_SLOTS", int(want)))));
-    P.nslots = std::min(want, P.nchunks * P.ppc);
+    P.nslots = stage_nothing ? 0 : std::min(want, P.nchunks * P.ppc);
   }
   const int nsets = int(std::min<size_t>(kMaxSets, std::max<size_t>(2, std::min<size_t>(P.nchunks, 4))));
   // device set: rows (reference layout: the larger of the two formats) | seeds | xs | ocws | ys
@@ -571,11 +571,11 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
   uint8_t *ys_pin = A.pin + P.nslots * P.slot_bytes;
   P.st.reset(new (std::nothrow) EvalPipe::PieceState[P.nchunks * P.ppc]);
   if (!P.st) return FSSB200_EINVAL;
-  P.tail.store(P.nchunks);
+  P.tail.store(stage_nothing ? 0 : P.nchunks);  // stage_nothing: every chunk crosses the link as it is, piece by piece
   P.free_upto.store(P.nslots);
 
   // (no idle worker and pageable inputs: the calling thread stages alone -- still correct, just slower)
-  const int lent = crew ? crew->begin(&P, t_crew_share > 0 ? t_crew_share : crew->workers()) : 0;
+  const int lent = (crew && !stage_nothing) ? crew->begin(&P, t_crew_share > 0 ? t_crew_share : crew->workers()) : 0;
 
   struct SetUse {
     bool busy = false;      // holds a chunk
@@ -666,6 +666,7 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
     cudaStream_t str = nullptr;
   };
   Open so, dio;              // the staged chunk (front of the batch) and the direct chunk (back) in progress
+  size_t direct_next = 0;    // stage_nothing: next chunk to send
   int dir_ev_next = 0;       // direct pieces take their link events from a small ring
   auto open_chunk = [&](Open &o, int s, size_t ch) {  // s: a free device set
     o.set = s;
@@ -683,7 +684,7 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
     if (rc) break;
     const size_t tl = P.tail.load(std::memory_order_acquire);
     const bool staged_left = next_piece / P.ppc < tl;
-    if (!staged_left && dio.set < 0) break;  // every chunk has been issued
+    if (!staged_left && dio.set < 0 && (!stage_nothing || direct_next >= P.nchunks)) break;  // every chunk has been issued
     bool progressed = false;
     if (staged_left) {
       const size_t ch = next_piece / P.ppc, pi = next_piece % P.ppc, kp = P.keys_of_piece(next_piece);
@@ -720,12 +721,14 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
     // The link is about to run dry and no staged piece is ready (or nothing is left to stage): rows from the back of
     // the batch cross as they are, one piece at a time so that a staged piece never waits long behind them.
     if (!progressed && allow_direct && (link_bytes < low_water || !staged_left) && link.size() < 24) {
-      if (dio.set < 0 && staged_left) {
+      if (dio.set < 0 && (staged_left || stage_nothing)) {
         const int s = acquire_set();  // (before the claim: a chunk taken from the back is never given back)
         if (rc) break;
         if (s >= 0) {
           size_t take = ~size_t(0);
-          {
+          if (stage_nothing) {  // nothing is staged: the chunks simply go in order
+            if (direct_next < P.nchunks) take = direct_next++;
+          } else {
             std::lock_guard<std::mutex> l(P.claim_mu);
             const size_t t = P.tail.load(std::memory_order_relaxed);
             if (t > 0 && t - 1 > P.cur.load(std::memory_order_relaxed) / P.ppc && t - 1 > next_piece / P.ppc) {
@@ -782,7 +785,7 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
   rc = L.drain(rc);
   c->last_direct_keys.store(direct_keys, std::memory_order_relaxed);
   c->last_packed_keys.store(nkeys - direct_keys, std::memory_order_relaxed);  // staged: packed, or copied (no padding)
-  c->last_pack_threads.store(lent + 1, std::memory_order_relaxed);
+  c->last_pack_threads.store(stage_nothing ? 0 : lent + 1, std::memory_order_relaxed);
   return rc;
 }
 
@@ -877,7 +880,7 @@ int fssb200_ctx_host_stats(const fssb200_ctx *c, uint64_t *packed_keys, uint64_t
 }
 
 int fssb200_ctx_set_host_mode(fssb200_ctx *c, int mode) {
-  if (!c || mode < 0 || mode > 2) return FSSB200_EINVAL;
+  if (!c || mode < 0 || mode > 3) return FSSB200_EINVAL;
   c->host_mode.store(mode, std::memory_order_relaxed);
   return 0;
 }
@@ -907,18 +910,28 @@ int fssb200_eval_host(fssb200_ctx *c, int party, const void *seeds, const void *
   if (!seeds || !cws || !xs || !ys) return FSSB200_EINVAL;
   if (c->p.scheme == FSSB200_SCHEME_HALFTREE && !ocws) return FSSB200_EINVAL;
   if (nkeys == 0) return 0;
-  Crew *crew = nkeys >= 8192 ? Crew::get() : nullptr;
-  if (crew) {
+  if (nkeys >= 8192) {
     DeviceGuard g(c->p.device);
     if (g.err != cudaSuccess) return int(g.err);
+    Crew *crew = Crew::get();
     const bool in_pinned = is_pinned_or_device(cws) && is_pinned_or_device(seeds) && is_pinned_or_device(xs) &&
         (!ocws || is_pinned_or_device(ocws));
     const bool packable = fssb200_packed_row_bytes(c) != 0;
-    // pinned inputs of a scheme without padding: nothing to gain from staging, the link takes the rows as they are
-    const int mode = c->host_mode.load(std::memory_order_relaxed);
-    if (mode != 1 && (packable || !in_pinned))
+    int mode = c->host_mode.load(std::memory_order_relaxed);
+    // Auto (0): packing pays while the LINKS are the bound -- one or two GPUs per host on the boxes measured.  From
+    // three GPUs on, the links together ask for more than the host memory system serves (4 GPUs: 167 GB/s for all,
+    // 38-52 GB/s each), a packed key costs the same DRAM read as a plain one, and the packing cores only take
+    // bandwidth from the copy engines: 137 ms packed vs 119 ms plain per 2^22 keys and rank (profiles/r02_host_pipeline.md).
+    if (mode == 0 && in_pinned && std::max(env_int("LOCAL_WORLD_SIZE", 1), t_devices_sharing_host) >= 3) mode = 1;
+    if (mode == 3) mode = 0;  // adaptive pipeline whatever the rank count (A/B measurements)
+    if (mode == 1 && in_pinned)  // the reference layout crosses as it is, in pieces that keep the link's queue full
+      return eval_host_pipelined(c, party, seeds, cws, ocws, xs, ys, nkeys, nullptr, true, is_pinned_or_device(ys), true);
+    // (pinned inputs of a scheme without padding: nothing to gain from staging either)
+    if (crew && mode != 1 && (packable || !in_pinned))
       return eval_host_pipelined(c, party, seeds, cws, ocws, xs, ys, nkeys, crew, in_pinned && mode != 2,
           is_pinned_or_device(ys));
+    if (in_pinned)
+      return eval_host_pipelined(c, party, seeds, cws, ocws, xs, ys, nkeys, nullptr, true, is_pinned_or_device(ys), true);
   }
   return eval_host_simple(c, party, seeds, cws, ocws, xs, ys, nkeys);
 }

@@ -311,9 +311,12 @@ int fssb200_eval_levelmajor(const fssb200_ctx *ctx, int party, const void *seeds
  * fssb200_eval_packed + D2H; whenever the link is about to run dry and no packed chunk is
  * ready, a chunk from the back of the batch crosses in the reference layout straight from
  * the caller's (pinned) buffer.  Pageable inputs are always staged by the workers (packed,
- * or copied for schemes without padding).  fssb200_ctx_set_host_mode(): 0 = adaptive
- * (default), 1 = reference layout only, 2 = staged chunks only.  A call that finds the
- * worker threads lent to another call runs the plain chunked path instead. */
+ * or copied for schemes without padding).  fssb200_ctx_set_host_mode(): 0 = automatic (default:
+ * the adaptive pipeline with one or two ranks per host; from three ranks on the links together
+ * ask for more than the host memory serves and packing only takes bandwidth from the copy
+ * engines, so the rows cross as they are), 1 = reference layout only, 2 = staged chunks only,
+ * 3 = adaptive pipeline whatever the rank count.  A call that finds no idle worker thread stages
+ * with the calling thread alone. */
 int fssb200_ctx_reserve_host(fssb200_ctx *ctx, size_t max_keys_per_chunk);
 int fssb200_ctx_set_host_mode(fssb200_ctx *ctx, int mode);
 /* Keys of this context's last fssb200_eval_host call that crossed the link staged by the host

@@ -428,7 +428,7 @@ def test_error_codes_on_device(dev):
     assert L.lib.fssb200_eval_all(hs, 0, p, p, None, p, 1, gr, 2 ** 64 - gr, None) == L.E_RANGE
     assert L.lib.fssb200_eval_all_host(hs, 0, p, p, None, p, 1, gr, 2 ** 64 - gr) == L.E_RANGE
     assert L.lib.fssb200_eval_host(h, 2, p, p, None, p, p, 1) == L.E_INVAL
-    assert L.lib.fssb200_ctx_set_host_mode(h, 3) == L.E_INVAL
+    assert L.lib.fssb200_ctx_set_host_mode(h, 4) == L.E_INVAL
     g = fss_b200.Context("grotto", 10)
     assert L.lib.fssb200_eval(g.handle(0), 0, p, p, None, p, p, 1, None) == L.E_SCHEME
 
