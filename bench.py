@@ -502,6 +502,8 @@ def run_own_arm(args) -> None:
         my_gbs = 6 * probe_bytes / (time.perf_counter() - t0) / 1e9
         ceiling = {"per_rank_min_gbs": reduce_ranks(my_gbs, "min"), "per_rank_max_gbs": reduce_ranks(my_gbs, "max"),
                    "total_gbs": reduce_ranks(my_gbs, "sum"), "ranks": world,
+                   # every rank holds the same number of keys, so a step lasts as long as the SLOWEST link needs
+                   "balanced_total_gbs": world * reduce_ranks(my_gbs, "min"),
                    "how": "every rank copies 1 GiB of pinned host memory to its GPU 6 times back to back, all ranks at "
                           "once (cudaMemcpyAsync, wall clock per rank)"}
         del d_probe
@@ -522,6 +524,7 @@ def run_own_arm(args) -> None:
         e2e["h2d_ceiling"] = ceiling
         e2e["h2d_gbs_total"] = agg_h2d_gbs
         e2e["link_utilisation"] = agg_h2d_gbs / ceiling["total_gbs"]
+        e2e["frac_of_balanced_h2d_ceiling"] = agg_h2d_gbs / ceiling["balanced_total_gbs"]
         e2e["evals_per_s_if_reference_layout_at_ceiling"] = plain_ceiling
         e2e["value_over_plain_copy_ceiling"] = e2e["value"] / plain_ceiling
         e2e["direct_copy"]["frac_of_h2d_ceiling"] = (world * e2e["direct_copy"]["h2d_bytes_per_step"] /
