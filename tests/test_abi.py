@@ -77,3 +77,17 @@ def test_error_codes_without_gpu():
         assert L.lib.fssb200_microbench(0, 0, C.byref(v)) == L.E_NODEVICE
     assert L.lib.fssb200_ctx_ncw(None) == L.E_INVAL
     assert L.lib.fssb200_eval(None, 0, None, None, None, None, None, 0, None) == L.E_INVAL
+
+
+@pytest.mark.parametrize("src,extra", [("shim_sample.cpp", []), ("omp_eval.cpp", ["-fopenmp"])])
+def test_header_shim_compiles_with_plain_gxx(tmp_path, src, extra):
+    """include/fss/*.cuh with the built-in plugins needs no nvcc: g++ -std=c++20 + the C-ABI library (compile and link
+    only here; the -m gpu tests run the binaries)."""
+    exe = str(tmp_path / src.replace(".cpp", ""))
+    subprocess.run(["g++", "-std=c++20", "-O1", *extra, "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "cpp", src), "-o", exe, "-L", os.path.join(ROOT, "fss_b200"), "-lfssb200",
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "fss_b200")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import torch
+    if not torch.cuda.is_available():   # fails loudly without a GPU: an exception from fssb200_ctx_create, never a CPU result
+        assert r.returncode != 0 and "no such CUDA device" in (r.stdout + r.stderr)
