@@ -149,6 +149,10 @@ class Context:
             return t.to(torch.int64).view(torch.uint8).reshape(-1, 8)[:, :nb].contiguous().to(device)
         if isinstance(vals, int):
             vals = [vals]
+        top = 1 << self.in_bits
+        for v in vals:  # (tensors are not range-checked: that would cost a device synchronisation per call)
+            if not 0 <= int(v) < top:
+                raise ValueError(f"domain value {int(v)} outside [0, 2^{self.in_bits})")
         raw = b"".join(int(v).to_bytes(nb, "little") for v in vals)
         return torch.frombuffer(bytearray(raw), dtype=torch.uint8).reshape(len(vals), nb).to(device)
 

@@ -152,3 +152,42 @@ def test_cpp_openmp_eval(dev, tmp_path):
                     "-Wl,-rpath," + os.path.join(ROOT, "fss_b200")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="8"))
     assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("prg", ["aes128_mmo", "chacha"])
+@pytest.mark.parametrize("n,in_bytes,nkeys", [(1, 1, 5), (5, 1, 33), (8, 1, 1000), (10, 2, 257), (16, 2, 31), (20, 4, 4097),
+                                               (32, 4, 20000), (33, 8, 100), (64, 8, 3000), (100, 16, 64), (128, 16, 999)])
+def test_grotto_walk(dev, orc, prg, n, in_bytes, nkeys):
+    """fssb200_grotto_eval_walk: share0 ^ share1 == 1[alpha <= x] on every key (ragged tiles, every In width, both PRGs,
+    the e == 0 / e == N edge), and == the reference's Preprocess + Eval reconstructed where the parity tree exists."""
+    p = Params(scheme="grotto", in_bits=n, prg=prg, in_bytes=in_bytes)
+    ctx = mkctx(p)
+    s0s, alphas, _, xs = synth_inputs(p, nkeys, seed=1000 + n)
+    top = (1 << n) - 1
+    xs[0] = top                       # e == N (or e wraps to 0 when n == 8 * in_bytes): the whole domain
+    if nkeys > 4:
+        xs[1], alphas[2], xs[2], alphas[3], xs[3] = 0, 0, 0, top, top
+    cws = orc.gen(p, s0s, alphas, None, threads=8)
+    cw_d = T(cws, dev)
+    w = [N(ctx.grotto_walk(b, T(s0s[:, b], dev), cw_d, xs), np.uint8) for b in (0, 1)]
+    want = np.array([1 if int(a) <= int(x) else 0 for a, x in zip(alphas, xs)], np.uint8)
+    assert np.array_equal(w[0] ^ w[1], want)
+    assert set(np.unique(w[0])) <= {0, 1}
+    if n <= 16:
+        k = min(nkeys, 8)
+        ref = [orc.grotto_lookup(p, orc.grotto_preprocess(p, b, s0s[:k, b], cws[:k]), xs[:k]) for b in (0, 1)]
+        assert np.array_equal((w[0] ^ w[1])[:k], ref[0] ^ ref[1])
+
+
+def test_grotto_walk_rejects_other_schemes(dev):
+    import fss_b200
+    from fss_b200 import _lib as L
+    ctx = fss_b200.Context("dpf", 16)
+    buf = torch.zeros(4096, dtype=torch.int32, device=dev)
+    p = C.c_void_p(buf.data_ptr())
+    assert L.lib.fssb200_grotto_eval_walk(ctx.handle(0), 0, p, p, p, p, 1, None) == L.E_SCHEME
+    g = fss_b200.Context("grotto", 16)
+    assert L.lib.fssb200_grotto_eval_walk(g.handle(0), 2, p, p, p, p, 1, None) == L.E_INVAL
+    assert L.lib.fssb200_grotto_eval_walk(g.handle(0), 0, p, p, p, p, 0, None) == 0
+    with pytest.raises(RuntimeError):
+        g.grotto_walk(0, torch.zeros((1, 4), dtype=torch.int32), torch.zeros((1, 17, 8), dtype=torch.int32), [0])

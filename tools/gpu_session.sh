@@ -10,6 +10,7 @@
 #   launches  ncu launch list of the bench command               -> gpurun_out/launches.csv
 #   ncu       ncu --set full of the kernels in $NCU_KERNELS      -> gpurun_out/prof_<name>.ncu-rep
 #   host      lscpu / numactl / nvidia-smi topo of the box       -> gpurun_out/host.txt
+#   sanitize  compute-sanitizer ($SAN_TOOLS) over tools/sanitize_cases.py ($SAN_CASES) -> gpurun_out/sanitize_<tool>.log
 set -u
 mkdir -p gpurun_out
 for step in "$@"; do
@@ -41,6 +42,12 @@ for step in "$@"; do
         timeout 600 ncu --set full --clock-control none --import-source on -k regex:${NCU_REGEX:-$rx} -s ${NCU_SKIP:-2} -c 1 \
           -f -o gpurun_out/prof_$k python tools/prof_one.py $k > gpurun_out/prof_$k.log 2>&1
         echo "ncu $k rc=$?"
+      done ;;
+    sanitize)
+      for tool in ${SAN_TOOLS:-memcheck racecheck}; do
+        timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_cases.py ${SAN_CASES:-walk pipeline packed} \
+          > gpurun_out/sanitize_$tool.log 2>&1
+        echo "sanitize $tool rc=$?"; tail -4 gpurun_out/sanitize_$tool.log
       done ;;
     *) echo "unknown step $step" ;;
   esac

@@ -117,5 +117,31 @@ if not only or "packed" in only:
         yh = ctx.eval(1, torch.from_numpy(np.ascontiguousarray(s0s[:, 1]).view(np.int32)), torch.from_numpy(oc.view(np.int32)),
                       xs, None if ooc is None else torch.from_numpy(ooc.view(np.int32)))
         same(f"eval_host packed pipeline {scheme}-{n}", yh, w)
+if not only or "walk" in only:
+    # Grotto O(n) walk (TMA tiles, mode 4) and every mode of the host pipeline (pinned + pageable, ragged pieces)
+    for n, nkeys, prg in ((32, 1000, "aes128_mmo"), (9, 77, "chacha"), (64, 333, "aes128_mmo")):
+        p = Params(scheme="grotto", in_bits=n, prg=prg)
+        s0s, alphas, _, xs = synth_inputs(p, nkeys, seed=n)
+        ctx = fss_b200.Context("grotto", n, "bytes", prg=prg, prg_key=p.prg_key)
+        cws = ctx.gen(t(s0s), alphas, None)
+        w0 = ctx.grotto_walk(0, t(s0s[:, 0]), cws, xs).cpu().numpy()
+        w1 = ctx.grotto_walk(1, t(s0s[:, 1]), cws, xs).cpu().numpy()
+        assert np.array_equal(w0 ^ w1, np.array([int(a) <= int(x) for a, x in zip(alphas, xs)], np.uint8))
+        print(f"ok grotto walk n={n} {prg}", flush=True)
+if not only or "pipeline" in only:
+    p = Params(scheme="dpf", in_bits=32)
+    nk = 40000
+    s0s, alphas, betas, xs = synth_inputs(p, nk, seed=31)
+    oc = orc.gen(p, s0s, alphas, betas, threads=4)
+    w = orc.eval(p, 0, s0s[:, 0], oc, xs, threads=4)
+    ctx = fss_b200.Context("dpf", 32, "bytes", prg="aes128_mmo")
+    ctx.reserve_host(9000)
+    hs, hc = torch.from_numpy(np.ascontiguousarray(s0s[:, 0]).view(np.int32)), torch.from_numpy(oc.view(np.int32))
+    hx = ctx.in_tensor(xs, torch.device("cpu"))
+    for mode in (0, 1, 2, 3):
+        ctx.set_host_mode(mode)
+        for pin in (True, False):
+            a = [v.pin_memory() for v in (hs, hc, hx)] if pin else [hs, hc, hx]
+            same(f"host pipeline mode {mode} pinned={pin}", ctx.eval(0, a[0], a[1], a[2]), w)
 torch.cuda.synchronize()
 print("ALL OK")
