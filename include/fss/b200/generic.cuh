@@ -154,6 +154,63 @@ FSS_SHIM_HD void DcfGen(Prg &prg, bool lt, Cw cws[], const int4 s0s[2], In a, in
   cws[in_bits].v = v_np1.Into();
 }
 
+// ---- Half-Tree DPF ------------------------------------------------------------------------------------------------------
+// H(node) = prg.Gen(hash_key ^ node)[0] with the control bit t = lsb(node) INSIDE the hashed value (half_tree_dpf.cuh:195).
+template <typename Prg>
+FSS_SHIM_HD int4 HtHash(Prg &prg, int4 hash_key, int4 node) { return prg.Gen(util::Xor(hash_key, node))[0]; }
+
+// HalfTreeDpf::Eval, half_tree_dpf.cuh:187-231: n hashes per evaluation.
+template <int in_bits, typename Group, typename In, typename Prg, typename Cw>
+FSS_SHIM_HD int4 HalfTreeEval(Prg &prg, int4 hash_key, bool b, int4 s0, const Cw cws[], int4 ocw, In x) {
+  int4 node = util::SetLsb(s0, b);
+  for (int i = 0; i < in_bits - 1; ++i) {
+    const bool t = util::GetLsb(node), right = BitMsbFirst(x, in_bits, i);
+    const int4 h = HtHash(prg, hash_key, node);
+    node = Masked(Masked(h, right, node), t, cws[i].s);                  // :202-204 (the cw's lsb included)
+  }
+  const bool sigma = (x & 1) != 0, t = util::GetLsb(node);
+  const Cw &last = cws[in_bits - 1];
+  int4 h = HtHash(prg, hash_key, util::SetLsb(node, sigma));              // :208-216
+  h = Masked(h, t, util::SetLsb(last.s, sigma ? bool(last.extra) : util::GetLsb(last.s)));   // high ^= HCW, low ^= LCW_sigma
+  Group y = Group::From(Clamp(h));
+  if (util::GetLsb(h)) y = y + Group::From(ocw);
+  if (b) y = -y;
+  return y.Into();
+}
+
+// HalfTreeDpf::Gen, half_tree_dpf.cuh:68-175.  Levels 0..n-2: only `.s` and `.extra = false` are defined by the
+// reference (aggregate assignment, :91); both 16-byte halves are written here, padding zero.
+template <int in_bits, typename Group, typename In, typename Prg, typename Cw>
+FSS_SHIM_HD void HalfTreeGen(Prg &prg, int4 hash_key, Cw cws[], int4 &ocw, const int4 s0s[2], In a, int4 b_buf) {
+  static_assert(sizeof(Cw) == 32, "HalfTreeDpf::Cw is {int4 s; bool extra} padded to 32 bytes (half_tree_dpf.cuh:53-57)");
+  int4 n0 = Clamp(s0s[0]), n1 = util::SetLsb(s0s[1], true);
+  for (int i = 0; i < in_bits - 1; ++i) {
+    const int4 h0 = HtHash(prg, hash_key, n0), h1 = HtHash(prg, hash_key, n1);
+    const bool right = BitMsbFirst(a, in_bits, i);
+    const int4 cw = Masked(util::Xor(h0, h1), !right, util::Xor(n0, n1));   // :83-89
+    int4 *raw = reinterpret_cast<int4 *>(&cws[i]);
+    raw[0] = cw;
+    raw[1] = int4{0, 0, 0, 0};
+    const bool t0 = util::GetLsb(n0), t1 = util::GetLsb(n1);
+    n0 = Masked(Masked(h0, right, n0), t0, cw);
+    n1 = Masked(Masked(h1, right, n1), t1, cw);
+  }
+  const bool an = (a & 1) != 0, t0 = util::GetLsb(n0), t1 = util::GetLsb(n1);
+  const int4 h00 = HtHash(prg, hash_key, Clamp(n0)), h01 = HtHash(prg, hash_key, util::SetLsb(n0, true));
+  const int4 h10 = HtHash(prg, hash_key, Clamp(n1)), h11 = HtHash(prg, hash_key, util::SetLsb(n1, true));
+  const int4 hcw = an ? Clamp(util::Xor(h00, h10)) : Clamp(util::Xor(h01, h11));            // :123-125
+  const bool lcw0 = util::GetLsb(h00) ^ util::GetLsb(h10) ^ !an;                             // :132
+  const bool lcw1 = util::GetLsb(h01) ^ util::GetLsb(h11) ^ an;                              // :133
+  int4 *raw = reinterpret_cast<int4 *>(&cws[in_bits - 1]);
+  raw[0] = util::SetLsb(hcw, lcw0);
+  raw[1] = int4{lcw1 ? 1 : 0, 0, 0, 0};
+  const int4 leaf_cw = util::SetLsb(hcw, an ? lcw1 : lcw0);
+  const int4 leaf0 = Masked(an ? h01 : h00, t0, leaf_cw), leaf1 = Masked(an ? h11 : h10, t1, leaf_cw);
+  Group v = Group::From(Clamp(b_buf)) + (-Group::From(Clamp(leaf0))) + Group::From(Clamp(leaf1));   // :168-170
+  if (util::GetLsb(leaf1)) v = -v;
+  ocw = v.Into();
+}
+
 // ---- batched kernels for user-defined plugins (instantiated in the user's translation unit) --------------------------
 #if defined(__CUDACC__)
 // One key per thread; `Scheme` is a scheme object (fss::Dpf / fss::Dcf of this shim) passed by value, like the
@@ -189,6 +246,33 @@ inline void CheckLaunch(const char *what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
+// Half-Tree: the output correction word is a second per-key array
+template <typename Scheme, typename In>
+__global__ void HtEvalKernel(Scheme sch, bool b, const int4 *seeds, const typename Scheme::Cw *cws, const int4 *ocws,
+                             const In *xs, int4 *ys, size_t nkeys) {
+  for (size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x; k < nkeys; k += size_t(gridDim.x) * blockDim.x)
+    ys[k] = sch.Eval(b, seeds[k], cws + k * Scheme::kNumCw, ocws[k], xs[k]);
+}
+template <typename Scheme, typename In>
+__global__ void HtGenKernel(Scheme sch, const int4 *s0s, const In *alphas, const int4 *betas, typename Scheme::Cw *cws,
+                            int4 *ocws, size_t nkeys) {
+  for (size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x; k < nkeys; k += size_t(gridDim.x) * blockDim.x) {
+    const int4 s[2] = {s0s[2 * k], s0s[2 * k + 1]};
+    int4 ocw;
+    sch.Gen(cws + k * Scheme::kNumCw, ocw, s, alphas[k], betas[k]);
+    ocws[k] = ocw;
+  }
+}
+template <typename Scheme, typename In>
+__global__ void HtEvalAllKernel(Scheme sch, bool b, const int4 *seeds, const typename Scheme::Cw *cws, const int4 *ocws,
+                                int4 *ys, size_t nkeys, uint64_t leaf_begin, uint64_t leaf_count) {
+  const uint64_t total = uint64_t(nkeys) * leaf_count;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t k = i / leaf_count, x = leaf_begin + (i - k * leaf_count);
+    ys[i] = sch.Eval(b, seeds[k], cws + k * Scheme::kNumCw, ocws[k], In(x));
+  }
+}
+
 inline unsigned GridFor(uint64_t work, unsigned block) {
   const uint64_t want = (work + block - 1) / block;
   return unsigned(want < 1 ? 1 : (want > 148u * 16u ? 148u * 16u : want));  // a few waves of the 148 SMs, grid-stride beyond

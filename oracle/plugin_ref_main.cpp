@@ -6,6 +6,7 @@
 
 #include <fss/dcf.cuh>
 #include <fss/dpf.cuh>
+#include <fss/half_tree_dpf.cuh>
 
 #include "../tests/cpp/plugin_user_main.inc"
 

@@ -11,6 +11,7 @@
 #include <fss/dpf.cuh>
 #include <fss/group/bytes.cuh>
 #include <fss/group/uint.cuh>
+#include <fss/half_tree_dpf.cuh>
 #include <fss/prg/chacha.cuh>
 
 #include "plugin_user_main.inc"
