@@ -122,11 +122,11 @@ struct EvalAllPlan {
   int unit_bits, breadth_bits, dfs_bits;
 };
 // thread_bits: log2(threads per CTA) of the kernel (9; 8 for the DCF kernel whose nodes carry a value)
-EvalAllPlan plan_evalall(int n, int thread_bits = kEvalAllThreadBits) {
+EvalAllPlan plan_evalall(int n, int thread_bits = kEvalAllThreadBits, int max_dfs = kMaxDfsBits) {
   EvalAllPlan pl;
   int dfs = n - thread_bits;
   if (dfs < 1) dfs = 1;
-  if (dfs > kMaxDfsBits) dfs = kMaxDfsBits;
+  if (dfs > max_dfs) dfs = max_dfs;
   int bt = n - dfs;
   if (bt > thread_bits) bt = thread_bits;
   pl.dfs_bits = dfs;
@@ -402,12 +402,24 @@ int fssb200_relayout(const fssb200_ctx *cc, const void *cws, void *cw_s, void *c
 }
 
 // ---- full-domain evaluation ---------------------------------------------------------------------------------------
-static int evalall_thread_bits(const fssb200_ctx *c) {
-  return c->p.scheme == FSSB200_SCHEME_DCF ? kDcfAllThreadBits : kEvalAllThreadBits;
+// DCF full-domain kernel: 256 threads / dfs <= 8 (default), or 512 threads / dfs <= 6 with FSSB200_DCF_ALL_THREADS=512.
+// Measured on a B200 (profiles/r02_dcf_evalall_ab.md): 16 warps per SM do NOT help -- u127 0.857 vs 0.875, Bytes 0.860 vs
+// 0.861 of the LDS ceiling -- so the kernel is not bound by the latency 8 warps can hide; the larger work unit stays.
+static int dcf_all_thread_bits() {
+  static const int tb = [] {
+    const char *e = std::getenv("FSSB200_DCF_ALL_THREADS");
+    return (e && std::atoi(e) == 512) ? kDcfAllThreadBits : kDcfAllThreadBitsSmall;
+  }();
+  return tb;
+}
+static EvalAllPlan plan_for(const fssb200_ctx *c, bool dcf) {
+  if (!dcf) return plan_evalall(c->p.in_bits);
+  const int tb = dcf_all_thread_bits();
+  return plan_evalall(c->p.in_bits, tb, tb == kDcfAllThreadBits ? kDcfAllMaxDfsBits : kMaxDfsBits);
 }
 uint64_t fssb200_eval_all_granule(const fssb200_ctx *c) {
   if (!c) return 0;
-  return uint64_t(1) << plan_evalall(c->p.in_bits, evalall_thread_bits(c)).unit_bits;
+  return uint64_t(1) << plan_for(c, c->p.scheme == FSSB200_SCHEME_DCF).unit_bits;
 }
 
 static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, const void *cws, const void *ocws,
@@ -423,8 +435,8 @@ static int evalall_impl(fssb200_ctx *c, int mode, int party, const void *seeds, 
   if (leaf_begin >= N) return FSSB200_ERANGE;
   if (leaf_count == 0) leaf_count = N - leaf_begin;
   if (leaf_count > N - leaf_begin) return FSSB200_ERANGE;  // (not begin + count > N: that sum can wrap)
-  const int tbits = mode == 3 ? kDcfAllThreadBits : kEvalAllThreadBits;
-  const EvalAllPlan pl = plan_evalall(n, tbits);
+  const int tbits = mode == 3 ? dcf_all_thread_bits() : kEvalAllThreadBits;
+  const EvalAllPlan pl = plan_for(c, mode == 3);
   const uint64_t granule = uint64_t(1) << pl.unit_bits;
   if ((leaf_begin | leaf_count) & (granule - 1)) return FSSB200_ERANGE;
   if (nkeys == 0) return 0;

@@ -758,10 +758,18 @@ evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAl
 }
 
 // ---- DCF full-domain evaluation (Dcf::EvalAll, dcf.cuh:294-385; the reference has no GPU version) ---------------------
-// Same three phases as evalall_kernel with 256 threads per CTA: a node carries its running value share
-// (32 bytes per stack / frontier entry), four AES blocks per node with fixed keys 0..3.
-constexpr int kDcfAllThreads = 256;
-constexpr int kDcfAllThreadBits = 8;
+// Same three phases as evalall_kernel; a node carries its running value share (32 bytes per stack / frontier entry),
+// four AES blocks per node with fixed keys 0..3.  Two geometries (TB = log2 threads per CTA):
+//   TB = 8  256 threads, up to 7 stack levels (56 KB), 8 warps per SM, work unit 2^16 leaves: the shipped default
+//           (0.86-0.88 of the LDS ceiling);
+//   TB = 9  512 threads, 16 warps per SM (FSSB200_DCF_ALL_THREADS=512).  99 KB of scratch beside the 128 KB of tables hold
+//           five 16 KB levels: the two breadth buffers are dead once every thread has taken its start node and become
+//           stack levels 0 and 1, three more levels live below the tables => dfs <= 6, work unit 2^15 leaves.  Built to
+//           test the round-1 guess that 8 warps cannot hide the 4-block latency: they can -- 16 warps are no faster
+//           (profiles/r02_dcf_evalall_ab.md).
+constexpr int kDcfAllThreadBitsSmall = 8;
+constexpr int kDcfAllThreadBits = 9;
+constexpr int kDcfAllMaxDfsBits = 6;   // TB = 9: five stack levels
 
 // group values travel through shared memory in their Into() form
 template <int G>
@@ -773,12 +781,13 @@ FSS_D void smem_store_val(const GroupArgs &ga, uint32_t addr, typename Grp<G>::V
   sts_blk(addr, Grp<G>::into(ga, v));
 }
 
-template <int G, int PRG>
-__global__ void __launch_bounds__(kDcfAllThreads, 1)
+template <int G, int PRG, int TB>
+__global__ void __launch_bounds__(1 << TB, 1)
 dcf_evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ EvalAllArgs A) {
   typedef Grp<G> GR;
   typedef typename GR::V V;
-  constexpr uint32_t T = kDcfAllThreads;
+  constexpr uint32_t T = 1u << TB;
+  constexpr bool kReuseBfs = TB == 9;
   SmemPlan sp = smem_plan<PRG>();
   const typename Prg<PRG>::ctx_t pc = prg_ctx_init<PRG>(sp);
   const int n = A.in_bits, ncw = n + 1;
@@ -787,7 +796,13 @@ dcf_evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ Ev
   const int du = n - A.unit_bits;
   const uint32_t s_cw = sp.alloc(uint32_t(ncw) * 48u, true);            // {cwl, cwr, Into(vcw)} per level
   const uint32_t s_bfs = sp.alloc(2u * T * 32u, true);                    // {node, value} x 2 buffers
-  const uint32_t s_stk = sp.alloc(uint32_t(dfs > 1 ? dfs - 1 : 1) * T * 32u, false);
+  // stack level d (right sibling parked at depth d+1): levels [0, kReuse) are the breadth buffers, the rest one block
+  constexpr int kReuse = kReuseBfs ? 2 : 0;
+  const int nlev = dfs > 1 ? dfs - 1 : 1;
+  const uint32_t s_more = nlev > kReuse ? sp.alloc(uint32_t(nlev - kReuse) * T * 32u, false) : 0u;
+  auto level_addr = [&](int d) -> uint32_t {
+    return (d < kReuse ? s_bfs + uint32_t(d) * (T * 32u) : s_more + uint32_t(d - kReuse) * (T * 32u)) + uint32_t(tid) * 32u;
+  };
 
   const uint64_t upk = A.leaf_count >> A.unit_bits;
   const uint64_t total = A.nkeys * upk;
@@ -846,10 +861,16 @@ dcf_evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ Ev
       }
       __syncthreads();
     }
-    if (tid < (1 << bt)) {  // phase 2: depth-first per thread
-      const uint32_t slot = s_bfs + uint32_t(bt & 1) * (T * 32u) + 32u * tid;
-      blk cur = lds_blk(slot);
-      V u = smem_load_val<G>(P.ga, slot + 16u);
+    // phase 2: depth-first per thread
+    const uint32_t slot = s_bfs + uint32_t(bt & 1) * (T * 32u) + 32u * tid;
+    blk cur = {0u, 0u, 0u, 0u};
+    V u = GR::zero(P.ga);
+    if (tid < (1 << bt)) {
+      cur = lds_blk(slot);
+      u = smem_load_val<G>(P.ga, slot + 16u);
+    }
+    if (kReuseBfs) __syncthreads();  // every start node is in registers: the breadth buffers become stack levels 0 and 1
+    if (tid < (1 << bt)) {
       const int lvl0 = du + bt;
       const uint64_t out0 = key * A.ys_stride + (leaf0 - A.leaf_begin) + (uint64_t(tid) << dfs);
       const uint32_t pairs = 1u << (dfs - 1);
@@ -866,11 +887,11 @@ dcf_evalall_kernel(const __grid_constant__ KParams P, const __grid_constant__ Ev
           ++done;
           if (done == pairs) break;
           d = dfs - __ffs(int(done));
-          const uint32_t e = s_stk + (uint32_t(d - 1) * T + tid) * 32u;
+          const uint32_t e = level_addr(d - 1);
           cur = lds_blk(e);
           u = smem_load_val<G>(P.ga, e + 16u);
         } else {
-          const uint32_t e = s_stk + (uint32_t(d) * T + tid) * 32u;
+          const uint32_t e = level_addr(d);
           sts_blk(e, r);
           smem_store_val<G>(P.ga, e + 16u, ur);
           cur = l;

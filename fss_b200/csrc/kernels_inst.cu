@@ -111,7 +111,9 @@ evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int) { return &evala
 #elif FSS_INST_SCHEME == 1
 template <int G>
 static cudaError_t evalall_launch_dcf(const KParams &P, const EvalAllArgs &A, const LaunchCfg &c) {
-  return launch_kernel(dcf_evalall_kernel<G, kInstPrg>, c, P, A);
+  // geometry by the CTA size api.cu chose: 512 threads (default) or 256 (FSSB200_DCF_ALL_THREADS=256, A/B runs)
+  if (c.block.x == 512u) return launch_kernel(dcf_evalall_kernel<G, kInstPrg, 9>, c, P, A);
+  return launch_kernel(dcf_evalall_kernel<G, kInstPrg, 8>, c, P, A);
 }
 evalall_launch_fn CAT3(evalall_launcher_, PRGNAME, SCHNAME)(int gk) {
   switch (gk) {
