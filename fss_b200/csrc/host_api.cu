@@ -22,6 +22,7 @@
 // half).  No barriers: workers claim 512-key blocks with one fetch_add, hand-offs are per-chunk counters.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -770,7 +771,10 @@ int eval_host_pipelined(fssb200_ctx *c, int party, const void *seeds_v, const vo
     } else if (++idle < 64) {
       cpu_relax();
     } else {
-      std::this_thread::yield();
+      // nothing to submit and nothing to stage: the link or the GPU has to make progress first.  Back off instead of
+      // hammering cudaEventQuery -- in a process that drives several GPUs the submitters share the driver's locks
+      // (2 GPUs from one process: 90.9 ms per step with a spinning poll)
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
   }
   P.stop.store(true, std::memory_order_release);
