@@ -8,7 +8,14 @@
 #pragma once
 #include <atomic>
 
+#if defined(FSSB200_HOST_MOCK)
+// tests/host_emul/host_pipe_mock.cpp: the host-side logic of host_api.cu compiled for the CPU against a mock CUDA runtime
+// (worker-thread streams, events, a pinned-memory registry) -- how the lock-free pipeline is exercised, also under
+// ThreadSanitizer, in the GPU-less build container.  Never defined in the product build.
+#include "mock_cuda.h"
+#else
 #include "dispatch.h"
+#endif
 
 struct fssb200_ctx {
   fssb200_params p;
