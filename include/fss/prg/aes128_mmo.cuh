@@ -5,18 +5,27 @@
 // (lane-replicated T-tables, fss_b200/csrc/aes.cuh).  `Aes128MmoRaw` (aes128_mmo_raw.cuh:38-111) and
 // `Aes128Soft` (aes128_mmo_soft.cuh:185-218) compute the same function and map to the same kernels.
 #pragma once
-#include <array>
 #include <cstring>
-#include <span>
+#include <cuda/std/array>
+#include <cuda/std/span>
 #include <fss/b200/runtime.hpp>
 #include <fss/prg.cuh>
+
+// The reference's Aes128Mmo hands out OpenSSL cipher contexts (`cuda::std::array<EVP_CIPHER_CTX *, mul>`,
+// prg/aes128_mmo.cuh:49-70) and its users name that type (src/dpf_test.cu:167).  The shim keeps the type NAME -- the same
+// opaque declaration OpenSSL makes, so both headers can be included together -- but what CreateCtxs() returns are handles to
+// the 16-byte user keys: the cipher runs on the GPU, nothing here links libcrypto.  Only pass Aes128Mmo what its own
+// CreateCtxs() made.
+typedef struct evp_cipher_ctx_st EVP_CIPHER_CTX;
 
 namespace fss::prg {
 
 namespace b200_detail {
-struct AesKey {  // stands in for the reference's EVP_CIPHER_CTX*: one user key
+struct AesKey {  // what an `EVP_CIPHER_CTX *` of this shim points at: one user key
   uint8_t key[16];
 };
+inline EVP_CIPHER_CTX *ToHandle(AesKey *k) { return reinterpret_cast<EVP_CIPHER_CTX *>(k); }
+inline AesKey *FromHandle(EVP_CIPHER_CTX *h) { return reinterpret_cast<AesKey *>(h); }
 template <int mul>
 cuda::std::array<int4, mul> GenOnDevice(int prg_tag, const uint8_t key64[64], int4 seed) {
   fssb200_params p;
@@ -38,25 +47,23 @@ class Aes128Mmo {
 
 public:
   static constexpr int kFssB200Prg = FSSB200_PRG_AES128_MMO;
-  using Ctx = b200_detail::AesKey;
 
-  explicit Aes128Mmo(std::span<Ctx *, mul> ctxs) {
-    for (int i = 0; i < mul; ++i) std::memcpy(keys_[i], ctxs[i]->key, 16);
+  Aes128Mmo(cuda::std::span<EVP_CIPHER_CTX *, mul> ctxs) {                 // prg/aes128_mmo.cuh:40
+    for (int i = 0; i < mul; ++i) std::memcpy(keys_[i], b200_detail::FromHandle(ctxs[i])->key, 16);
   }
-  Aes128Mmo(std::array<Ctx *, mul> &ctxs) : Aes128Mmo(std::span<Ctx *, mul>(ctxs)) {}
   // prg/aes128_mmo.cuh:49-64: one context per 16-byte user key
-  static std::array<Ctx *, mul> CreateCtxs(const unsigned char *keys[mul]) {
-    std::array<Ctx *, mul> c{};
+  static cuda::std::array<EVP_CIPHER_CTX *, mul> CreateCtxs(const unsigned char *keys[mul]) {
+    cuda::std::array<EVP_CIPHER_CTX *, mul> c{};
     for (int i = 0; i < mul; ++i) {
-      c[i] = new Ctx;
-      std::memcpy(c[i]->key, keys[i], 16);
+      auto *k = new b200_detail::AesKey;
+      std::memcpy(k->key, keys[i], 16);
+      c[i] = b200_detail::ToHandle(k);
     }
     return c;
   }
-  static void FreeCtxs(std::span<Ctx *, mul> ctxs) {
-    for (auto *c : ctxs) delete c;
+  static void FreeCtxs(cuda::std::span<EVP_CIPHER_CTX *, mul> ctxs) {     // :66-70
+    for (auto *c : ctxs) delete b200_detail::FromHandle(c);
   }
-  static void FreeCtxs(std::array<Ctx *, mul> &ctxs) { FreeCtxs(std::span<Ctx *, mul>(ctxs)); }
 
   void FssB200Key(uint8_t key64[64]) const { std::memcpy(key64, keys_, 16 * mul); }
   cuda::std::array<int4, mul> Gen(int4 seed) const {
@@ -65,31 +72,7 @@ public:
     return b200_detail::GenOnDevice<mul>(kFssB200Prg, k, seed);
   }
 };
-
-// aes128_mmo_raw.cuh:76-81: constructed from `mul` 16-byte keys
-template <int mul>
-class Aes128MmoRaw {
-  uint8_t keys_[mul][16];
-
-public:
-  static constexpr int kFssB200Prg = FSSB200_PRG_AES128_MMO;
-  explicit Aes128MmoRaw(const uint8_t keys[][16]) { std::memcpy(keys_, keys, 16 * mul); }
-  void FssB200Key(uint8_t key64[64]) const { std::memcpy(key64, keys_, 16 * mul); }
-  cuda::std::array<int4, mul> Gen(int4 seed) const {
-    uint8_t k[64] = {0};
-    FssB200Key(k);
-    return b200_detail::GenOnDevice<mul>(kFssB200Prg, k, seed);
-  }
-};
-
-// aes128_mmo_soft.cuh:197-207: the table pointers of the reference constructor are accepted and ignored
-// (the tables live in the evaluator's shared memory).
-template <int mul>
-class Aes128Soft : public Aes128MmoRaw<mul> {
-public:
-  Aes128Soft(const uint8_t keys[][16], const uint32_t * /*te0*/, const uint8_t * /*sbox*/) : Aes128MmoRaw<mul>(keys) {}
-};
-
-static_assert(Prgable<Aes128Mmo<2>, 2> && Prgable<Aes128Mmo<4>, 4> && b200::DevicePrg<Aes128Mmo<1>, 1>);
 
 }  // namespace fss::prg
+
+#include <fss/prg/aes128_mmo_soft.cuh>  // Aes128MmoRaw / Aes128Soft: the same function on the same kernels

@@ -1,0 +1,34 @@
+"""The reference's OWN googletest suites (src/{dpf,dcf,half_tree_dpf,grotto_dcf,vdpf,group}_test.cu), compiled UNMODIFIED --
+but against this repository's header tree and linked with libfssb200.so (oracle/Makefile: `make reftests`, built in the
+container where the reference checkout is; the binaries travel to the GPU box under oracle/_ref/reftests/).  A user of the
+reference switches by changing one include path and one library; this is that switch applied to the reference's own
+tests: 33 group-axiom tests on the CPU, 70 scheme tests (reconstruction at / off alpha, EvalAll, Grotto edge cases, VDPF
+verification; ChaCha, Aes128Mmo and Aes128Soft PRGs; Bytes / Uint64 / Uint127 groups; in_bits = 1) on the B200."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "reftests")
+
+
+def run(name):
+    exe = os.path.join(BIN, name + "_test")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs the reference checkout: make -C oracle reftests)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    m = re.search(r"\[  PASSED  \] (\d+) tests", r.stdout)
+    assert r.returncode == 0 and m and "FAILED" not in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+    return int(m.group(1))
+
+
+def test_reference_group_axioms_on_the_shim_groups():
+    assert run("group") >= 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,at_least", [("dpf", 10), ("dcf", 7), ("half_tree_dpf", 27), ("grotto_dcf", 5), ("vdpf", 8)])
+def test_reference_gtest_suite_passes_against_this_library(name, at_least):
+    assert run(name) >= at_least

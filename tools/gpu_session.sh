@@ -18,7 +18,7 @@ for step in "$@"; do
     host)
       { lscpu; echo; numactl -H 2>/dev/null || cat /sys/devices/system/node/node*/cpulist; echo; nvidia-smi topo -m; echo; free -g; nproc; } > gpurun_out/host.txt 2>&1 ;;
     newtests)
-      ( timeout 1200 python -m pytest tests/test_host_pipeline.py tests/test_multi.py tests/test_plugins.py -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_new.log
+      ( timeout 1200 python -m pytest tests/test_host_pipeline.py tests/test_multi.py tests/test_plugins.py tests/test_ref_gtests.py -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_new.log
       tail -5 gpurun_out/pytest_new.log ;;
     tests)
       ( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_gpu.log
