@@ -12,8 +12,8 @@
 namespace fss::prg {
 
 namespace aes_detail {
-constexpr uint8_t XTime(uint8_t a) { return static_cast<uint8_t>((a << 1) ^ ((a & 0x80) ? 0x1b : 0)); }
-constexpr uint8_t GfMul(uint8_t a, uint8_t b) {
+FSS_SHIM_HD constexpr uint8_t XTime(uint8_t a) { return static_cast<uint8_t>((a << 1) ^ ((a & 0x80) ? 0x1b : 0)); }
+FSS_SHIM_HD constexpr uint8_t GfMul(uint8_t a, uint8_t b) {
   uint8_t r = 0;
   for (int i = 0; i < 8; ++i) {
     if (b & 1) r ^= a;
