@@ -10,6 +10,7 @@
 #   launches  ncu launch list of the bench command               -> gpurun_out/launches.csv
 #   ncu       ncu --set full of the kernels in $NCU_KERNELS      -> gpurun_out/prof_<name>.ncu-rep
 #   host      lscpu / numactl / nvidia-smi topo of the box       -> gpurun_out/host.txt
+#   fuzz      tests/test_gpu_fuzz.py with $FUZZ_CASES cases (default 1500) and seed $FUZZ_SEED  -> gpurun_out/fuzz.log
 #   sanitize  compute-sanitizer ($SAN_TOOLS) over tools/sanitize_cases.py ($SAN_CASES) -> gpurun_out/sanitize_<tool>.log
 set -u
 mkdir -p gpurun_out
@@ -43,6 +44,9 @@ for step in "$@"; do
           -f -o gpurun_out/prof_$k python tools/prof_one.py $k > gpurun_out/prof_$k.log 2>&1
         echo "ncu $k rc=$?"
       done ;;
+    fuzz)
+      ( FSSB200_FUZZ_CASES=${FUZZ_CASES:-1500} FSSB200_FUZZ_SEED=${FUZZ_SEED:-7} timeout ${FUZZ_TIMEOUT:-1200} python -m pytest tests/test_gpu_fuzz.py -m gpu -x -q 2>&1 | tail -40 ) > gpurun_out/fuzz.log
+      tail -6 gpurun_out/fuzz.log ;;
     sanitize)
       for tool in ${SAN_TOOLS:-memcheck racecheck}; do
         timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_cases.py ${SAN_CASES:-walk pipeline packed} \
