@@ -302,16 +302,21 @@ class Context:
         return ys
 
     # ---- level-major layout (point_eval_gpu.cuh:324-492) ----------------------------------------------------------
-    def relayout(self, cws: torch.Tensor):
+    def relayout(self, cws: torch.Tensor, out=None):
+        """Key-major Cw[N][ncw] -> the level-major arrays (cw_s, cw_v, extra, out_cw); ``out`` reuses a previous result."""
         cws = cws.contiguous()
         self._need_cuda("relayout", cws)
         n, nb = cws.shape[0], self.in_bits
         _, dev = self._dev(cws)
         d = cws.device
-        cw_s = torch.empty((nb, n, 4), dtype=torch.int32, device=d)
-        cw_v = torch.empty((nb, n, 4), dtype=torch.int32, device=d) if self.scheme == "dcf" else None
-        extra = torch.zeros(((nb + 31) // 32, n), dtype=torch.int32, device=d) if self.scheme != "dcf" else None
-        out_cw = torch.empty((n, 4), dtype=torch.int32, device=d) if self.scheme not in ("halftree", "vdpf") else None
+        if out is not None:
+            cw_s, cw_v, extra, out_cw = out
+            self._check_out(cw_s, (nb, n, 4), torch.int32, d)
+        else:
+            cw_s = torch.empty((nb, n, 4), dtype=torch.int32, device=d)
+            cw_v = torch.empty((nb, n, 4), dtype=torch.int32, device=d) if self.scheme == "dcf" else None
+            extra = torch.empty(((nb + 31) // 32, n), dtype=torch.int32, device=d) if self.scheme != "dcf" else None
+            out_cw = torch.empty((n, 4), dtype=torch.int32, device=d) if self.scheme not in ("halftree", "vdpf") else None
         with torch.cuda.device(dev):
             L.check(L.lib.fssb200_relayout(self.handle(dev), _ptr(cws), _ptr(cw_s), _ptr(cw_v), _ptr(extra),
                                            _ptr(out_cw), n, self._stream(dev)), "fssb200_relayout")

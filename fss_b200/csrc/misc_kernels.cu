@@ -10,64 +10,107 @@
 namespace fssb200 {
 
 // ---- relayout (point_eval_gpu.cuh:39-91) ------------------------------------------------------------------
-// Key-major Cw[nkeys][ncw] -> level-major arrays.  One warp per tile of 32 consecutive keys: the tile is read in
-// chunks of 4 levels -- lane = (key-in-group r, 16-byte piece q), 8 adjacent lanes read the 128 contiguous bytes of
-// one key -- into a padded shared-memory slab, then written level by level with lane = key, so every store
-// instruction covers 512 contiguous bytes of cw_s[level] / cw_v[level] (the first version stored 16 bytes per key
-// per level from different warps: half-sector writes, 2.2 TB/s).  The control bits are packed per key into `extra`.
+// Key-major Cw[nkeys][ncw] -> level-major arrays: an HBM-bound transpose (ncw * 32 bytes read, ~ncw * 16 written per key).
+// One CTA per SM, 8 warps, every warp on its own tiles of 32 consecutive keys.  A tile crosses in chunks of <= 8 levels:
+// every lane asks the copy engine for ITS key's chunk (`cp.async.bulk`, 224-256 contiguous bytes) into a padded
+// shared-memory row, three chunks ahead per warp (~180 KB of reads in flight per SM: the first version loaded through
+// registers, one chunk at a time, and was latency-bound at 0.45 of the HBM peak, profiles/r02_relayout.md).  The chunk
+// is then written level by level with lane = key, so every store instruction covers 512 contiguous bytes of
+// cw_s[level] / cw_v[level].  Row stride = (2 L + 1) * 16 bytes: the lane = key reads are conflict-free.  The control
+// bits are packed per key into `extra`.
 constexpr int kRlWarps = 8;
-constexpr int kRlLevels = 4;                                  // levels per chunk
-constexpr uint32_t kRlRow = kRlLevels * 32u + 16u;            // slab row stride per key (bytes): conflict-free both ways
-__global__ void __launch_bounds__(kRlWarps * 32) relayout_kernel(int scheme, int n, int ncw,
+constexpr int kRlLevels = 8;                                  // levels per chunk (at most)
+constexpr int kRlStages = 3;                                  // chunks in flight per warp
+constexpr uint32_t kRlRow = kRlLevels * 32u + 16u;            // shared-memory row stride per key (bytes)
+constexpr uint32_t kRlStage = 32u * kRlRow;
+constexpr uint32_t kRlBarBytes = 256u;                        // kRlWarps * kRlStages mbarriers
+constexpr uint32_t kRlSmem = kRlBarBytes + kRlWarps * kRlStages * kRlStage;
+static_assert(kRlWarps * kRlStages * 8 <= kRlBarBytes);
+
+__global__ void __launch_bounds__(kRlWarps * 32, 1) relayout_kernel(int scheme, int n, int ncw,
     const uint8_t *__restrict__ cws, blk *__restrict__ cw_s, blk *__restrict__ cw_v, uint32_t *__restrict__ extra,
     blk *__restrict__ out_cw, uint64_t nkeys) {
-  __shared__ __align__(16) uint8_t slab_all[kRlWarps][32 * kRlRow];
+  extern __shared__ __align__(128) uint8_t rl_smem[];
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  uint8_t *slab = slab_all[wid];
+  const uint32_t smem0 = uint32_t(__cvta_generic_to_shared(rl_smem));
+  const uint32_t bar0 = smem0 + wid * kRlStages * 8u;
+  const uint32_t buf0 = smem0 + kRlBarBytes + wid * kRlStages * kRlStage;
+  const uint8_t *bufg = rl_smem + kRlBarBytes + wid * kRlStages * kRlStage;
   const uint64_t ntiles = (nkeys + 31) >> 5;
   const bool dcf = scheme == FSSB200_SCHEME_DCF;
   const bool has_out = scheme != FSSB200_SCHEME_HALFTREE && scheme != FSSB200_SCHEME_VDPF && out_cw;
   const uint32_t key_bytes = uint32_t(ncw) * 32u;
-  for (uint64_t tile = uint64_t(blockIdx.x) * kRlWarps + wid; tile < ntiles; tile += uint64_t(gridDim.x) * kRlWarps) {
-    const uint64_t k0 = tile * 32, k = k0 + lane;
+  const uint32_t nchunks = uint32_t(ncw + kRlLevels - 1) / kRlLevels;
+  const uint64_t tile0 = uint64_t(blockIdx.x) * kRlWarps + wid, tstep = uint64_t(gridDim.x) * kRlWarps;
+  if (tile0 >= ntiles) return;
+  const uint64_t my_tiles = (ntiles - tile0 + tstep - 1) / tstep, items = my_tiles * nchunks;
+
+  if (lane == 0) {
+    for (int s = 0; s < kRlStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  // item q = chunk (q % nchunks) of this warp's (q / nchunks)-th tile; levels [lo, hi) split evenly over the chunks
+  auto request = [&](uint64_t q) {
+    const uint64_t t = tile0 + (q / nchunks) * tstep;
+    const uint32_t c = uint32_t(q % nchunks), s = uint32_t(q % kRlStages);
+    const uint32_t lo = c * uint32_t(ncw) / nchunks, hi = (c + 1u) * uint32_t(ncw) / nchunks, bytes = (hi - lo) * 32u;
+    const uint64_t k0 = t * 32;
     const uint32_t nvalid = nkeys - k0 < 32 ? uint32_t(nkeys - k0) : 32u;
-    uint32_t bits = 0;
-    for (int base = 0; base < ncw; base += kRlLevels) {
-      const uint32_t chunk_bytes = uint32_t(ncw - base < kRlLevels ? ncw - base : kRlLevels) * 32u;
-      __syncwarp();
-      // load: 2 * kRlLevels lanes per key, 32 / (2 * kRlLevels) keys per step
-      constexpr uint32_t kLpk = 2u * kRlLevels;
-      const uint32_t q = lane % kLpk;
-#pragma unroll 4
-      for (uint32_t r = lane / kLpk; r < 32u; r += 32u / kLpk) {
-        if (r < nvalid && q * 16u < chunk_bytes) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(cws + (k0 + r) * key_bytes + uint32_t(base) * 32u) + q);
-          *reinterpret_cast<uint4 *>(slab + r * kRlRow + q * 16u) = v;
-        }
-      }
-      __syncwarp();
-      if (lane < nvalid) {
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(bytes * nvalid) : "memory");
+    __syncwarp();
+    if (lane < nvalid)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       buf0 + s * kRlStage + lane * kRlRow),
+                   "l"(cws + (k0 + lane) * key_bytes + lo * 32u), "r"(bytes), "r"(bar0 + 8u * s)
+                   : "memory");
+  };
+  for (uint64_t q = 0; q < kRlStages && q < items; ++q) request(q);
+
+  uint32_t bits = 0;
+  for (uint64_t q = 0; q < items; ++q) {
+    const uint64_t t = tile0 + (q / nchunks) * tstep;
+    const uint32_t c = uint32_t(q % nchunks), s = uint32_t(q % kRlStages), parity = uint32_t(q / kRlStages) & 1u;
+    const uint32_t lo = c * uint32_t(ncw) / nchunks, hi = (c + 1u) * uint32_t(ncw) / nchunks;
+    const uint64_t k0 = t * 32, k = k0 + lane;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FSS_RL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra FSS_RL_WAIT;\n"
+        "}\n" ::"r"(bar0 + 8u * s),
+        "r"(parity)
+        : "memory");
+    if (k < nkeys) {
+      const uint8_t *row = bufg + s * kRlStage + lane * kRlRow;
 #pragma unroll
-        for (int j = 0; j < kRlLevels; ++j) {
-          const int i = base + j;
-          if (i >= ncw) break;
-          const uint4 s = *reinterpret_cast<const uint4 *>(slab + lane * kRlRow + j * 32);
-          const uint4 v = *reinterpret_cast<const uint4 *>(slab + lane * kRlRow + j * 32 + 16);
-          if (i < n) {
-            reinterpret_cast<uint4 *>(cw_s)[uint64_t(i) * nkeys + k] = s;
-            if (dcf) reinterpret_cast<uint4 *>(cw_v)[uint64_t(i) * nkeys + k] = v;
+      for (uint32_t j = 0; j < uint32_t(kRlLevels); ++j) {
+        const uint32_t i = lo + j;
+        if (i >= hi) break;
+        const uint4 sblk = *reinterpret_cast<const uint4 *>(row + j * 32u);
+        if (i < uint32_t(n)) {
+          __stcs(reinterpret_cast<uint4 *>(cw_s) + uint64_t(i) * nkeys + k, sblk);
+          if (dcf) {
+            __stcs(reinterpret_cast<uint4 *>(cw_v) + uint64_t(i) * nkeys + k, *reinterpret_cast<const uint4 *>(row + j * 32u + 16u));
+          } else {
             // Dpf::Cw::tr / HalfTreeDpf::Cw::extra (bool at byte 16)
-            bits |= uint32_t((v.x & 0xffu) != 0) << (i & 31);
-            if (!dcf && ((i & 31) == 31 || i == n - 1)) {
+            bits |= uint32_t(row[j * 32u + 16u] != 0) << (i & 31u);
+            if ((i & 31u) == 31u || i == uint32_t(n) - 1u) {
               extra[uint64_t(i >> 5) * nkeys + k] = bits;
               bits = 0;
             }
-          } else if (has_out) {  // i == n: output correction word
-            reinterpret_cast<uint4 *>(out_cw)[k] = dcf ? v : s;
           }
+        } else if (has_out) {  // i == n: output correction word
+          reinterpret_cast<uint4 *>(out_cw)[k] = dcf ? *reinterpret_cast<const uint4 *>(row + j * 32u + 16u) : sblk;
         }
       }
     }
+    __syncwarp();  // every lane has read stage s
+    if (q + kRlStages < items) request(q + kRlStages);
   }
 }
 
@@ -76,10 +119,13 @@ cudaError_t launch_relayout(int scheme, int in_bits, int ncw, const uint8_t *cws
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const cudaError_t attr =
+      cudaFuncSetAttribute(relayout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRlSmem));
+  if (attr != cudaSuccess) return attr;
   const uint64_t ntiles = (nkeys + 31) >> 5;
-  const uint64_t want = (ntiles + kRlWarps - 1) / kRlWarps, cap = uint64_t(sms) * 8;
+  const uint64_t want = (ntiles + kRlWarps - 1) / kRlWarps, cap = uint64_t(sms);
   const unsigned blocks = unsigned(want < cap ? (want ? want : 1) : cap);
-  relayout_kernel<<<blocks, kRlWarps * 32, 0, stream>>>(scheme, in_bits, ncw, cws, cw_s, cw_v, extra, out_cw, nkeys);
+  relayout_kernel<<<blocks, kRlWarps * 32, kRlSmem, stream>>>(scheme, in_bits, ncw, cws, cw_s, cw_v, extra, out_cw, nkeys);
   return cudaGetLastError();
 }
 

@@ -1,6 +1,6 @@
 """One small workload per invocation, for `ncu -k regex:<kernel> -s 2 -c 1` captures (profiles/).
 
-  python tools/prof_one.py evalall_dpf|evalall_ht|evalall_dcf|gen_dcf|gen_dpf|grotto|c2|c3|ht|packed|vdpf|walk
+  python tools/prof_one.py evalall_dpf|evalall_ht|evalall_dcf|gen_dcf|gen_dpf|grotto|c2|c3|ht|packed|vdpf|walk|relayout
 """
 import os
 import sys
@@ -28,7 +28,12 @@ def main():
         alphas = torch.randint(0, 1 << min(n, 62), (k,), dtype=torch.int64, device=dev, generator=g)
         return s0s, alphas, betas
 
-    if which in ("c2", "c3", "ht", "packed", "vdpf", "walk"):
+    if which == "relayout":
+        ctx = fss_b200.Context("dpf", 32, "bytes", prg="aes128_mmo")
+        cws = rnd((1 << 22, 33, 8))
+        for _ in range(4):
+            ctx.relayout(cws)
+    elif which in ("c2", "c3", "ht", "packed", "vdpf", "walk"):
         scheme, n, k, group = {"c2": ("dpf", 32, 1 << 22, "bytes"), "c3": ("dcf", 64, 1 << 21, "u128"),
                                "ht": ("halftree", 32, 1 << 20, "bytes"), "packed": ("dpf", 32, 1 << 21, "bytes"),
                                "vdpf": ("vdpf", 32, 1 << 20, "bytes"), "walk": ("grotto", 32, 1 << 20, "bytes")}[which]
