@@ -830,7 +830,33 @@ def run_own_arm(args) -> None:
                                  "keys_per_gpu": k7, "lsu_roofline_frac_aes_only": lsu_frac(k7, 32, msk7),
                                  "note": "n AES blocks for the walk + 2 Blake3 compressions per evaluation; includes the "
                                          "torch.empty of the outputs"}
-        del s0s, betas, vcws, vcs, vocws, seeds0, seeds1, vbox
+        # Vdpf::Gen on the same batch, and Vdpf::EvalAll (n = 16): the proof of a key chains its 2^n leaf hashes IN ORDER
+        # (vdpf.cuh:313-341), so a key is one sequential Blake3 chain and only keys run in parallel
+        msg7, mskg7 = timed(lambda: c7.vdpf_gen(s0s, alphas, betas), x_steps, x_warm)
+        extra["gen_vdpf_n32"] = {"value": world * k7 / (msg7 * 1e-3), "unit": "keys/s", "ms_per_step": msg7, "keys_per_gpu": k7,
+                                 "note": "4 AES blocks per level and key + the two parties' leaf hashes (4 Blake3 compressions)"}
+        del vcws, vcs, vocws, vbox
+        c8 = fss_b200.Context("vdpf", 16, "bytes", prg="aes128_mmo")
+        k8 = 2048
+        a8 = alphas[:k8] & 0xFFFF
+        v8 = c8.vdpf_gen(s0s[:k8], a8, betas[:k8])
+        abox = {}
+        ms8, msk8 = timed(lambda: abox.__setitem__("r", c8.vdpf_eval_all(0, seeds0[:k8], v8[0], v8[1], v8[2])), max(2, x_steps // 4), 2)
+        ya0, pa0 = abox["r"]
+        ya1, pa1 = c8.vdpf_eval_all(1, seeds1[:k8], v8[0], v8[1], v8[2])
+        ok8 = v8[3] == 0
+        rec = (ya0 ^ ya1)[ok8]
+        a8l = a8[ok8].to(torch.int64) & 0xFFFF
+        idx = torch.arange(rec.shape[0], device=dev)
+        if not torch.equal(pa0[ok8], pa1[ok8]) or not torch.equal(rec[idx, a8l], betas[:k8][ok8]) or \
+                int((rec != 0).any(dim=2).sum()) != int((betas[:k8][ok8] != 0).any(dim=1).sum()):
+            raise SystemExit("bench: VDPF EvalAll reconstruction / proof equality failed on the timed batch")
+        if chk:
+            chk.done.append(f"vdpf evalall n=16: both parties' proofs equal and shares reconstruct the point function ({int(ok8.sum())} keys)")
+        extra["vdpf_evalall_n16"] = {"value": world * k8 * 65536 / (ms8 * 1e-3), "unit": "leaves/s", "ms_per_step": ms8, "keys_per_gpu": k8,
+                                     "note": "tree + 2 Blake3 compressions per leaf in parallel, then one sequential hash chain of "
+                                             "2^16 links per key (a warp per key): latency-bound by the chain's definition"}
+        del s0s, betas, seeds0, seeds1, abox, ya0, ya1, v8
         torch.cuda.empty_cache()
         sampler.stop()
 
@@ -930,17 +956,32 @@ def run_single_process(args) -> None:
         h_cws = torch.cat([t.cpu() for t in cws]).pin_memory()
         h_xs = torch.cat([t.cpu() for t in xs]).pin_memory()
         h_ys = torch.empty((ndev * nkeys, 4), dtype=torch.int32).pin_memory()
-        for _ in range(2):
-            mc.eval_host(0, h_seeds, h_cws, h_xs, out=h_ys)
-        t0 = time.perf_counter()
+        want_ys = torch.cat([t.cpu() for t in ys])
         e_steps = 3
-        for _ in range(e_steps):
-            mc.eval_host(0, h_seeds, h_cws, h_xs, out=h_ys)
-        dt = (time.perf_counter() - t0) / e_steps
-        if not torch.equal(h_ys, torch.cat([t.cpu() for t in ys])):
-            raise SystemExit("bench: fssb200_eval_host_multi disagrees with the device path")
+
+        def host_leg():
+            for _ in range(2):
+                mc.eval_host(0, h_seeds, h_cws, h_xs, out=h_ys)
+            h_ys.zero_()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                mc.eval_host(0, h_seeds, h_cws, h_xs, out=h_ys)
+            dt = (time.perf_counter() - t0) / e_steps
+            if not torch.equal(h_ys, want_ys):
+                raise SystemExit("bench: fssb200_eval_host_multi disagrees with the device path")
+            return dt
+
+        dt = host_leg()                                  # the library's choice (balanced blocks from 3 devices on)
+        os.environ["FSSB200_MULTI_BALANCE"] = "0"
+        dt_static = host_leg()                           # equal contiguous ranges per device (= what N processes do)
+        del os.environ["FSSB200_MULTI_BALANCE"]
         e2e = {"value": ndev * nkeys / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e_steps,
-               "api": "fssb200_eval_host_multi: one process, one host thread per GPU, host arrays of the whole batch"}
+               "h2d_bytes_per_step": ndev * nkeys * (33 * 32 + 16 + 4), "d2h_bytes_per_step": ndev * nkeys * 16,
+               "h2d_gbs": ndev * nkeys * (33 * 32 + 16 + 4) / dt / 1e9,
+               "static_split": {"value": ndev * nkeys / dt_static, "ms_per_step": dt_static * 1e3,
+                                "note": "FSSB200_MULTI_BALANCE=0: device d takes key_shard(d); lasts as long as the slowest link"},
+               "api": "fssb200_eval_host_multi: one process, host arrays of the whole batch; from 3 devices on the devices "
+                      "claim key blocks from one counter (two calls in flight per device)"}
     line = {
         "metric": METRIC, "value": ndev * nkeys / (ms_step * 1e-3), "unit": UNIT, "n_gpus": ndev, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_ms, "higher_is_better": True,

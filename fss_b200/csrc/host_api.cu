@@ -1178,9 +1178,14 @@ int fssb200_eval_all_host(fssb200_ctx *c, int party, const void *seeds, const vo
 }
 
 // ---- one process, several GPUs: host arrays of the WHOLE batch -------------------------------------------------------
-// Keys are independent (dpf.cuh:170-214), so device d takes the contiguous key range [d*K/ndev .., (d+1)*K/ndev) of
-// the caller's arrays; one host thread per device runs the pipeline above on its range with its share of the worker
-// threads.  No collective, no peer traffic.
+// Keys are independent (dpf.cuh:170-214); no collective, no peer traffic.  Two ways to spread them:
+//  * static: device d takes the contiguous range key_shard(nkeys, d, ndev); one host thread per device runs the
+//    pipeline above on its range with its share of the worker threads (1-2 devices: links independent, packing pays);
+//  * balanced: when the keys cross in the reference layout (>= 3 devices share the host, or host mode 1) the LINKS
+//    differ -- 22.8 ... 34.4 GB/s at 8 GPUs, the host memory system arbitrates -- and an equal split lasts as long as
+//    the slowest link needs.  Devices then claim blocks of keys from one counter (two calls in flight per device so a
+//    link never waits for a call to drain; blocks shrink towards the end of the batch), and the batch finishes when
+//    the host memory system has served all of it: profiles/r02_host_pipeline.md.
 int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const void *seeds, const void *cws,
     const void *ocws, const void *xs, void *ys, size_t nkeys, int *rcs) {
   if (!ctxs || ndev < 1 || ndev > 64) return FSSB200_EINVAL;
@@ -1194,29 +1199,79 @@ int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const
   if (!seeds || !cws || !xs || !ys) return FSSB200_EINVAL;
   const size_t cwb = size_t(ctxs[0]->ncw) * 32, ib = size_t(ctxs[0]->p.in_bytes);
   Crew *crew = Crew::get();
-  const int share = crew ? std::max(1, crew->workers() / ndev) : 0;
   std::vector<int> rc(size_t(ndev), 0);
   std::vector<std::thread> th;
-  const size_t base = nkeys / size_t(ndev), rem = nkeys % size_t(ndev);
-  auto run = [&](int d) {
-    const size_t k0 = size_t(d) * base + std::min<size_t>(size_t(d), rem), k = base + (size_t(d) < rem ? 1 : 0);
-    t_crew_share = share;
-    t_devices_sharing_host = ndev;
-    rc[size_t(d)] = fssb200_eval_host(ctxs[d], party, static_cast<const uint8_t *>(seeds) + k0 * 16,
+  auto call = [&](int d, size_t k0, size_t k) {
+    return fssb200_eval_host(ctxs[d], party, static_cast<const uint8_t *>(seeds) + k0 * 16,
         static_cast<const uint8_t *>(cws) + k0 * cwb, ocws ? static_cast<const uint8_t *>(ocws) + k0 * 16 : nullptr,
         static_cast<const uint8_t *>(xs) + k0 * ib, static_cast<uint8_t *>(ys) + k0 * 16, k);
-    t_crew_share = 0;
-    t_devices_sharing_host = 1;
   };
-  for (int d = 1; d < ndev; ++d) th.emplace_back(run, d);
-  run(0);
-  for (auto &t : th) t.join();
-  int first = 0;
+  const int mode0 = ctxs[0]->host_mode.load(std::memory_order_relaxed);
+  const size_t min_block = size_t(1) << std::min(24, std::max(8, env_int("FSSB200_MULTI_MIN_BLOCK_BITS", 15)));
+  const size_t max_block = std::max(min_block, size_t(1) << std::min(28, std::max(8, env_int("FSSB200_MULTI_MAX_BLOCK_BITS", 17))));
+  const bool balanced = ndev >= 2 && (mode0 == 1 || (mode0 == 0 && ndev >= 3)) && nkeys >= 2 * min_block * size_t(ndev) &&
+      env_int("FSSB200_MULTI_BALANCE", 1) != 0;
+  if (balanced) {
+    std::mutex mu;
+    size_t next = 0;
+    auto claim = [&](size_t *k0, size_t *k) {
+      std::lock_guard<std::mutex> l(mu);
+      if (next >= nkeys) return false;
+      const size_t left = nkeys - next;
+      size_t b = left / (size_t(4) * size_t(ndev));        // guided: large blocks first, small ones to even out the end
+      b = std::min(max_block, std::max(min_block, b)) & ~size_t(255);
+      if (left - std::min(left, b) < min_block / 2) b = left;  // no crumbs
+      b = std::min(b, left);
+      *k0 = next;
+      *k = b;
+      next += b;
+      return true;
+    };
+    std::vector<std::atomic<int>> first(static_cast<size_t>(ndev));
+    for (auto &f : first) f.store(0);
+    auto run = [&](int d) {
+      t_crew_share = crew ? std::max(1, crew->workers() / (2 * ndev)) : 0;
+      t_devices_sharing_host = ndev;
+      size_t k0, k;
+      while (first[size_t(d)].load(std::memory_order_relaxed) == 0 && claim(&k0, &k)) {
+        const int r = call(d, k0, k);
+        int zero = 0;
+        if (r) first[size_t(d)].compare_exchange_strong(zero, r);
+        if (r) {  // the block still has to be evaluated for the batch to be complete: report, do not hide
+          std::lock_guard<std::mutex> l(mu);
+          next = nkeys;  // stop handing out blocks; the call fails as a whole
+        }
+      }
+      t_crew_share = 0;
+      t_devices_sharing_host = 1;
+    };
+    for (int d = 0; d < ndev; ++d)
+      for (int j = 0; j < 2; ++j)
+        if (d || j) th.emplace_back(run, d);
+    run(0);
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; ++d) rc[size_t(d)] = first[size_t(d)].load();
+  } else {
+    const int share = crew ? std::max(1, crew->workers() / ndev) : 0;
+    const size_t base = nkeys / size_t(ndev), rem = nkeys % size_t(ndev);
+    auto run = [&](int d) {
+      const size_t k0 = size_t(d) * base + std::min<size_t>(size_t(d), rem), k = base + (size_t(d) < rem ? 1 : 0);
+      t_crew_share = share;
+      t_devices_sharing_host = ndev;
+      rc[size_t(d)] = call(d, k0, k);
+      t_crew_share = 0;
+      t_devices_sharing_host = 1;
+    };
+    for (int d = 1; d < ndev; ++d) th.emplace_back(run, d);
+    run(0);
+    for (auto &t : th) t.join();
+  }
+  int first_rc = 0;
   for (int d = 0; d < ndev; ++d) {
     if (rcs) rcs[d] = rc[size_t(d)];
-    if (!first && rc[size_t(d)]) first = rc[size_t(d)];
+    if (!first_rc && rc[size_t(d)]) first_rc = rc[size_t(d)];
   }
-  return first;
+  return first_rc;
 }
 
 }  // extern "C"

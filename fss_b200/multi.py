@@ -42,6 +42,14 @@ class MultiContext:
         for c in self.ctxs:
             c.close()
 
+    def set_host_mode(self, mode: int) -> None:
+        """fssb200_ctx_set_host_mode on every device's context (eval_host)."""
+        for c, d in zip(self.ctxs, self.devices):
+            c.set_host_mode(mode, d)
+
+    def launch_count(self) -> int:
+        return sum(c.launch_count(d) for c, d in zip(self.ctxs, self.devices))
+
     # ---- helpers ---------------------------------------------------------------------------------------------
     def _ptrs(self, ts: Optional[Sequence[Optional[torch.Tensor]]]):
         if ts is None:
@@ -131,7 +139,9 @@ class MultiContext:
     # ---- host tensors of the whole batch ------------------------------------------------------------------------------
     def eval_host(self, party: int, seeds: torch.Tensor, cws: torch.Tensor, xs: IntLike,
                   ocws: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """fssb200_eval_host_multi: CPU tensors of the whole batch; device d evaluates key_shard(N, d, ndev)."""
+        """fssb200_eval_host_multi: CPU tensors of the whole batch.  Device d evaluates key_shard(N, d, ndev), or -- when
+        the keys cross in the reference layout (>= 3 devices, or host mode 1) -- the devices claim key blocks from one
+        counter so that unequal links finish together."""
         if seeds.device.type != "cpu":
             raise RuntimeError("eval_host takes CPU tensors")
         seeds, cws = seeds.contiguous(), cws.contiguous()

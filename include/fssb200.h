@@ -378,10 +378,16 @@ int fssb200_gen_multi(const fssb200_ctx *const *ctxs, int ndev, const void *cons
 int fssb200_multi_sync(const fssb200_ctx *const *ctxs, int ndev, void *const *streams, int *rcs);
 int fssb200_key_shard(size_t nkeys, int d, int n, size_t *begin, size_t *end);
 int fssb200_leaf_shard(const fssb200_ctx *ctx, int d, int n, uint64_t *begin, uint64_t *count);
-/* Host arrays of the WHOLE batch, evaluated on ndev GPUs: device d takes key range
- * fssb200_key_shard(nkeys, d, ndev) of the caller's arrays; one host thread per device runs the
- * fssb200_eval_host pipeline on its range with its share of the worker threads.  Returns when ys
- * is complete. */
+/* Host arrays of the WHOLE batch, evaluated on ndev GPUs.  Returns when ys is complete.
+ *  - 1-2 devices (host modes 0 / 2 / 3): device d takes key range fssb200_key_shard(nkeys, d, ndev);
+ *    one host thread per device runs the fssb200_eval_host pipeline on its range with its share of
+ *    the worker threads.
+ *  - from 3 devices on, or in host mode 1 (keys cross in the reference layout): the links of one
+ *    host are not equally fast (22.8 ... 34.4 GB/s at 8 GPUs), so the devices CLAIM key blocks
+ *    (2^15 ... 2^17 keys, shrinking towards the end) from one counter, two calls in flight per
+ *    device; which device evaluates a key is not fixed.  8 GPUs: 167.5 ms per 8 x 2^22 keys against
+ *    205.0 ms for the equal split (FSSB200_MULTI_BALANCE=0 keeps the equal split).
+ * rcs[d] (may be NULL) = the first error device d saw; the return value = the first non-zero one. */
 int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const void *seeds,
                             const void *cws, const void *ocws, const void *xs, void *ys, size_t nkeys,
                             int *rcs);

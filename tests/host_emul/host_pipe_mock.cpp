@@ -220,6 +220,38 @@ int main(int argc, char **argv) {
     mockcuda::unregister_pinned(b_dpf.cws.data());
     mockcuda::unregister_pinned(b_dpf.xs.data());
   }
+  // the same with blocks small enough for the BALANCED split (devices claim key blocks from one counter, two calls in
+  // flight per device), with and without an injected launch error
+  setenv("FSSB200_MULTI_MIN_BLOCK_BITS", "10", 1);
+  setenv("FSSB200_MULTI_MAX_BLOCK_BITS", "13", 1);
+  for (int fail : {-1, 5}) {
+    const int ndev = 3;
+    std::vector<fssb200_ctx *> cs;
+    for (int d = 0; d < ndev; ++d) cs.push_back(MakeCtx(FSSB200_SCHEME_DPF, 32, 4));
+    std::vector<uint8_t> ys(16 * b_dpf.n);
+    mockcuda::register_pinned(b_dpf.seeds.data(), b_dpf.seeds.size());
+    mockcuda::register_pinned(b_dpf.cws.data(), b_dpf.cws.size());
+    mockcuda::register_pinned(b_dpf.xs.data(), b_dpf.xs.size());
+    std::vector<int> rcs(size_t(ndev), -1);
+    const long launches0 = g_kernel_launches.load();
+    g_fail_after.store(fail);
+    const int rc = fssb200_eval_host_multi(cs.data(), ndev, 1, b_dpf.seeds.data(), b_dpf.cws.data(), nullptr, b_dpf.xs.data(), ys.data(),
+                                           b_dpf.n, rcs.data());
+    g_fail_after.store(-1);
+    if (fail < 0) {
+      CHECK(rc == 0 && std::memcmp(ys.data(), b_dpf.want.data(), ys.size()) == 0, "balanced eval_host_multi rc=%d", rc);
+      CHECK(g_kernel_launches.load() - launches0 >= 6, "balanced split did not split: %ld launches", g_kernel_launches.load() - launches0);
+    } else {
+      int bad = 0;
+      for (int d = 0; d < ndev; ++d) bad += rcs[size_t(d)] == 700;
+      CHECK(rc == 700 && bad >= 1, "balanced: injected launch error not reported: rc = %d", rc);
+    }
+    mockcuda::unregister_pinned(b_dpf.seeds.data());
+    mockcuda::unregister_pinned(b_dpf.cws.data());
+    mockcuda::unregister_pinned(b_dpf.xs.data());
+  }
+  unsetenv("FSSB200_MULTI_MIN_BLOCK_BITS");
+  unsetenv("FSSB200_MULTI_MAX_BLOCK_BITS");
   // error path: the 2nd launch of a call fails -> the call returns the error, nothing stays in flight, the next call is fine
   for (int mode : {0, 1, 2}) {
     mockcuda::register_pinned(b_dpf.seeds.data(), b_dpf.seeds.size());

@@ -88,3 +88,31 @@ def test_eval_all_subtree_shards_equal_the_full_domain(orc):
     got = np.concatenate([y.cpu().numpy().view(np.uint32) for y in ys], axis=1)
     assert np.array_equal(got, want)
     mc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [True, False])
+def test_eval_host_multi_balanced_split(orc, monkeypatch, pinned):
+    """fssb200_eval_host_multi in host mode 1 (or with >= 3 devices): devices claim key blocks from one counter, two calls
+    in flight per device (small blocks here so that a test-sized batch is split many times)."""
+    from fss_b200.multi import MultiContext
+    monkeypatch.setenv("FSSB200_MULTI_MIN_BLOCK_BITS", "12")
+    monkeypatch.setenv("FSSB200_MULTI_MAX_BLOCK_BITS", "14")
+    ndev = min(max(torch.cuda.device_count(), 2), 4)
+    devs = [d % torch.cuda.device_count() for d in range(ndev)]
+    p = Params(scheme="dpf", in_bits=32)
+    nkeys = 70001
+    s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=4)
+    oc = orc.gen(p, s0s, alphas, betas, threads=8)
+    want = orc.eval(p, 1, s0s[:, 1], oc, xs, threads=8)
+    mc = MultiContext(devs, "dpf", 32, "bytes", prg_key=p.prg_key)
+    mc.set_host_mode(1)
+    h = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32))  # noqa: E731
+    a = [h(s0s[:, 1]), h(oc)]
+    if pinned:
+        a = [t.pin_memory() for t in a]
+    launches0 = mc.launch_count()
+    yh = mc.eval_host(1, a[0], a[1], xs)
+    assert np.array_equal(yh.numpy().view(np.uint32), want)
+    assert mc.launch_count() - launches0 >= 5      # several blocks, not one range per device
+    mc.close()
