@@ -309,3 +309,20 @@ def test_gpu_vdpf_scheme_errors(dev):
     with pytest.raises(L.FssError) as e:
         dpf.vdpf_eval(0, s, z[:, :16], torch.zeros((4, 4, 4), dtype=torch.int32, device=dev), s, [1, 2, 3, 4])
     assert e.value.code == L.E_SCHEME
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+def test_gpu_evalall_lanes_per_key(dev, orc, monkeypatch, lanes):
+    """vdpf_finish_kernel<G, LPK>: every lanes-per-key variant (the launcher picks one from the key count) against the
+    oracle -- ragged key groups in the last warp, domains smaller and larger than LPK, both parties."""
+    monkeypatch.setenv("FSSB200_VDPF_FINISH_LANES", str(lanes))
+    for n, group, nkeys in ((6, "u64", 37), (3, "bytes", 5), (1, "u32", 67), (9, "u128", 130)):
+        p = Params(scheme="vdpf", in_bits=n, group=group)
+        ctx = _ctx(p)
+        s0s, alphas, betas, _ = synth_inputs(p, nkeys, seed=lanes * 100 + n)
+        cws, cs, ocws, _ = orc.vdpf_gen(p, s0s, alphas, betas, threads=4)
+        for party in (0, 1):
+            ya, pa = ctx.vdpf_eval_all(party, _t(s0s[:, party], dev), _t(cws, dev), _t(cs, dev), _t(ocws, dev))
+            wy, wp = orc.vdpf_evalall(p, party, s0s[:, party], cws, cs, ocws, threads=4)
+            assert np.array_equal(_n(ya), wy) and np.array_equal(_n(pa), wp), (n, group, party)
