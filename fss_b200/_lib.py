@@ -24,7 +24,7 @@ class Params(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("in_bits", C.c_int32), ("in_bytes", C.c_int32), ("group", C.c_int32),
                 ("mod_lo", C.c_uint64), ("mod_hi", C.c_uint64), ("prg", C.c_int32), ("pred", C.c_int32),
                 ("prg_key", C.c_uint8 * 64), ("hash_key", C.c_uint8 * 16), ("device", C.c_int32),
-                ("reserved", C.c_int32), ("hash_iv", C.c_uint8 * 64)]
+                ("hash", C.c_int32), ("hash_iv", C.c_uint8 * 64)]
 
 
 class FssError(RuntimeError):

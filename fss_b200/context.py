@@ -33,6 +33,7 @@ DEFAULT_AES_KEYS = bytes(range(1, 17)) + bytes(range(16, 0, -1)) + bytes(
 DEFAULT_CHACHA_NONCE = (0x12345678).to_bytes(4, "little") + (0x9ABCDEF0).to_bytes(4, "little")
 DEFAULT_HASH_KEY = b"".join(v.to_bytes(4, "little") for v in (0x12345678, 0x9ABCDEF0, 0x0FEDCBA9, 0x87654321))
 # VDPF: IVs of the XorHash / Hash Blake3 plugins (first one = the reference tests' constant, src/vdpf_test.cu:35-36)
+_HASHES = {"blake3": 0, "sha256": 1}
 DEFAULT_HASH_IVS = b"".join(v.to_bytes(4, "little") for v in (
     0x11111111, 0x22222222, 0x33333333, 0x44444444, 0x55555555, 0x66666666, 0x77777777, 0x88888888,
     0x99999999, 0xAAAAAAAA, 0xBBBBBBBB, 0xCCCCCCCC, 0xDDDDDDDD, 0xEEEEEEEE, 0xFFFFFFFF, 0x01234567))
@@ -52,7 +53,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class Context:
     def __init__(self, scheme: str, in_bits: int, group: str = "bytes", mod: int = 0, prg: str = "aes128_mmo",
                  pred: str = "lt", prg_key: Optional[bytes] = None, hash_key: Optional[bytes] = None,
-                 in_bytes: Optional[int] = None, hash_iv: Optional[bytes] = None):
+                 in_bytes: Optional[int] = None, hash_iv: Optional[bytes] = None, hash: "str | tuple[str, str]" = "blake3"):
         self.scheme, self.in_bits, self.group, self.prg, self.pred = scheme, in_bits, group, prg, pred
         if group == "u128" and mod == 0:
             mod = 1 << 127
@@ -64,6 +65,12 @@ class Context:
         self.hash_iv = hash_iv if hash_iv is not None else DEFAULT_HASH_IVS
         if len(self.hash_iv) != 64:
             raise ValueError("hash_iv must be 64 bytes (XorHash IV || Hash IV)")
+        # VDPF hash plugins (XorHash, Hash): "blake3" (hash/blake3.cuh) or "sha256" (hash/sha256.cuh; its 16-byte key is
+        # the first 16 bytes of the plugin's 32-byte hash_iv slot); one name = both plugins
+        hx, hh = (hash, hash) if isinstance(hash, str) else hash
+        if hx not in _HASHES or hh not in _HASHES:
+            raise ValueError(f"hash must be one of {sorted(_HASHES)}")
+        self.hash_plugins = (hx, hh)
         self.ncw = in_bits if scheme in ("halftree", "vdpf") else in_bits + 1
         self.mul = {"dpf": 2, "dcf": 4, "halftree": 1, "grotto": 2, "vdpf": 2}[scheme]
         self._handles: dict[int, C.c_void_p] = {}
@@ -79,6 +86,7 @@ class Context:
         C.memmove(p.prg_key, key, 64)
         C.memmove(p.hash_key, bytes(self.hash_key), 16)
         C.memmove(p.hash_iv, bytes(self.hash_iv), 64)
+        p.hash = _HASHES[self.hash_plugins[0]] | (_HASHES[self.hash_plugins[1]] << 8)
         return p
 
     def handle(self, device: Optional[int] = None) -> C.c_void_p:

@@ -165,6 +165,7 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   if (p->scheme < FSSB200_SCHEME_DPF || p->scheme > FSSB200_SCHEME_VDPF) return FSSB200_EINVAL;
   if (p->prg != FSSB200_PRG_AES128_MMO && p->prg != FSSB200_PRG_CHACHA) return FSSB200_EINVAL;
   if (p->pred != FSSB200_PRED_LT && p->pred != FSSB200_PRED_GT) return FSSB200_EINVAL;
+  if ((p->hash & ~0x0101) != 0) return FSSB200_EINVAL;  // byte 0 / byte 1: FSSB200_HASH_BLAKE3 or FSSB200_HASH_SHA256
   if (p->in_bytes != 1 && p->in_bytes != 2 && p->in_bytes != 4 && p->in_bytes != 8 && p->in_bytes != 16)
     return FSSB200_EINVAL;
   if (p->in_bits < 1 || p->in_bits > 8 * p->in_bytes) return FSSB200_EDOMAIN;
@@ -217,6 +218,8 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   }
   std::memcpy(c->kp.keys.hash_key, q.hash_key, 16);
   std::memcpy(c->kp.keys.hash_iv, q.hash_iv, 64);
+  c->kp.keys.hash_kind[0] = uint32_t(q.hash) & 0xffu;
+  c->kp.keys.hash_kind[1] = (uint32_t(q.hash) >> 8) & 0xffu;
   c->kp.ga.vmask = vmask;
   c->kp.ga.mod[0] = uint32_t(q.mod_lo);
   c->kp.ga.mod[1] = uint32_t(q.mod_lo >> 32);

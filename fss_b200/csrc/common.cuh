@@ -56,6 +56,7 @@ struct PrgKeys {
   uint32_t nonce[2];    // ChaCha nonce words (prg/chacha.cuh:108-110)
   uint32_t hash_key[4]; // HalfTreeDpf::hash_key (half_tree_dpf.cuh:44)
   uint32_t hash_iv[2][8]; // VDPF: IVs of the XorHash (0) / Hash (1) Blake3 plugins (hash/blake3.cuh:131)
+  uint32_t hash_kind[2];  // FSSB200_HASH_* of the two plugins; a SHA-256 plugin's key = hash_iv[i][0..4) (hash/sha256.cuh:35)
 };
 
 struct GroupMod {

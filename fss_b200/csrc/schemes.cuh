@@ -13,6 +13,7 @@
 // on the CPU.
 #pragma once
 #include "blake3.cuh"
+#include "sha256.cuh"
 #include "group.cuh"
 #include "prg.cuh"
 
@@ -168,6 +169,17 @@ FSS_HD void dpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
 // ---- VDPF (vdpf.cuh) -------------------------------------------------------------------------------------
 FSS_HD blk pack_in(const InVal &x) { return make_blk(x.w[0], x.w[1], x.w[2], x.w[3]); }  // util.cuh:46-63 Pack<In>
 
+// The scheme's two hash plugins (vdpf.cuh:55-58): XorHash H (x, s) -> 64 B and Hash H' 64 B -> 32 B, each Blake3 or SHA-256.
+// The kind is a kernel parameter (warp-uniform branch), not a template parameter: the hashes sit outside the level loop.
+FSS_HD void vdpf_xor_hash(const PrgKeys &K, blk a, blk b, blk out[4]) {
+  if (K.hash_kind[0] == FSSB200_HASH_SHA256) sha_xor_hash(K.hash_iv[0], a, b, out);
+  else b3_xor_hash(K.hash_iv[0], a, b, out);
+}
+FSS_HD void vdpf_hash(const PrgKeys &K, const blk msg[4], blk out[2]) {
+  if (K.hash_kind[1] == FSSB200_HASH_SHA256) sha_hash(K.hash_iv[1], msg, out);
+  else b3_hash(K.hash_iv[1], msg, out);
+}
+
 // Output share and corrected per-point hash of a packed leaf (s | t) at input x: vdpf.cuh:224-242, :318-331.
 template <int G>
 FSS_HD blk vdpf_leaf(const PrgKeys &K, const GroupArgs &ga, uint32_t party, blk st, const InVal &x, blk ocw,
@@ -178,7 +190,7 @@ FSS_HD blk vdpf_leaf(const PrgKeys &K, const GroupArgs &ga, uint32_t party, blk 
   typename GR::V y = GR::from(ga, s);
   y = GR::add_masked(ga, y, tm, GR::from(ga, ocw));
   y = GR::cneg(ga, y, party);
-  b3_xor_hash(K.hash_iv[0], pack_in(x), s, pi);
+  vdpf_xor_hash(K, pack_in(x), s, pi);
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = xor_masked(pi[j], tm, ld_blk(cs + j));
   return GR::into(ga, y);
@@ -251,8 +263,8 @@ FSS_HD int vdpf_gen_body(const PrgKeys &K, const GroupArgs &ga, const typename P
     out.put(i, s_cw, make_blk(tr_cw, 0, 0, 0));                // vdpf.cuh:147-149
   }
   blk p0[4], p1[4];                                             // :153-157
-  b3_xor_hash(K.hash_iv[0], pack_in(a), s0, p0);
-  b3_xor_hash(K.hash_iv[0], pack_in(a), s1, p1);
+  vdpf_xor_hash(K, pack_in(a), s0, p0);
+  vdpf_xor_hash(K, pack_in(a), s1, p1);
   if (write) {  // (idle lanes of a ragged tile shadow the last key and write nothing)
 #pragma unroll
     for (int j = 0; j < 4; ++j) st_blk(cs + j, p0[j] ^ p1[j]);
@@ -269,7 +281,7 @@ FSS_HD void vdpf_accumulate(const PrgKeys &K, blk pi[4], const blk pt[4]) {
   blk in[4], h[2];
 #pragma unroll
   for (int j = 0; j < 4; ++j) in[j] = pi[j] ^ pt[j];
-  b3_hash(K.hash_iv[1], in, h);
+  vdpf_hash(K, in, h);
   pi[0] = pi[0] ^ h[0];
   pi[1] = pi[1] ^ h[1];
 }

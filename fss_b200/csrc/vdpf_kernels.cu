@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(256) hash_kernel(const __grid_constant__ KPara
   if (i >= n) return;
   if (which == 0) {
     blk o[4];
-    b3_xor_hash(P.keys.hash_iv[0], ld_blk(msgs + 2 * i), ld_blk(msgs + 2 * i + 1), o);
+    vdpf_xor_hash(P.keys, ld_blk(msgs + 2 * i), ld_blk(msgs + 2 * i + 1), o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) st_blk(out + 4 * i + j, o[j]);
   } else {
     blk m[4], o[2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) m[j] = ld_blk(msgs + 4 * i + j);
-    b3_hash(P.keys.hash_iv[1], m, o);
+    vdpf_hash(P.keys, m, o);
     st_blk(out + 2 * i, o[0]);
     st_blk(out + 2 * i + 1, o[1]);
   }

@@ -33,7 +33,6 @@ inline fssb200_ctx *ContextFor(fssb200_params p, int device = -1) {  // device <
   int dev = device;
   if (dev < 0) cudaGetDevice(&dev);
   p.device = dev;
-  p.reserved = 0;
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(p);
   if (it != cache.end()) return it->second;

@@ -20,8 +20,11 @@ concept XorHashable = requires(Hash hash, cuda::std::tuple<int4, const int4> msg
 };
 
 namespace fss::b200 {
+// A hash the evaluator runs on the device: it exports its key material (32-byte slot of fssb200_params::hash_iv) and which
+// built-in function it is (FSSB200_HASH_BLAKE3 / FSSB200_HASH_SHA256).
 template <typename Hash>
 concept DeviceHash = requires(const Hash h, uint8_t *iv32) {
   { h.FssB200Iv(iv32) };
+  { Hash::kFssB200Hash } -> std::convertible_to<int>;
 };
 }  // namespace fss::b200

@@ -39,6 +39,7 @@ class Blake3 {
 public:
   explicit Blake3(cuda::std::span<const int4, 2> iv) : iv_{iv[0], iv[1]} {}  // hash/blake3.cuh:131
 
+  static constexpr int kFssB200Hash = FSSB200_HASH_BLAKE3;
   void FssB200Iv(uint8_t iv32[32]) const { std::memcpy(iv32, iv_, 32); }
 
   // hash/blake3.cuh:145-149: 64 B -> 32 B

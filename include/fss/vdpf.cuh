@@ -35,6 +35,7 @@ public:
     fssb200_params p = b200::MakeParams<in_bits, Group, Prg, In>(FSSB200_SCHEME_VDPF, prg);
     xor_hash.FssB200Iv(p.hash_iv[0]);
     hash.FssB200Iv(p.hash_iv[1]);
+    p.hash = XorHash::kFssB200Hash | (Hash::kFssB200Hash << 8);
     return b200::ContextFor(p);
   }
 

@@ -55,7 +55,7 @@ enum {
   FSSB200_SCHEME_DCF = 1,      /* fss::Dcf          dcf.cuh:74-386            */
   FSSB200_SCHEME_HALFTREE = 2, /* fss::HalfTreeDpf  half_tree_dpf.cuh:39-355  */
   FSSB200_SCHEME_GROTTO = 3,   /* fss::GrottoDcf    grotto_dcf.cuh:45-239     */
-  FSSB200_SCHEME_VDPF = 4      /* fss::Vdpf         vdpf.cuh:63-403 (XorHash = Hash = fss::hash::Blake3);
+  FSSB200_SCHEME_VDPF = 4      /* fss::Vdpf         vdpf.cuh:63-403 (XorHash / Hash = fss::hash::Blake3 or ::Sha256);
                                   only the fssb200_vdpf_* entry points apply          */
 };
 
@@ -78,6 +78,9 @@ enum {
 
 /* DCF predicate (dcf.cuh:58-61); only Gen depends on it. */
 enum { FSSB200_PRED_LT = 0, FSSB200_PRED_GT = 1 };
+/* VDPF hash plugins (vdpf.cuh:55-58): fss::hash::Blake3 hash/blake3.cuh:24-172, fss::hash::Sha256 hash/sha256.cuh:25-90
+ * (host-only in the reference; here both run on the device) */
+enum { FSSB200_HASH_BLAKE3 = 0, FSSB200_HASH_SHA256 = 1 };
 
 /* Error codes (negative).  Positive return values are cudaError_t. */
 enum {
@@ -106,8 +109,10 @@ enum {
  *   hash_key  : HalfTreeDpf::hash_key         (half_tree_dpf.cuh:44)
  *   pred      : DcfPred                       (dcf.cuh:58-61)
  *   device    : CUDA device ordinal the context's kernels run on.
- *   hash_iv   : VDPF only: the 32-byte IVs of the two fss::hash::Blake3 plugins
- *               (hash/blake3.cuh:131): [0] = XorHash `H` (vdpf.cuh:55), [1] = Hash `H'` (:56).
+ *   hash_iv   : VDPF only: key material of the two hash plugins, [0] = XorHash `H` (vdpf.cuh:55),
+ *               [1] = Hash `H'` (:56): the 32-byte IV of a fss::hash::Blake3 (hash/blake3.cuh:131) or the
+ *               16-byte key of a fss::hash::Sha256 (hash/sha256.cuh:35) in the first half of the slot.
+ *   hash      : VDPF only: which function each plugin is, FSSB200_HASH_* in byte 0 (XorHash) and byte 1 (Hash).
  */
 typedef struct fssb200_params {
   int32_t scheme;
@@ -121,8 +126,9 @@ typedef struct fssb200_params {
   uint8_t prg_key[64];
   uint8_t hash_key[16];
   int32_t device;
-  int32_t reserved;
-  uint8_t hash_iv[2][32];
+  int32_t hash;            /* VDPF hash plugins: byte 0 = XorHash (H), byte 1 = Hash (H'); FSSB200_HASH_* (0 = Blake3) */
+  uint8_t hash_iv[2][32];  /* [0] XorHash, [1] Hash: Blake3 IV (32 B, hash/blake3.cuh:131) or SHA-256 key (first 16 B,
+                              hash/sha256.cuh:35) */
 } fssb200_params;
 
 typedef struct fssb200_ctx fssb200_ctx;
@@ -262,7 +268,7 @@ int fssb200_vdpf_prove(const fssb200_ctx *ctx, const void *pi_tildes, const void
 int fssb200_vdpf_eval_all(const fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
                           const void *cs, const void *ocws, void *ys, void *pis, size_t nkeys,
                           void *stream);
-/* Hash known-answer hook (hash/blake3.cuh:143-171): which = 0: XorHash, msgs = (a, b) pairs of
+/* Hash known-answer hook (hash/blake3.cuh:143-171, hash/sha256.cuh:44-89; the context's plugins): which = 0: XorHash, msgs = (a, b) pairs of
  * int4 (32 B) -> 64 B each; which = 1: Hash, msgs = 64 B -> 32 B each.  Device pointers. */
 int fssb200_hash(const fssb200_ctx *ctx, int which, const void *msgs, void *out, size_t n,
                  void *stream);

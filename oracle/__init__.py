@@ -28,6 +28,7 @@ SCHEME = {"dpf": 0, "dcf": 1, "halftree": 2, "grotto": 3, "vdpf": 4}
 GROUP = {"bytes": 0, "u8": 1, "u16": 2, "u32": 3, "u64": 4, "u128": 5}
 PRG = {"aes128_mmo": 0, "chacha": 1, "aes128_mmo_raw": 2}
 PRED = {"lt": 0, "gt": 1}
+HASH = {"blake3": 0, "sha256": 1}
 
 # fixtures used by the reference's own tests / samples
 AES_KEYS = bytes(range(1, 17)) + bytes(range(16, 0, -1)) + bytes(
@@ -48,7 +49,7 @@ class CParams(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("in_bits", C.c_int32), ("in_bytes", C.c_int32), ("group", C.c_int32),
                 ("mod_lo", C.c_uint64), ("mod_hi", C.c_uint64), ("prg", C.c_int32), ("pred", C.c_int32),
                 ("prg_key", C.c_uint8 * 64), ("hash_key", C.c_uint8 * 16), ("device", C.c_int32),
-                ("reserved", C.c_int32), ("hash_iv", C.c_uint8 * 64)]
+                ("hash", C.c_int32), ("hash_iv", C.c_uint8 * 64)]
 
 
 class CRefParams(C.Structure):
@@ -77,6 +78,7 @@ class Params:
     hash_key: bytes = HASH_KEY_SAMPLE
     in_bytes: int = 0
     hash_iv: bytes = HASH_IVS
+    hash: tuple = ("blake3", "blake3")   # VDPF (XorHash, Hash) plugins: "blake3" | "sha256"
 
     def __post_init__(self):
         if not self.in_bytes:
@@ -105,6 +107,8 @@ class Params:
         for i in range(16):
             p.hash_key[i] = self.hash_key[i]
         C.memmove(p.hash_iv, bytes(self.hash_iv), 64)
+        hx, hh = (self.hash, self.hash) if isinstance(self.hash, str) else self.hash
+        p.hash = HASH[hx] | (HASH[hh] << 8)
         return p
 
 
@@ -324,8 +328,10 @@ class Ref(_Base):
 
     @staticmethod
     def _sel(p: Params) -> CRefSel:
-        return CRefSel(SCHEME[p.scheme], p.in_bits, GROUP[p.group], PRG[p.prg], PRED[p.pred], 0,
-                       p.mod & (2 ** 64 - 1), p.mod >> 64)
+        hx, hh = (p.hash, p.hash) if isinstance(p.hash, str) else p.hash
+        # (the reference shim instantiates XorHash == Hash only; a mixed pair selects nothing)
+        return CRefSel(SCHEME[p.scheme], p.in_bits, GROUP[p.group], PRG[p.prg], PRED[p.pred],
+                       HASH[hx] if hx == hh else 99, p.mod & (2 ** 64 - 1), p.mod >> 64)
 
     @staticmethod
     def _rp(p: Params) -> CRefParams:
@@ -431,7 +437,9 @@ class Ref(_Base):
         msgs = _u32(msgs, (-1, 2, 4) if which == 0 else (-1, 4, 4))
         out = np.zeros((len(msgs), 4 if which == 0 else 2, 4), dtype=np.uint32)
         iv = (C.c_uint8 * 32).from_buffer_copy(bytes(p.hash_iv)[32 * which:32 * which + 32])
-        rc = self.lib.ref_blake3(iv, which, C.c_size_t(len(msgs)), _vp(msgs), _vp(out))
+        hname = (p.hash if isinstance(p.hash, str) else p.hash[which])
+        fn = self.lib.ref_sha256 if hname == "sha256" else self.lib.ref_blake3
+        rc = fn(iv, which, C.c_size_t(len(msgs)), _vp(msgs), _vp(out))
         assert rc == 0, rc
         return out
 

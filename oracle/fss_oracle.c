@@ -726,14 +726,88 @@ static void b3_xor_hash(const uint8_t iv[32], blk a, blk b, blk out[4]) {
   b3_compress(h, (const uint32_t *)padded, 32, B3_FLAGS, o);
   memcpy(&out[2], o, 32);
 }
+/* ---- SHA-256 keyed hash: hash/sha256.cuh (EVP_Digest over key || message) ------------------------ */
+/* FIPS 180-4, byte-oriented: `len` message bytes, digest as 32 bytes. */
+static void sha256_bytes(const uint8_t *msg, size_t len, uint8_t digest[32]) {
+  static const uint32_t K[64] = {
+      0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+      0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+      0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+      0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+      0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+      0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+      0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+      0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+  uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+  uint8_t buf[192];
+  size_t total = ((len + 9 + 63) / 64) * 64;
+  memset(buf, 0, sizeof(buf));
+  memcpy(buf, msg, len);
+  buf[len] = 0x80;
+  for (int i = 0; i < 8; ++i) buf[total - 1 - i] = (uint8_t)(((uint64_t)len * 8) >> (8 * i));
+  for (size_t off = 0; off < total; off += 64) {
+    uint32_t w[64], s[8];
+    for (int i = 0; i < 16; ++i)
+      w[i] = ((uint32_t)buf[off + 4 * i] << 24) | ((uint32_t)buf[off + 4 * i + 1] << 16) |
+          ((uint32_t)buf[off + 4 * i + 2] << 8) | buf[off + 4 * i + 3];
+    for (int i = 16; i < 64; ++i) {
+      const uint32_t s0 = rotr32(w[i - 15], 7) ^ rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+      const uint32_t s1 = rotr32(w[i - 2], 17) ^ rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    memcpy(s, h, sizeof(s));
+    for (int i = 0; i < 64; ++i) {
+      const uint32_t S1 = rotr32(s[4], 6) ^ rotr32(s[4], 11) ^ rotr32(s[4], 25);
+      const uint32_t ch = (s[4] & s[5]) ^ (~s[4] & s[6]);
+      const uint32_t t1 = s[7] + S1 + ch + K[i] + w[i];
+      const uint32_t S0 = rotr32(s[0], 2) ^ rotr32(s[0], 13) ^ rotr32(s[0], 22);
+      const uint32_t maj = (s[0] & s[1]) ^ (s[0] & s[2]) ^ (s[1] & s[2]);
+      const uint32_t t2 = S0 + maj;
+      s[7] = s[6]; s[6] = s[5]; s[5] = s[4]; s[4] = s[3] + t1; s[3] = s[2]; s[2] = s[1]; s[1] = s[0]; s[0] = t1 + t2;
+    }
+    for (int i = 0; i < 8; ++i) h[i] += s[i];
+  }
+  for (int i = 0; i < 8; ++i) {
+    digest[4 * i] = (uint8_t)(h[i] >> 24); digest[4 * i + 1] = (uint8_t)(h[i] >> 16);
+    digest[4 * i + 2] = (uint8_t)(h[i] >> 8); digest[4 * i + 3] = (uint8_t)h[i];
+  }
+}
+/* Sha256::Hash(span<int4,4>) hash/sha256.cuh:44-58: SHA-256(key || 64-byte message) */
+static void sha_hash(const uint8_t key[16], const blk msg[4], blk out[2]) {
+  uint8_t buf[80];
+  memcpy(buf, key, 16);
+  memcpy(buf + 16, msg, 64);
+  sha256_bytes(buf, 80, (uint8_t *)out);
+}
+/* Sha256::Hash(tuple<int4,int4>) hash/sha256.cuh:69-89: SHA-256(key || a lsb=0 || b) || SHA-256(key || a lsb=1 || b) */
+static void sha_xor_hash(const uint8_t key[16], blk a, blk b, blk out[4]) {
+  uint8_t buf[48];
+  blk a0 = set_lsb(a, 0), a1 = set_lsb(a, 1);
+  memcpy(buf, key, 16);
+  memcpy(buf + 16, &a0, 16);
+  memcpy(buf + 32, &b, 16);
+  sha256_bytes(buf, 48, (uint8_t *)&out[0]);
+  memcpy(buf + 16, &a1, 16);
+  sha256_bytes(buf, 48, (uint8_t *)&out[2]);
+}
+/* the VDPF hash plugins of a parameter set: fssb200_params::hash, byte 0 = XorHash, byte 1 = Hash (0 Blake3, 1 SHA-256;
+   a SHA-256 plugin's key is the first 16 bytes of its hash_iv slot) */
+static void p_xor_hash(const fssb200_params *p, blk a, blk b, blk out[4]) {
+  if ((p->hash & 0xff) == FSSB200_HASH_SHA256) sha_xor_hash(p->hash_iv[0], a, b, out);
+  else b3_xor_hash(p->hash_iv[0], a, b, out);
+}
+static void p_hash(const fssb200_params *p, const blk msg[4], blk out[2]) {
+  if (((p->hash >> 8) & 0xff) == FSSB200_HASH_SHA256) sha_hash(p->hash_iv[1], msg, out);
+  else b3_hash(p->hash_iv[1], msg, out);
+}
 int orc_hash(const fssb200_params *p, int which, size_t n, const void *msgs, void *out) {
   if (!p || !msgs || !out) return FSSB200_EINVAL;
   for (size_t i = 0; i < n; ++i) {
     if (which == 0) {
       const blk *m = (const blk *)msgs + 2 * i;
-      b3_xor_hash(p->hash_iv[0], m[0], m[1], (blk *)out + 4 * i);
+      p_xor_hash(p, m[0], m[1], (blk *)out + 4 * i);
     } else {
-      b3_hash(p->hash_iv[1], (const blk *)msgs + 4 * i, (blk *)out + 2 * i);
+      p_hash(p, (const blk *)msgs + 4 * i, (blk *)out + 2 * i);
     }
   }
   return 0;
@@ -774,8 +848,8 @@ static int vdpf_gen(const octx *c, cw32 *cws, blk cs[4], blk *ocw, const blk s0s
     cws[i].v = bzero(); cws[i].v.w[0] = (uint32_t)tr_cw;          /* :147-149 */
   }
   blk a_buf = pack_in(c, a), p0[4], p1[4];                         /* :153-157 */
-  b3_xor_hash(c->p.hash_iv[0], a_buf, s0, p0);
-  b3_xor_hash(c->p.hash_iv[0], a_buf, s1, p1);
+  p_xor_hash(&c->p, a_buf, s0, p0);
+  p_xor_hash(&c->p, a_buf, s1, p1);
   for (int j = 0; j < 4; ++j) cs[j] = bxor(p0[j], p1[j]);
   if (t0 == t1) return 1;                                          /* :160 */
   u128 v = g_add(c, g_add(c, g_from(c, b_buf), g_neg(c, g_from(c, s0))), g_from(c, s1));
@@ -791,7 +865,7 @@ static void vdpf_leaf(const octx *c, int b, blk st, const blk cs[4], blk ocw, u1
   if (t) g = g_add(c, g, g_from(c, ocw));
   if (b) g = g_neg(c, g);
   *y = g_into(c, g);
-  b3_xor_hash(c->p.hash_iv[0], pack_in(c, x), s, pi_tilde);
+  p_xor_hash(&c->p, pack_in(c, x), s, pi_tilde);
   if (t) for (int j = 0; j < 4; ++j) pi_tilde[j] = bxor(pi_tilde[j], cs[j]);
 }
 static void vdpf_eval(const octx *c, int b, blk s0, const cw32 *cws, const blk cs[4], blk ocw, u128 x, blk *y,
@@ -809,7 +883,7 @@ static void vdpf_eval(const octx *c, int b, blk s0, const cw32 *cws, const blk c
 static void vdpf_accumulate(const octx *c, blk pi[4], const blk pi_tilde[4]) {
   blk in[4], h[2];
   for (int j = 0; j < 4; ++j) in[j] = bxor(pi[j], pi_tilde[j]);
-  b3_hash(c->p.hash_iv[1], in, h);
+  p_hash(&c->p, in, h);
   pi[0] = bxor(pi[0], h[0]);
   pi[1] = bxor(pi[1], h[1]);
 }

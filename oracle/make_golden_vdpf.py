@@ -6,7 +6,8 @@ reference `fss::Vdpf` (oracle/_ref/libfssref.so = oracle/ref_vdpf.cpp over /root
 
 Each case stores inputs (seeds, alphas, betas, xs, hash IVs) and the reference's outputs: cws, cs, ocws,
 Gen status, per-party (y, pi_tilde) of Eval, Prove over all points of a key, and EvalAll (ys + proof,
-or SHA-256 of ys + proof for n = 16).  Also Blake3 known answers for both hash interfaces.
+or SHA-256 of ys + proof for n = 16).  Also known answers of both hash interfaces.  A second file,
+golden_vdpf_sha256_v1.*, holds the same for XorHash = Hash = fss::hash::Sha256 (hash/sha256.cuh).
 """
 from __future__ import annotations
 
@@ -31,21 +32,27 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def main():
+def build(hash_name):
+    """All cases with XorHash = Hash = `hash_name` ("blake3": hash/blake3.cuh, "sha256": hash/sha256.cuh)."""
     ref = Ref()
     arrays, manifest = {}, []
     rng = np.random.default_rng(11)
-    p0 = Params(scheme="vdpf", in_bits=8)
+    p0 = Params(scheme="vdpf", in_bits=8, hash=hash_name)
+    sha_only = hash_name != "blake3"
+    pre = "sha_" if sha_only else ""
     arrays["hash/xor_in"] = rng.integers(0, 2 ** 32, size=(32, 2, 4), dtype=np.uint64).astype(np.uint32)
     arrays["hash/hash_in"] = rng.integers(0, 2 ** 32, size=(32, 4, 4), dtype=np.uint64).astype(np.uint32)
     arrays["hash/xor_out"] = ref.hash(p0, 0, arrays["hash/xor_in"])
     arrays["hash/hash_out"] = ref.hash(p0, 1, arrays["hash/hash_in"])
 
     def add_case(name, p, s0s, alphas, betas, xs, evalall="none", evalall_keys=2):
+        name = pre + name
+        p.hash = hash_name
+        assert ref.vdpf_supported(p), name
         cws, cs, ocws, status = ref.vdpf_gen(p, s0s, alphas, betas)
         assert not status.any()
         case = {"name": name, "in_bits": p.in_bits, "in_bytes": p.in_bytes, "group": p.group, "mod": str(p.mod),
-                "prg": p.prg, "prg_key": p.prg_key.hex(), "hash_iv": bytes(p.hash_iv).hex(),
+                "prg": p.prg, "prg_key": p.prg_key.hex(), "hash_iv": bytes(p.hash_iv).hex(), "hash": hash_name,
                 "alphas": [str(a) for a in alphas], "xs": [str(x) for x in xs], "evalall": evalall}
         arrays[f"{name}/s0s"], arrays[f"{name}/betas"] = s0s, betas
         arrays[f"{name}/cws"], arrays[f"{name}/cs"], arrays[f"{name}/ocws"] = cws, cs, ocws
@@ -84,20 +91,30 @@ def main():
         t = "aes" if prg.startswith("aes") else "chacha"
         rand_case(f"vdpf_n32_bytes_{t}", Params(scheme="vdpf", in_bits=32, prg=prg), 32)
         rand_case(f"vdpf_n64_u127_{t}", Params(scheme="vdpf", in_bits=64, group="u128", prg=prg), 16)
-        rand_case(f"vdpf_n20_u64_{t}", Params(scheme="vdpf", in_bits=20, group="u64", prg=prg), 16)
+        if not sha_only:  # (the reference shim instantiates fewer domains with Sha256)
+            rand_case(f"vdpf_n20_u64_{t}", Params(scheme="vdpf", in_bits=20, group="u64", prg=prg), 16)
         rand_case(f"vdpf_n12_u32_{t}", Params(scheme="vdpf", in_bits=12, group="u32", prg=prg), 8, "full", 2)
-        rand_case(f"vdpf_n16_bytes_{t}", Params(scheme="vdpf", in_bits=16, prg=prg), 8, "sha", 2)
+        if not sha_only:
+            rand_case(f"vdpf_n16_bytes_{t}", Params(scheme="vdpf", in_bits=16, prg=prg), 8, "sha", 2)
         rand_case(f"vdpf_n128_u64p_{t}", Params(scheme="vdpf", in_bits=128, group="u64", mod=18446744073709551557,
                                                  prg=prg), 8)
-        for n in (1, 3, 40):
+        for n in ((1,) if sha_only else (1, 3, 40)):
             rand_case(f"vdpf_n{n}_u64_{t}", Params(scheme="vdpf", in_bits=n, group="u64", prg=prg), 8,
                       "full" if n <= 3 else "none", 8, seed=n)
 
-    np.savez_compressed(os.path.join(OUT_DIR, "golden_vdpf_v1.npz"), **arrays)
-    with open(os.path.join(OUT_DIR, "golden_vdpf_v1.json"), "w") as f:
-        json.dump({"generator": "oracle/make_golden_vdpf.py", "reference_commit": "c1ebc87 (v1.2.0)",
-                   "cases": manifest}, f, indent=1)
-    print(f"{len(manifest)} cases, {len(arrays)} arrays ->", OUT_DIR)
+    return arrays, manifest
+
+
+def main():
+    for hash_name, stem in (("blake3", "golden_vdpf_v1"), ("sha256", "golden_vdpf_sha256_v1")):
+        arrays, manifest = build(hash_name)
+        if hash_name != "blake3":  # the hash known answers of this file live under their own keys
+            arrays = {(k.replace("hash/", "hash_sha256/") if k.startswith("hash/") else k): v for k, v in arrays.items()}
+        np.savez_compressed(os.path.join(OUT_DIR, stem + ".npz"), **arrays)
+        with open(os.path.join(OUT_DIR, stem + ".json"), "w") as f:
+            json.dump({"generator": "oracle/make_golden_vdpf.py", "reference_commit": "c1ebc87 (v1.2.0)",
+                       "cases": manifest}, f, indent=1)
+        print(f"{hash_name}: {len(manifest)} cases, {len(arrays)} arrays ->", OUT_DIR)
 
 
 if __name__ == "__main__":

@@ -3,8 +3,8 @@
 // TEST INFRASTRUCTURE ONLY -- not part of the product path.
 //
 // ref_vdpf.cpp: extern "C" shim over the UNMODIFIED reference `fss::Vdpf` (vdpf.cuh) with
-// XorHash = Hash = fss::hash::Blake3, included from /root/reference/include, for a table of
-// (in_bits, group, prg) instantiations.  Part of oracle/_ref/libfssref.so; pins the VDPF part of the
+// XorHash = Hash = fss::hash::Blake3 or fss::hash::Sha256 (RefSel::pad = 0 / 1), included from
+// /root/reference/include, for a table of (in_bits, group, prg, hash) instantiations.  Part of oracle/_ref/libfssref.so; pins the VDPF part of the
 // C restatement (oracle/fss_oracle.c) and generates the VDPF golden fixtures.
 #include <cstdint>
 #include <cstring>
@@ -17,6 +17,7 @@
 #include <fss/group/bytes.cuh>
 #include <fss/group/uint.cuh>
 #include <fss/hash/blake3.cuh>
+#include <fss/hash/sha256.cuh>
 #include <fss/prg/aes128_mmo.cuh>
 #include <fss/prg/chacha.cuh>
 #include <fss/vdpf.cuh>
@@ -56,10 +57,19 @@ In LoadIn(const uint8_t *p, int in_bytes) {
   return static_cast<In>(v);
 }
 
-fss::hash::Blake3 MakeHash(const uint8_t iv[32]) {
+template <class H>
+H MakeHash(const uint8_t iv[32]);
+template <>
+fss::hash::Blake3 MakeHash<fss::hash::Blake3>(const uint8_t iv[32]) {
   int4 v[2];
   memcpy(v, iv, 32);
   return fss::hash::Blake3(cuda::std::span<const int4, 2>(v, 2));
+}
+template <>
+fss::hash::Sha256 MakeHash<fss::hash::Sha256>(const uint8_t iv[32]) {  // 16-byte key = the first half of the slot
+  int4 k;
+  memcpy(&k, iv, 16);
+  return fss::hash::Sha256(k);
 }
 
 struct VdpfOps {
@@ -72,10 +82,10 @@ struct VdpfOps {
       const void *, void *, void *, int);
 };
 
-template <int N, class G, class Prg>
+template <int N, class G, class Prg, class H>
 struct Ad {
   using In = InOf<N>;
-  using S = fss::Vdpf<N, G, Prg, fss::hash::Blake3, fss::hash::Blake3, In>;
+  using S = fss::Vdpf<N, G, Prg, H, H, In>;
   using Cw = typename S::Cw;
   using Arr4 = cuda::std::array<int4, 4>;
 
@@ -85,7 +95,7 @@ struct Ad {
 #pragma omp parallel num_threads(threads > 0 ? threads : 1)
     {
       Holder<Prg> h(p);
-      S s{h.make(), MakeHash(ivs), MakeHash(ivs + 32)};
+      S s{h.make(), MakeHash<H>(ivs), MakeHash<H>(ivs + 32)};
 #pragma omp for schedule(static)
       for (size_t k = 0; k < nkeys; ++k) {
         const int4 *s0s = static_cast<const int4 *>(s0s_) + 2 * k;
@@ -102,7 +112,7 @@ struct Ad {
 #pragma omp parallel num_threads(threads > 0 ? threads : 1)
     {
       Holder<Prg> h(p);
-      S s{h.make(), MakeHash(ivs), MakeHash(ivs + 32)};
+      S s{h.make(), MakeHash<H>(ivs), MakeHash<H>(ivs + 32)};
 #pragma omp for schedule(static)
       for (size_t k = 0; k < nkeys; ++k) {
         const Arr4 &cs = static_cast<const Arr4 *>(cs_)[k];
@@ -119,7 +129,7 @@ struct Ad {
   static void Prove(const RefParams *pp, const uint8_t *ivs, size_t nkeys, size_t m, const void *pts_,
       const void *cs_, void *pis_) {
     Holder<Prg> h(*pp);
-    S s{h.make(), MakeHash(ivs), MakeHash(ivs + 32)};
+    S s{h.make(), MakeHash<H>(ivs), MakeHash<H>(ivs + 32)};
     for (size_t k = 0; k < nkeys; ++k) {
       const Arr4 &cs = static_cast<const Arr4 *>(cs_)[k];
       s.Prove(cuda::std::span<const Arr4>(static_cast<const Arr4 *>(pts_) + k * m, m),
@@ -133,7 +143,7 @@ struct Ad {
 #pragma omp parallel num_threads(threads > 0 ? threads : 1)
     {
       Holder<Prg> h(p);
-      S s{h.make(), MakeHash(ivs), MakeHash(ivs + 32)};
+      S s{h.make(), MakeHash<H>(ivs), MakeHash<H>(ivs + 32)};
 #pragma omp for schedule(dynamic, 1)
       for (size_t k = 0; k < nkeys; ++k) {
         const Arr4 &cs = static_cast<const Arr4 *>(cs_)[k];
@@ -154,7 +164,7 @@ struct Ad {
   }
 };
 
-using Table = std::map<std::tuple<int, int, uint64_t, uint64_t, int>, VdpfOps>;
+using Table = std::map<std::tuple<int, int, uint64_t, uint64_t, int, int>, VdpfOps>;
 Table &table() {
   static Table t;
   return t;
@@ -166,29 +176,53 @@ using GU64 = fss::group::Uint<uint64_t>;
 using GU127 = fss::group::Uint<u128, (u128(1) << 127)>;
 using GU64p = fss::group::Uint<uint64_t, 18446744073709551557ull>;
 
-template <int N, class Prg, int prg_tag>
+template <int N, class Prg, int prg_tag, class H, int hash_tag>
 void RegN() {
-  table()[{N, 0, 0, 0, prg_tag}] = Ad<N, GBytes, Prg>::Ops();
-  table()[{N, 3, 0, 0, prg_tag}] = Ad<N, GU32, Prg>::Ops();
-  table()[{N, 4, 0, 0, prg_tag}] = Ad<N, GU64, Prg>::Ops();
-  table()[{N, 5, 0, 0x8000000000000000ull, prg_tag}] = Ad<N, GU127, Prg>::Ops();
-  table()[{N, 4, 18446744073709551557ull, 0, prg_tag}] = Ad<N, GU64p, Prg>::Ops();
+  table()[{N, 0, 0, 0, prg_tag, hash_tag}] = Ad<N, GBytes, Prg, H>::Ops();
+  table()[{N, 3, 0, 0, prg_tag, hash_tag}] = Ad<N, GU32, Prg, H>::Ops();
+  table()[{N, 4, 0, 0, prg_tag, hash_tag}] = Ad<N, GU64, Prg, H>::Ops();
+  table()[{N, 5, 0, 0x8000000000000000ull, prg_tag, hash_tag}] = Ad<N, GU127, Prg, H>::Ops();
+  table()[{N, 4, 18446744073709551557ull, 0, prg_tag, hash_tag}] = Ad<N, GU64p, Prg, H>::Ops();
 }
 template <int N>
 void Reg() {
-  RegN<N, fss::prg::Aes128Mmo<2>, REF_PRG_AES128_MMO>();
-  RegN<N, fss::prg::ChaCha<2>, REF_PRG_CHACHA>();
+  RegN<N, fss::prg::Aes128Mmo<2>, REF_PRG_AES128_MMO, fss::hash::Blake3, 0>();
+  RegN<N, fss::prg::ChaCha<2>, REF_PRG_CHACHA, fss::hash::Blake3, 0>();
+}
+template <int N>
+void RegSha() {  // fewer domains (compile time): the hash plugin does not interact with in_bits
+  RegN<N, fss::prg::Aes128Mmo<2>, REF_PRG_AES128_MMO, fss::hash::Sha256, 1>();
+  RegN<N, fss::prg::ChaCha<2>, REF_PRG_CHACHA, fss::hash::Sha256, 1>();
 }
 
 struct Init {
   Init() {
     Reg<1>(); Reg<3>(); Reg<8>(); Reg<12>(); Reg<16>(); Reg<20>(); Reg<32>(); Reg<40>(); Reg<64>(); Reg<128>();
+    RegSha<1>(); RegSha<8>(); RegSha<12>(); RegSha<32>(); RegSha<64>(); RegSha<128>();
   }
 } g_init;
 
 const VdpfOps *Find(const RefSel *s) {
-  auto it = table().find({s->in_bits, s->group, s->mod_lo, s->mod_hi, s->prg});
+  auto it = table().find({s->in_bits, s->group, s->mod_lo, s->mod_hi, s->prg, s->pad});
   return it == table().end() ? nullptr : &it->second;
+}
+
+// which = 0: XorHash (a, b) -> 64 B; 1: Hash 64 B -> 32 B
+template <class H>
+static int RunHash(const uint8_t *iv, int which, size_t n, const void *msgs, void *out) {
+  H h = MakeHash<H>(iv);
+  for (size_t i = 0; i < n; ++i) {
+    if (which == 0) {
+      const int4 *m = static_cast<const int4 *>(msgs) + 2 * i;
+      auto o = h.Hash(cuda::std::tuple<int4, const int4>{m[0], m[1]});
+      memcpy(static_cast<int4 *>(out) + 4 * i, o.data(), 64);
+    } else {
+      const int4 *m = static_cast<const int4 *>(msgs) + 4 * i;
+      auto o = h.Hash(cuda::std::span<const int4, 4>(m, 4));
+      memcpy(static_cast<int4 *>(out) + 2 * i, o.data(), 32);
+    }
+  }
+  return 0;
 }
 
 }  // namespace
@@ -228,19 +262,10 @@ int ref_vdpf_evalall(const RefSel *sel, const RefParams *p, const uint8_t *ivs, 
 }
 // which = 0: XorHash (a, b) -> 64 B; 1: Hash 64 B -> 32 B   (hash/blake3.cuh:143-171)
 int ref_blake3(const uint8_t *iv, int which, size_t n, const void *msgs, void *out) {
-  fss::hash::Blake3 h = MakeHash(iv);
-  for (size_t i = 0; i < n; ++i) {
-    if (which == 0) {
-      const int4 *m = static_cast<const int4 *>(msgs) + 2 * i;
-      auto o = h.Hash(cuda::std::tuple<int4, const int4>{m[0], m[1]});
-      memcpy(static_cast<int4 *>(out) + 4 * i, o.data(), 64);
-    } else {
-      const int4 *m = static_cast<const int4 *>(msgs) + 4 * i;
-      auto o = h.Hash(cuda::std::span<const int4, 4>(m, 4));
-      memcpy(static_cast<int4 *>(out) + 2 * i, o.data(), 32);
-    }
-  }
-  return 0;
+  return RunHash<fss::hash::Blake3>(iv, which, n, msgs, out);
 }
-
+// the same two interfaces of fss::hash::Sha256 (hash/sha256.cuh:44-89); iv = 16-byte key (+ 16 ignored bytes)
+int ref_sha256(const uint8_t *iv, int which, size_t n, const void *msgs, void *out) {
+  return RunHash<fss::hash::Sha256>(iv, which, n, msgs, out);
+}
 }  // extern "C"

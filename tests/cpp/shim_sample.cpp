@@ -18,6 +18,7 @@
 #include <fss/point_eval_gpu.cuh>
 #include <fss/prg/aes128_mmo.cuh>
 #include <fss/prg/chacha.cuh>
+#include <fss/hash/sha256.cuh>
 #include <fss/vdpf.cuh>
 
 static int g_fail = 0;
@@ -317,9 +318,70 @@ static void VdpfN8() {
   Prg::FreeCtxs(ctxs);
 }
 
+// The same scheme with the reference's second hash plugin, fss::hash::Sha256 (hash/sha256.cuh; host-only there, on the device
+// here), alone and mixed with Blake3, plus known answers of the plugin computed with Python's hashlib.
+template <class HX, class HH>
+static void VdpfHashes(const char *tag, HX xor_hash, HH hash) {
+  using Group = fss::group::Uint<uint64_t>;
+  using Prg = fss::prg::ChaCha<2>;
+  using Vdpf = fss::Vdpf<10, Group, Prg, HX, HH, uint16_t>;
+  static const int nonce[2] = {0x12345678, int(0x9abcdef0u)};
+  Prg prg(nonce);
+  Vdpf vdpf{prg, xor_hash, hash};
+  typename Vdpf::Cw cws[10];
+  cuda::std::array<int4, 4> cs;
+  int4 ocw, seeds[2];
+  int ret, r = 0;
+  do {
+    seeds[0] = {0x11111111 + r, 0x22222222 + r, 0x33333333 + r, 0x44444440 + r};
+    seeds[1] = {0x55555555 + r, 0x66666666 + r, 0x77777777 + r, int(0x88888880u) + r};
+    ret = vdpf.Gen(cws, cs, ocw, cuda::std::span<const int4, 2>(seeds, 2), 777, kBeta);
+    ++r;
+  } while (ret != 0 && r < 64);
+  EXPECT(ret == 0, tag);
+  const auto cwspan = cuda::std::span<const typename Vdpf::Cw>(cws, 10);
+  const auto csspan = cuda::std::span<const int4, 4>(cs);
+  std::vector<int4> ys0(1024), ys1(1024);
+  cuda::std::array<int4, 4> qa, qb;
+  vdpf.EvalAll(false, seeds[0], cwspan, csspan, ocw, cuda::std::span<int4>(ys0), qa);
+  vdpf.EvalAll(true, seeds[1], cwspan, csspan, ocw, cuda::std::span<int4>(ys1), qb);
+  int bad = 0;
+  const int4 want = Group::From(kBeta).Into();
+  for (int x = 0; x < 1024; ++x) bad += !Eq(Add<Group>(ys0[x], ys1[x]), x == 777 ? want : kZero);
+  EXPECT(bad == 0, tag);
+  EXPECT(Vdpf::Verify(cuda::std::span<const int4, 4>(qa), cuda::std::span<const int4, 4>(qb)), tag);
+  int4 y;
+  auto pt = vdpf.Eval(false, seeds[0], cwspan, csspan, ocw, 777, y);
+  EXPECT(Eq(y, ys0[777]), tag);
+  cws[4].s.y ^= 8;
+  vdpf.EvalAll(true, seeds[1], cwspan, csspan, ocw, cuda::std::span<int4>(ys1), qb);
+  EXPECT(!Vdpf::Verify(cuda::std::span<const int4, 4>(qa), cuda::std::span<const int4, 4>(qb)), tag);
+  (void)pt;
+}
+static void VdpfSha256() {
+  using S = fss::hash::Sha256;
+  using B = fss::hash::Blake3;
+  const int4 key = {0x12345678, int(0x9abcdef0u), 0x13572468, 0x2468ace0};
+  const int4 iv[2] = {{int(0x0fedcba9u), int(0x87654321u), 0x2468ace0, 0x13572468}, {5, 6, 7, 8}};
+  S sha(key);
+  // hashlib.sha256(key || msg) and the two digests of (a, b), words little-endian
+  const int4 msg[4] = {{1, 2, 3, 4}, {5, 6, 7, 8}, {9, 10, 11, 12}, {13, 14, 15, 16}};
+  auto h = sha.Hash(cuda::std::span<const int4, 4>(msg, 4));
+  const uint32_t want_h[8] = {0xf045bcdfu, 0x57a787deu, 0xdc80996fu, 0xc989b531u, 0x0036c49cu, 0x2c667c7du, 0x8452b952u, 0x8f54d914u};
+  EXPECT(std::memcmp(h.data(), want_h, 32) == 0, "Sha256::Hash(64 B) == hashlib");
+  auto x4 = sha.Hash(cuda::std::tuple<int4, const int4>(int4{1, 2, 3, 5}, msg[1]));  // a's lsb is overwritten: 4 and 5
+  const uint32_t want_x[16] = {0x4e9d17d5u, 0x3f300836u, 0x880bfb60u, 0x16f8a5d0u, 0x321211efu, 0x9d7bcd2bu, 0xc4a1f849u, 0xc980a395u,
+                               0xd1ee6fa3u, 0x16d749f6u, 0x49e83e72u, 0x75db73e7u, 0xcdcc72acu, 0x571697f3u, 0x1ecf46bfu, 0x5557a2ffu};
+  EXPECT(std::memcmp(x4.data(), want_x, 64) == 0, "Sha256::Hash(a, b) == hashlib");
+  VdpfHashes("vdpf<Sha256, Sha256>", S(key), S(int4{9, 8, 7, 6}));
+  VdpfHashes("vdpf<Sha256, Blake3>", S(key), B(cuda::std::span<const int4, 2>(iv, 2)));
+  VdpfHashes("vdpf<Blake3, Sha256>", B(cuda::std::span<const int4, 2>(iv, 2)), S(key));
+}
+
 int main() {
   try {
     VdpfN8();
+    VdpfSha256();
     DpfN8();
     DcfN64();
     HalfTreeAndGrotto();

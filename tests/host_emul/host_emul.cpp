@@ -74,6 +74,8 @@ static void make_ctx(const fssb200_params &p, EmuCtx &c) {
   }
   std::memcpy(c.keys.hash_key, q.hash_key, 16);
   std::memcpy(c.keys.hash_iv, q.hash_iv, 64);
+  c.keys.hash_kind[0] = uint32_t(q.hash) & 0xffu;
+  c.keys.hash_kind[1] = (uint32_t(q.hash) >> 8) & 0xffu;
   c.ga.mod[0] = uint32_t(q.mod_lo); c.ga.mod[1] = uint32_t(q.mod_lo >> 32);
   c.ga.mod[2] = uint32_t(q.mod_hi); c.ga.mod[3] = uint32_t(q.mod_hi >> 32);
 }
@@ -332,8 +334,8 @@ int emul_hash(const fssb200_params *p, int which, size_t n, const void *msgs, vo
   const blk *m = static_cast<const blk *>(msgs);
   blk *o = static_cast<blk *>(out);
   for (size_t i = 0; i < n; ++i) {
-    if (which == 0) b3_xor_hash(c.keys.hash_iv[0], m[2 * i], m[2 * i + 1], o + 4 * i);
-    else b3_hash(c.keys.hash_iv[1], m + 4 * i, o + 2 * i);
+    if (which == 0) vdpf_xor_hash(c.keys, m[2 * i], m[2 * i + 1], o + 4 * i);
+    else vdpf_hash(c.keys, m + 4 * i, o + 2 * i);
   }
   return 0;
 }

@@ -43,8 +43,10 @@ def draw_params(r: random.Random) -> Params:
             mod = (1 << w) - r.choice([1, 3, 5, 59, 189])  # just below the top
         else:
             mod = r.randrange(2, 1 << min(w, 20))      # small, even or odd
+    hashes = (r.choice(["blake3", "sha256"]), r.choice(["blake3", "sha256"])) if scheme == "vdpf" else ("blake3", "blake3")
     return Params(scheme=scheme, in_bits=n, group=group, mod=mod, prg=r.choice(["aes128_mmo", "chacha"]),
-                  pred=r.choice(["lt", "gt"]) if scheme == "dcf" else "lt", hash_key=HASH_KEY_BENCH, in_bytes=in_bytes)
+                  pred=r.choice(["lt", "gt"]) if scheme == "dcf" else "lt", hash_key=HASH_KEY_BENCH, in_bytes=in_bytes,
+                  hash=hashes)
 
 
 def draw_inputs(r: random.Random, p: Params, nkeys: int):
@@ -80,7 +82,7 @@ def run_vdpf(r, orc, dev, tag, p, s0s, alphas, betas, xs):
     """vdpf.cuh Gen / Eval (+ the proof tuples) / BatchProve inputs, device and host arrays."""
     import fss_b200
     ctx = fss_b200.Context("vdpf", p.in_bits, p.group, mod=p.mod, prg=p.prg, prg_key=p.prg_key, in_bytes=p.in_bytes,
-                           hash_iv=bytes(p.hash_iv))
+                           hash_iv=bytes(p.hash_iv), hash=p.hash)
     want = orc.vdpf_gen(p, s0s, alphas, betas, threads=8)
     got = ctx.vdpf_gen(T(s0s, dev), alphas, T(betas, dev))
     for u, v in zip(want, got):

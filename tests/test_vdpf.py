@@ -26,7 +26,7 @@ class VCase:
         self.meta, self.name = meta, meta["name"]
         self.p = Params(scheme="vdpf", in_bits=meta["in_bits"], group=meta["group"], mod=int(meta["mod"]),
                         prg=meta["prg"], prg_key=bytes.fromhex(meta["prg_key"]), in_bytes=meta["in_bytes"],
-                        hash_iv=bytes.fromhex(meta["hash_iv"]))
+                        hash_iv=bytes.fromhex(meta["hash_iv"]), hash=meta.get("hash", "blake3"))
         self.alphas = [int(a) for a in meta["alphas"]]
         self.xs = [int(x) for x in meta["xs"]]
         self._a = arrays
@@ -37,10 +37,13 @@ class VCase:
 
 @pytest.fixture(scope="module")
 def vgolden():
-    with open(os.path.join(HERE, "golden", "golden_vdpf_v1.json")) as f:
-        man = json.load(f)
-    arrays = np.load(os.path.join(HERE, "golden", "golden_vdpf_v1.npz"))
-    return arrays, [VCase(m, arrays) for m in man["cases"]]
+    arrays, cases = {}, []
+    for stem in ("golden_vdpf_v1", "golden_vdpf_sha256_v1"):   # XorHash = Hash = Blake3 / Sha256
+        with open(os.path.join(HERE, "golden", stem + ".json")) as f:
+            man = json.load(f)
+        arrays.update(np.load(os.path.join(HERE, "golden", stem + ".npz")))
+        cases += [VCase(m, arrays) for m in man["cases"]]
+    return arrays, cases
 
 
 def sha(a):
@@ -49,11 +52,33 @@ def sha(a):
 
 # ---- CPU: the checker itself -----------------------------------------------------------------------------------
 
-def test_oracle_blake3_vs_golden(orc, vgolden):
+HASH_KEYS = (("blake3", "hash"), ("sha256", "hash_sha256"))   # plugin, key prefix of its known answers
+
+
+def test_oracle_hashes_vs_golden(orc, vgolden):
     arrays, _ = vgolden
-    p = Params(scheme="vdpf", in_bits=8)
-    assert np.array_equal(orc.hash(p, 0, arrays["hash/xor_in"]), arrays["hash/xor_out"])
-    assert np.array_equal(orc.hash(p, 1, arrays["hash/hash_in"]), arrays["hash/hash_out"])
+    for name, pre in HASH_KEYS:
+        p = Params(scheme="vdpf", in_bits=8, hash=name)
+        assert np.array_equal(orc.hash(p, 0, arrays[pre + "/xor_in"]), arrays[pre + "/xor_out"]), name
+        assert np.array_equal(orc.hash(p, 1, arrays[pre + "/hash_in"]), arrays[pre + "/hash_out"]), name
+
+
+def test_oracle_sha256_vs_hashlib(orc):
+    """hash/sha256.cuh:44-89 restated with hashlib: SHA-256(key || msg), and the two digests of (a lsb 0 / 1, b)."""
+    p = Params(scheme="vdpf", in_bits=8, hash="sha256")
+    key0, key1 = bytes(p.hash_iv)[:16], bytes(p.hash_iv)[32:48]
+    rng = np.random.default_rng(5)
+    msgs = rng.integers(0, 2 ** 32, size=(40, 4, 4), dtype=np.uint64).astype(np.uint32)
+    out = orc.hash(p, 1, msgs)
+    ab = rng.integers(0, 2 ** 32, size=(40, 2, 4), dtype=np.uint64).astype(np.uint32)
+    outx = orc.hash(p, 0, ab)
+    for i in range(40):
+        assert out[i].tobytes() == hashlib.sha256(key1 + msgs[i].tobytes()).digest()
+        a0, a1 = ab[i, 0].copy(), ab[i, 0].copy()
+        a0[3] &= 0xFFFFFFFE
+        a1[3] |= 1
+        assert outx[i].tobytes() == hashlib.sha256(key0 + a0.tobytes() + ab[i, 1].tobytes()).digest() + \
+            hashlib.sha256(key0 + a1.tobytes() + ab[i, 1].tobytes()).digest()
 
 
 def test_oracle_vs_golden(orc, vgolden):
@@ -83,10 +108,11 @@ def test_oracle_vs_golden(orc, vgolden):
 @pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (needs /root/reference)")
 def test_oracle_vs_compiled_reference(orc):
     ref = Ref()
-    for n in (1, 3, 8, 12, 32, 64, 128):
+    for n, hname in [(n, "blake3") for n in (1, 3, 8, 12, 32, 64, 128)] + [(n, "sha256") for n in (1, 8, 12, 32, 64, 128)]:
         for (g, mod) in GROUPS:
             for prg in ("aes128_mmo", "chacha"):
-                p = Params(scheme="vdpf", in_bits=n, group=g, mod=mod, prg=prg)
+                p = Params(scheme="vdpf", in_bits=n, group=g, mod=mod, prg=prg, hash=hname)
+                assert ref.vdpf_supported(p), p
                 s0s, alphas, betas, xs = synth_inputs(p, 12, seed=n * 5 + len(g))
                 a, b = orc.vdpf_gen(p, s0s, alphas, betas), ref.vdpf_gen(p, s0s, alphas, betas, threads=2)
                 for u, v in zip(a, b):
@@ -105,8 +131,8 @@ def test_oracle_vs_compiled_reference(orc):
 def test_vdpf_properties(orc):
     """src/vdpf_test.cu: shares reconstruct the point function, honest proofs verify, a flipped
     correction word is rejected."""
-    for (g, mod) in GROUPS:
-        p = Params(scheme="vdpf", in_bits=10, group=g, mod=mod)
+    for (g, mod), hname in zip(GROUPS * 2, ["blake3"] * 5 + ["sha256", ("sha256", "blake3"), ("blake3", "sha256"), "sha256", "sha256"]):
+        p = Params(scheme="vdpf", in_bits=10, group=g, mod=mod, hash=hname)
         s0s, alphas, betas, _ = synth_inputs(p, 3, seed=9)
         cws, cs, ocws, status = orc.vdpf_gen(p, s0s, alphas, betas)
         assert not status.any()
@@ -136,16 +162,17 @@ def emu():
 
 def test_kernel_bodies_match_oracle(emu, orc, vgolden):
     arrays, _ = vgolden
-    p0 = Params(scheme="vdpf", in_bits=8)
-    cp = p0.c()
-    for which, key_in, key_out, shape in ((0, "hash/xor_in", "hash/xor_out", (4, 4)), (1, "hash/hash_in", "hash/hash_out", (2, 4))):
-        out = np.zeros((len(arrays[key_in]),) + shape, np.uint32)
-        emu.emul_hash(C.byref(cp), which, C.c_size_t(len(out)), _vp(np.ascontiguousarray(arrays[key_in])), _vp(out))
-        assert np.array_equal(out, arrays[key_out])
+    for hname, pre in HASH_KEYS:
+        cp = Params(scheme="vdpf", in_bits=8, hash=hname).c()
+        for which, key_in, key_out, shape in ((0, "/xor_in", "/xor_out", (4, 4)), (1, "/hash_in", "/hash_out", (2, 4))):
+            out = np.zeros((len(arrays[pre + key_in]),) + shape, np.uint32)
+            emu.emul_hash(C.byref(cp), which, C.c_size_t(len(out)), _vp(np.ascontiguousarray(arrays[pre + key_in])), _vp(out))
+            assert np.array_equal(out, arrays[pre + key_out]), hname
     for n in (1, 2, 5, 8, 12, 32, 33, 64, 65, 128):
-        for (g, mod) in GROUPS:
+        for gi, (g, mod) in enumerate(GROUPS):
             for prg in ("aes128_mmo", "chacha"):
-                p = Params(scheme="vdpf", in_bits=n, group=g, mod=mod, prg=prg)
+                hname = ("blake3", "sha256", ("sha256", "blake3"), ("blake3", "sha256"))[(n + gi) % 4]
+                p = Params(scheme="vdpf", in_bits=n, group=g, mod=mod, prg=prg, hash=hname)
                 k = 40
                 s0s, alphas, betas, xs = synth_inputs(p, k, seed=n + len(g))
                 xs[1], xs[2] = 0, (1 << n) - 1
@@ -198,15 +225,16 @@ def _n(t):
 def _ctx(p):
     import fss_b200
     return fss_b200.Context("vdpf", p.in_bits, p.group, mod=p.mod, prg=p.prg, prg_key=p.prg_key, in_bytes=p.in_bytes,
-                            hash_iv=bytes(p.hash_iv))
+                            hash_iv=bytes(p.hash_iv), hash=p.hash)
 
 
 @pytest.mark.gpu
-def test_gpu_blake3(dev, vgolden):
+def test_gpu_hashes(dev, vgolden):
     arrays, _ = vgolden
-    ctx = _ctx(Params(scheme="vdpf", in_bits=8))
-    assert np.array_equal(_n(ctx.hash(0, _t(arrays["hash/xor_in"], dev))), arrays["hash/xor_out"])
-    assert np.array_equal(_n(ctx.hash(1, _t(arrays["hash/hash_in"], dev))), arrays["hash/hash_out"])
+    for hname, pre in HASH_KEYS:
+        ctx = _ctx(Params(scheme="vdpf", in_bits=8, hash=hname))
+        assert np.array_equal(_n(ctx.hash(0, _t(arrays[pre + "/xor_in"], dev))), arrays[pre + "/xor_out"]), hname
+        assert np.array_equal(_n(ctx.hash(1, _t(arrays[pre + "/hash_in"], dev))), arrays[pre + "/hash_out"]), hname
 
 
 @pytest.mark.gpu
@@ -236,14 +264,17 @@ def test_gpu_golden(dev, vgolden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("hname", ["blake3", "sha256", ("sha256", "blake3"), ("blake3", "sha256")])
 @pytest.mark.parametrize("n,group,mod,prg,nkeys", [
     (32, "bytes", 0, "aes128_mmo", 3000), (32, "u64", 0, "chacha", 1500), (64, "u128", 0, "aes128_mmo", 1031),
     (20, "u32", 0, "aes128_mmo", 777), (128, "u64", 18446744073709551557, "aes128_mmo", 257), (1, "bytes", 0, "chacha", 33),
     (33, "u64", 0, "aes128_mmo", 100),
 ])
-def test_gpu_random_batches(dev, orc, n, group, mod, prg, nkeys):
+def test_gpu_random_batches(dev, orc, n, group, mod, prg, nkeys, hname):
     import torch
-    p = Params(scheme="vdpf", in_bits=n, group=group, mod=mod, prg=prg)
+    if not isinstance(hname, str) and n not in (32, 1):
+        pytest.skip("mixed hash pairs: two shapes are enough")
+    p = Params(scheme="vdpf", in_bits=n, group=group, mod=mod, prg=prg, hash=hname)
     ctx = _ctx(p)
     s0s, alphas, betas, xs = synth_inputs(p, nkeys, seed=n + nkeys)
     xs[1], xs[2] = 0, (1 << n) - 1
@@ -276,7 +307,7 @@ def test_gpu_random_batches(dev, orc, n, group, mod, prg, nkeys):
                                               (14, "u128", "aes128_mmo", 2), (18, "bytes", "aes128_mmo", 1)])
 def test_gpu_evalall_and_tamper(dev, orc, n, group, prg, nkeys):
     import torch
-    p = Params(scheme="vdpf", in_bits=n, group=group, prg=prg)
+    p = Params(scheme="vdpf", in_bits=n, group=group, prg=prg, hash="sha256" if n in (3, 14) else "blake3")
     ctx = _ctx(p)
     s0s, alphas, betas, _ = synth_inputs(p, nkeys, seed=n)
     cws, cs, ocws, status = ctx.vdpf_gen(_t(s0s, dev), alphas, _t(betas, dev))
@@ -318,7 +349,7 @@ def test_gpu_evalall_lanes_per_key(dev, orc, monkeypatch, lanes):
     oracle -- ragged key groups in the last warp, domains smaller and larger than LPK, both parties."""
     monkeypatch.setenv("FSSB200_VDPF_FINISH_LANES", str(lanes))
     for n, group, nkeys in ((6, "u64", 37), (3, "bytes", 5), (1, "u32", 67), (9, "u128", 130)):
-        p = Params(scheme="vdpf", in_bits=n, group=group)
+        p = Params(scheme="vdpf", in_bits=n, group=group, hash="sha256" if n in (6, 1) else "blake3")
         ctx = _ctx(p)
         s0s, alphas, betas, _ = synth_inputs(p, nkeys, seed=lanes * 100 + n)
         cws, cs, ocws, _ = orc.vdpf_gen(p, s0s, alphas, betas, threads=4)
