@@ -125,6 +125,10 @@ int host_thread_budget() {
   int lws = env_int("LOCAL_WORLD_SIZE", 1);
   if (lws < 1) lws = 1;
   int t = usable_cpus() / lws;
+  // Several ranks on one host: leave two CPUs of the share to the rank's other busy threads (its submitter, the
+  // framework's) -- measured with 2 ranks on 24 CPUs, barrier-synchronised steps: 12 threads per rank 75.4 ms, 10 threads
+  // 68.0 ms, 8 69.2, 6 69.9, 4 74.3 (profiles/r02_host_pipeline.md).  One rank: every CPU helps (16: 46.7, 14: 46.6-48.7, 12: 51.7).
+  if (lws >= 2 && t > 4) t -= 2;
   if (t > 32) t = 32;
   t = env_int("FSSB200_PACK_THREADS", t);
   return t < 0 ? 0 : t;
@@ -1252,7 +1256,7 @@ int fssb200_eval_host_multi(fssb200_ctx *const *ctxs, int ndev, int party, const
     for (auto &t : th) t.join();
     for (int d = 0; d < ndev; ++d) rc[size_t(d)] = first[size_t(d)].load();
   } else {
-    const int share = crew ? std::max(1, crew->workers() / ndev) : 0;
+    const int share = crew ? std::max(1, crew->workers() / ndev - (ndev >= 2 ? 1 : 0)) : 0;  // (a CPU per device for its submitter)
     const size_t base = nkeys / size_t(ndev), rem = nkeys % size_t(ndev);
     auto run = [&](int d) {
       const size_t k0 = size_t(d) * base + std::min<size_t>(size_t(d), rem), k = base + (size_t(d) < rem ? 1 : 0);

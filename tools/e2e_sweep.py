@@ -86,7 +86,7 @@ def main():
             env = dict(os.environ)
             if t != "0":
                 env["FSSB200_PACK_THREADS"] = t
-            cfgs = base + (tune if i == 0 else [])
+            cfgs = base + (tune if i == 0 and args.tune != "none" else [])
             r = subprocess.run([sys.executable, __file__, "--child", "--configs", json.dumps(cfgs), "--keys", str(args.keys),
                                 "--steps", str(args.steps)], env=env, capture_output=True, text=True)
             f.write(r.stdout)
