@@ -92,6 +92,27 @@ if not only or "vdpf" in only:
     assert torch.equal(pa0, pa1)
     print("ok vdpf", flush=True)
 
+if not only or "vdpf2" in only:
+    # SHA-256 hash plugins and a narrow lanes-per-key variant of the finish kernel (ragged key groups in the last warp)
+    os.environ["FSSB200_VDPF_FINISH_LANES"] = "4"
+    for hname, n, nk in (("sha256", 6, 37), (("blake3", "sha256"), 9, 130)):
+        p = Params(scheme="vdpf", in_bits=n, group="u64", hash=hname)
+        ctx = fss_b200.Context("vdpf", n, "u64", prg_key=p.prg_key, hash_iv=bytes(p.hash_iv), hash=hname)
+        s0s, alphas, betas, xs = synth_inputs(p, nk, seed=n)
+        want = orc.vdpf_gen(p, s0s, alphas, betas, threads=4)
+        got = ctx.vdpf_gen(t(s0s), alphas, t(betas))
+        for u, v in zip(want[:3], got[:3]):
+            same(f"vdpf gen {hname}", v, u)
+        wy, wp = orc.vdpf_eval(p, 1, s0s[:, 1], want[0], want[1], want[2], xs, threads=4)
+        ys, pis = ctx.vdpf_eval(1, t(s0s[:, 1]), got[0], got[1], got[2], xs)
+        same(f"vdpf eval {hname}", ys, wy)
+        same(f"vdpf eval proofs {hname}", pis, wp)
+        way, wpa = orc.vdpf_evalall(p, 0, s0s[:, 0], want[0], want[1], want[2], threads=4)
+        ya, pa = ctx.vdpf_eval_all(0, t(s0s[:, 0]), got[0], got[1], got[2])
+        same(f"vdpf evalall {hname}", ya, way)
+        same(f"vdpf evalall proofs {hname}", pa, wpa)
+    os.environ.pop("FSSB200_VDPF_FINISH_LANES")
+
 if not only or "host" in only:
     p = Params(scheme="dpf", in_bits=32)
     s0s, alphas, betas, xs = synth_inputs(p, 3000, seed=9)
