@@ -25,20 +25,29 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int make_rows_tensor_map(uint8_t out[128], const void *rows, size_t nkeys, size_t row_bytes);
-int make_cw_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, int ncw) {
-  return make_rows_tensor_map(out, cws, nkeys, size_t(ncw) * 32u);
-}
-// 2-D byte tensor [nkeys][row_bytes], box 32 rows x 64 B, SWIZZLE_64B (CwTileT / CwTileOut in kernels.cuh)
-int make_rows_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, size_t row_bytes) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+// cuTensorMapEncodeTiled, resolved once through the runtime (no link-time dependency on libcuda)
+static int encode_tiled_fn(EncodeTiledFn *out) {
+  static std::atomic<EncodeTiledFn> fn{nullptr};
+  EncodeTiledFn f = fn.load(std::memory_order_acquire);
+  if (!f) {
     void *p = nullptr;
     cudaDriverEntryPointQueryResult q;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
     if (e != cudaSuccess) return int(e);
     if (q != cudaDriverEntryPointSuccess || !p) return int(cudaErrorNotSupported);
-    fn = reinterpret_cast<EncodeTiledFn>(p);
+    f = reinterpret_cast<EncodeTiledFn>(p);
+    fn.store(f, std::memory_order_release);
   }
+  *out = f;
+  return 0;
+}
+int make_cw_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, int ncw) {
+  return make_rows_tensor_map(out, cws, nkeys, size_t(ncw) * 32u);
+}
+// 2-D byte tensor [nkeys][row_bytes], box 32 rows x 64 B, SWIZZLE_64B (CwTileT / CwTileOut in kernels.cuh)
+int make_rows_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, size_t row_bytes) {
+  EncodeTiledFn fn = nullptr;
+  if (int rc = encode_tiled_fn(&fn)) return rc;
   static_assert(sizeof(CUtensorMap) == 128, "PointArgs::tmap size");
   alignas(64) CUtensorMap m;
   const cuuint64_t gdim[2] = {cuuint64_t(row_bytes), cuuint64_t(nkeys)};
@@ -47,6 +56,23 @@ int make_rows_tensor_map(uint8_t out[128], const void *cws, size_t nkeys, size_t
   const cuuint32_t estride[2] = {1u, 1u};
   const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(cws), gdim, gstride, box, estride,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return int(cudaErrorInvalidValue);
+  std::memcpy(out, &m, 128);
+  return 0;
+}
+
+// Level-major array [nlevels][nkeys] of 16-byte entries as a 2-D uint32 tensor, box = 32 keys x box_levels (CwLmTile)
+int make_lm_tensor_map(uint8_t out[128], const void *base, size_t nkeys, int nlevels, int box_levels) {
+  EncodeTiledFn fn = nullptr;
+  if (int rc = encode_tiled_fn(&fn)) return rc;
+  alignas(64) CUtensorMap m;
+  const cuuint64_t gdim[2] = {cuuint64_t(nkeys) * 4u, cuuint64_t(nlevels)};
+  const cuuint64_t gstride[1] = {cuuint64_t(nkeys) * 16u};
+  const cuuint32_t box[2] = {128u, cuuint32_t(box_levels)};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), gdim, gstride, box, estride,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return int(cudaErrorInvalidValue);
   std::memcpy(out, &m, 128);
@@ -87,7 +113,7 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
   cfg.stream = s;
   if (c->p.prg == FSSB200_PRG_AES128_MMO) {
     const unsigned threads = mode == 1 ? 1024u : (mode >= 5 ? 768u : unsigned(kPointThreads));
-    const uint64_t want = (n + threads - 1) / threads;
+    const uint64_t want = (n + 31) / 32;  // one CTA per SM as soon as there is a tile of 32 keys for each (tiles interleave over CTAs)
     cfg.grid = dim3(unsigned(want < uint64_t(c->sm_count) ? (want ? want : 1) : c->sm_count));
     cfg.block = dim3(threads);
     cfg.smem = kMaxDynSmem;
@@ -316,7 +342,13 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   if (scheme != FSSB200_SCHEME_GROTTO && !aligned16(ys)) return FSSB200_EALIGN;  // Grotto: bool ys[nkeys]
   if (reinterpret_cast<uintptr_t>(xs) % c->p.in_bytes) return FSSB200_EALIGN;
   if (nkeys == 0) return 0;
-  const int mode = level_major ? 2 : (packed ? 6 : c->point_mode);
+  // level-major: the TMA tiles of mode 7 (profiles/r02_levelmajor_tma.md) unless the batch does not fit 32-bit tensor
+  // coordinates (key * 4) or FSSB200_LM_MODE=2 asks for the direct loads of mode 2 (A/B runs)
+  static const int lm_mode = [] {
+    const char *e = std::getenv("FSSB200_LM_MODE");
+    return (e && std::atoi(e) == 2) ? 2 : 7;
+  }();
+  const int mode = level_major ? ((nkeys >> 28) ? 2 : lm_mode) : (packed ? 6 : c->point_mode);
   point_launch_fn fn = get_point_launcher(scheme, c->gk, c->p.prg, mode);
   if (!fn) return FSSB200_EGROUP;
   DeviceGuard g(c->p.device);
@@ -339,7 +371,12 @@ static int eval_impl(const fssb200_ctx *cc, int want_scheme, int party, const vo
   a.in_bytes = c->p.in_bytes;
   a.party = party;
   a.vmask = c->vmask;
-  if (mode >= 4) {
+  if (mode == 7) {
+    const bool dcf = scheme == FSSB200_SCHEME_DCF;
+    if (int rc = make_lm_tensor_map(a.tmap, cw_s, nkeys, c->p.in_bits, dcf ? 2 : 4)) return rc;
+    if (dcf)
+      if (int rc = make_lm_tensor_map(a.tmap2, cw_v, nkeys, c->p.in_bits, 2)) return rc;
+  } else if (mode >= 4) {
     if (nkeys >> 31) return FSSB200_EINVAL;  // TMA coordinates are 32-bit
     if (int rc = make_rows_tensor_map(a.tmap, cws, nkeys, mode == 6 ? size_t(c->ncw) * 16u + 16u : size_t(c->ncw) * 32u))
       return rc;

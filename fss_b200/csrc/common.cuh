@@ -100,6 +100,9 @@ struct PointArgs {
   // CUtensorMap of the key-major Cw array as a 2-D byte tensor [nkeys][ncw*32], box 32 keys x 64 B,
   // SWIZZLE_64B (point modes 4 / 5: correction words fetched by the TMA unit); opaque here
   alignas(64) uint8_t tmap[128];
+  // point mode 7 (level-major arrays through the TMA unit): tmap = cw_s as a 2-D uint32 tensor [n][nkeys*4], box 4 levels
+  // (DCF: 2) x 32 keys; tmap2 = cw_v likewise (DCF only)
+  alignas(64) uint8_t tmap2[128];
 };
 
 struct GenArgs {

@@ -251,6 +251,79 @@ struct CwTileT {
 };
 typedef CwTileT<false> CwTile;
 
+// ---- level-major arrays fetched by the TMA unit (point mode 7, fssb200_eval_levelmajor) -----------------------------------
+// The level-major layout of fssb200_relayout (the reference's GPU layout, point_eval_gpu.cuh:39-91) keeps level i of all keys
+// contiguous: cw_s[i][key] (16 B), DCF also cw_v[i][key], the control bits bit-packed in `extra`.  Mode 2 reads it with
+// per-level global loads next to the AES code (0.919 of the LDS ceiling: latency and scoreboard slots, not wavefronts).
+// Here the arrays are 2-D uint32 tensors [n][nkeys * 4] and one `cp.async.bulk.tensor.2d` per warp and chunk brings the
+// next 4 levels (DCF: 2 levels of s and of v, two requests) of the warp's 32 keys into the same double-buffered 2 KB tile
+// as CwTile: rows of 512 contiguous bytes, lane = key reads conflict-free without a swizzle, the control bits travel in
+// registers (one word per 32 levels, loaded per tile), 4 shared-memory wavefronts per level and no per-level flag read.
+// Levels past the array (the chunk that holds "entry n" of the key-major walk) are zero-filled by the hardware, so the
+// chunk sequence is the key-major one and the scheme bodies need no change.
+template <bool DCF>
+struct CwLmTile {
+  static constexpr uint32_t kBuf = 2048u;
+  static constexpr uint32_t kWarpBytes = 2u * kBuf;
+  static constexpr int kLpcBits = DCF ? 1 : 2;  // log2(levels per chunk)
+  uint32_t buf, mbar;
+  const void *tmap_s, *tmap_v;
+  uint32_t lane;
+  int key0, next_key0;  // first key of this tile / of the warp's next tile (-1: none)
+  int nchunks;
+  uint32_t *seq;
+  blk fl;               // this key's control bits (not DCF)
+  const blk *out_cw;    // this key's output correction word
+  static FSS_D void issue(const void *tmap_s, const void *tmap_v, uint32_t buf, uint32_t mbar, uint32_t q, int c, int key0) {
+    const uint32_t b = q & 1u, mb = mbar + 8u * b;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(kBuf) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            buf + b * kBuf),
+        "l"(tmap_s), "r"(key0 * 4), "r"(c << kLpcBits), "r"(mb)
+        : "memory");
+    if (DCF)
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+              buf + b * kBuf + 1024u),
+          "l"(tmap_v), "r"(key0 * 4), "r"(c << kLpcBits), "r"(mb)
+          : "memory");
+  }
+  FSS_D void begin_level(int j) const {
+    if (j & ((1 << kLpcBits) - 1)) return;
+    const int c = j >> kLpcBits;
+    const uint32_t q = *seq;
+    __syncwarp();  // every lane is done with chunk q-1, whose buffer the next request overwrites
+    if (lane == 0) {
+      if (c + 1 < nchunks) issue(tmap_s, tmap_v, buf, mbar, q + 1u, c + 1, key0);
+      else if (next_key0 >= 0) issue(tmap_s, tmap_v, buf, mbar, q + 1u, 0, next_key0);
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FSS_LMTILE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra FSS_LMTILE_WAIT;\n"
+        "}\n" ::"r"(mbar + 8u * (q & 1u)),
+        "r"((q >> 1) & 1u)
+        : "memory");
+    *seq = q + 1u;
+  }
+  FSS_D void done_level(int) const {}
+  FSS_D uint32_t at(int j, uint32_t h) const {
+    const uint32_t b = (*seq - 1u) & 1u;
+    return buf + b * kBuf + (DCF ? h * 1024u + (uint32_t(j) & 1u) * 512u : (uint32_t(j) & 3u) * 512u) + lane * 16u;
+  }
+  FSS_D blk s(int j) const { return lds_blk(at(j, 0)); }
+  FSS_D blk v(int j) const { return lds_blk(at(j, 1)); }
+  FSS_D uint32_t flag(int j) const {
+    const uint32_t w = j < 64 ? (j < 32 ? fl.x : fl.y) : (j < 96 ? fl.z : fl.w);
+    return (w >> (uint32_t(j) & 31u)) & 1u;
+  }
+  FSS_D blk out_s(int) const { return ld_blk(out_cw); }
+  FSS_D blk out_v(int) const { return ld_blk(out_cw); }
+};
+
 // ---- batched point evaluation --------------------------------------------------------------------------------
 // One key per thread; warps own tiles of 32 consecutive keys (grid-stride over tiles).
 // SCHEME: FSSB200_SCHEME_{DPF,DCF,HALFTREE,VDPF}, or GROTTO = the O(n) Grotto point walk (schemes.cuh).
@@ -261,13 +334,15 @@ typedef CwTileT<false> CwTile;
 //       4 = key-major, TMA tiles (CwTile), 512 threads
 //       5 = key-major, TMA tiles (CwTile), 768 threads (<= 85 regs)
 //       6 = packed rows (fssb200_pack_rows / fssb200_eval_packed), TMA tiles, 768 threads; DPF / Half-Tree only
-constexpr int kPointModes = 7;
+//       7 = level-major arrays, TMA tiles (CwLmTile), 768 threads
+constexpr int kPointModes = 8;
 template <int MODE>
 struct PointMode {
   static constexpr int kMaxThreads = MODE == 1 ? 1024 : (MODE >= 5 ? 768 : 512);
   static constexpr int kL = MODE == 1 ? 2 : 4;
   static constexpr bool kStaged = MODE <= 1;
-  static constexpr bool kTma = MODE >= 4;
+  static constexpr bool kTma = MODE >= 4 && MODE <= 6;
+  static constexpr bool kLmTma = MODE == 7;
 };
 
 template <int SCHEME, int G, int PRG, class Cw>
@@ -309,7 +384,10 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
   }
   const uint64_t ntiles = (A.nkeys + 31) >> 5;
   const uint64_t tile_stride = uint64_t(gridDim.x) * nwarps;
-  const uint64_t tile0 = uint64_t(blockIdx.x) * nwarps + wid;
+  // Warp w of CTA b takes tiles w * gridDim + b, + tile_stride, ...: consecutive tiles go to DIFFERENT SMs, so a batch that
+  // does not fill every warp (a 2^16-key chunk of the host pipeline = 2048 tiles for 3552 warps) and the last, partial round
+  // of any batch load all SMs evenly instead of filling the first CTAs (the kernels are bound by each SM's lookup pipe).
+  const uint64_t tile0 = uint64_t(wid) * gridDim.x + blockIdx.x;
   uint32_t tma_seq = 0;
   if (PM::kTma) {
     mbar = sp.alloc(16u * nwarps, false) + 16u * wid;
@@ -319,6 +397,16 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
     }
     CwTile::init_barriers(mbar, lane);
     if (lane == 0 && tile0 < ntiles) CwTile::issue(A.tmap, slab, mbar, 0u, 0, int(tile0 * 32));
+  }
+  typedef CwLmTile<SCHEME == FSSB200_SCHEME_DCF> LmTile;
+  if (PM::kLmTma) {
+    mbar = sp.alloc(16u * nwarps, false) + 16u * wid;
+    for (uint32_t w = 0; w < nwarps; ++w) {
+      const uint32_t a = sp.alloc(LmTile::kWarpBytes, false, 512u);
+      if (w == wid) slab = a;
+    }
+    CwTile::init_barriers(mbar, lane);
+    if (lane == 0 && tile0 < ntiles) LmTile::issue(A.tmap, A.tmap2, slab, mbar, 0u, 0, int(tile0 * 32));
   }
   for (uint64_t tile = tile0; tile < ntiles; tile += tile_stride) {
     const uint64_t k = tile * 32 + lane;
@@ -351,6 +439,26 @@ point_kernel(const __grid_constant__ KParams P, const __grid_constant__ PointArg
       cw.nchunks = MODE == 6 ? (ncw + 3) >> 2 : (ncw + 1) >> 1;
       cw.seq = &tma_seq;
       cw.fl = MODE == 6 ? ld_blk(A.cws + kk * (uint64_t(ncw) * 16u + 16u) + uint64_t(ncw) * 16u) : blk{0u, 0u, 0u, 0u};
+      y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
+    } else if (PM::kLmTma) {
+      LmTile cw;
+      cw.buf = slab;
+      cw.mbar = mbar;
+      cw.tmap_s = A.tmap;
+      cw.tmap_v = A.tmap2;
+      cw.lane = lane;
+      cw.key0 = int(tile * 32);
+      cw.next_key0 = tile + tile_stride < ntiles ? int((tile + tile_stride) * 32) : -1;
+      cw.nchunks = (ncw + (1 << LmTile::kLpcBits) - 1) >> LmTile::kLpcBits;
+      cw.seq = &tma_seq;
+      cw.fl = blk{0u, 0u, 0u, 0u};
+      if (SCHEME != FSSB200_SCHEME_DCF) {  // ceil(n / 32) words of control bits per key
+        cw.fl.x = A.extra[kk];
+        if (n > 32) cw.fl.y = A.extra[A.nkeys + kk];
+        if (n > 64) cw.fl.z = A.extra[2 * A.nkeys + kk];
+        if (n > 96) cw.fl.w = A.extra[3 * A.nkeys + kk];
+      }
+      cw.out_cw = A.out_cw ? A.out_cw + kk : nullptr;
       y = point_eval_one<SCHEME, G, PRG>(P, pc, A, s0, x, cw, kk, valid);
     } else if (MODE == 2) {
       const CwLevelMajor cw{A.cw_s, A.cw_v, A.extra, A.out_cw, A.nkeys, kk};
@@ -451,7 +559,7 @@ gen_kernel(const __grid_constant__ KParams P, const __grid_constant__ GenArgs A)
     }
   }
   const uint64_t ntiles = (A.nkeys + 31) >> 5;
-  for (uint64_t tile = uint64_t(blockIdx.x) * nwarps + wid; tile < ntiles; tile += uint64_t(gridDim.x) * nwarps) {
+  for (uint64_t tile = uint64_t(wid) * gridDim.x + blockIdx.x; tile < ntiles; tile += uint64_t(gridDim.x) * nwarps) {  // (see point_kernel)
     const uint64_t k = tile * 32 + lane;
     const bool valid = k < A.nkeys;
     if (OUT == 1) {

@@ -75,6 +75,7 @@ point_launch_fn CAT3(point_launcher_, PRGNAME, SCHNAME)(int gk, int mode) {
       case 3: return &point_launch<GK, 3>;                      \
       case 4: return &point_launch<GK, 4>;                      \
       case 5: return &point_launch<GK, 5>;                      \
+      case 7: return &point_launch<GK, 7>;                      \
       FSS_CASE_PACKED(GK)                                       \
     }                                                           \
     return nullptr;
