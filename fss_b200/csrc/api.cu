@@ -222,9 +222,11 @@ int fssb200_ctx_create(const fssb200_params *p, fssb200_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = int(prop.sharedMemPerBlockOptin);
   // measured on B200 (profiles/r01_point_modes.md): correction words fetched by the TMA unit (CwTile) beat the
-  // cp.async slabs for every scheme; DPF / DCF gain another 1-3 % from 24 warps per SM, Half-Tree does not
+  // cp.async slabs for every scheme; DPF / DCF gain another 1-3 % from 24 warps per SM -- and so does Half-Tree since
+  // the tiles interleave over the CTAs (2^20 keys 0.923 -> 0.926, 2^22 keys 0.939 -> 0.954: profiles/r02_levelmajor_tma.md;
+  // before, the 768-thread geometry lost a whole round of tiles at 2^20 keys).
   // (the Grotto walk expands both children per level like the gen kernels: 512 threads, no register cap of 85)
-  c->point_mode = (q.scheme == FSSB200_SCHEME_HALFTREE || q.scheme == FSSB200_SCHEME_GROTTO) ? 4 : 5;
+  c->point_mode = q.scheme == FSSB200_SCHEME_GROTTO ? 4 : 5;
   if (const char *e = std::getenv("FSSB200_POINT_MODE")) {  // A/B measurement knob
     const int m = std::atoi(e);
     const bool grotto = q.scheme == FSSB200_SCHEME_GROTTO;  // walk: instantiated for modes 3 / 4 / 5 only
