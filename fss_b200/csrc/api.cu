@@ -118,7 +118,7 @@ LaunchCfg point_cfg(const fssb200_ctx *c, uint64_t n, cudaStream_t s, int mode =
     cfg.block = dim3(threads);
     cfg.smem = kMaxDynSmem;
   } else {
-    const uint64_t want = (n + 255) / 256;
+    const uint64_t want = (n + 31) / 32;  // (tiles interleave over the CTAs: spread a small batch over every SM)
     const uint64_t cap = uint64_t(c->sm_count) * 6;
     cfg.grid = dim3(unsigned(want < cap ? (want ? want : 1) : cap));
     cfg.block = dim3(256);
