@@ -39,7 +39,7 @@ for step in "$@"; do
       echo "launches rc=$?" ;;
     ncu)
       for k in ${NCU_KERNELS:-c2}; do
-        case $k in c2|c3|ht|packed|vdpf|walk) rx=point_kernel ;; gen_*) rx=gen_kernel ;; relayout) rx=relayout_kernel ;; evalall_dcf) rx=dcf_evalall ;; *) rx=evalall_kernel ;; esac
+        case $k in c2|c3|ht|packed|vdpf|walk|lm) rx=point_kernel ;; gen_*) rx=gen_kernel ;; relayout) rx=relayout_kernel ;; evalall_dcf) rx=dcf_evalall ;; *) rx=evalall_kernel ;; esac
         timeout 600 ncu --set full --clock-control none --import-source on -k regex:${NCU_REGEX:-$rx} -s ${NCU_SKIP:-2} -c 1 \
           -f -o gpurun_out/prof_$k python tools/prof_one.py $k > gpurun_out/prof_$k.log 2>&1
         echo "ncu $k rc=$?"

@@ -1,6 +1,6 @@
 """One small workload per invocation, for `ncu -k regex:<kernel> -s 2 -c 1` captures (profiles/).
 
-  python tools/prof_one.py evalall_dpf|evalall_ht|evalall_dcf|gen_dcf|gen_dpf|grotto|c2|c3|ht|packed|vdpf|walk|relayout
+  python tools/prof_one.py evalall_dpf|evalall_ht|evalall_dcf|gen_dcf|gen_dpf|grotto|c2|c3|ht|packed|vdpf|walk|relayout|lm
 """
 import os
 import sys
@@ -33,9 +33,9 @@ def main():
         cws = rnd((1 << 22, 33, 8))
         for _ in range(4):
             ctx.relayout(cws)
-    elif which in ("c2", "c3", "ht", "packed", "vdpf", "walk"):
+    elif which in ("c2", "c3", "ht", "packed", "vdpf", "walk", "lm"):
         scheme, n, k, group = {"c2": ("dpf", 32, 1 << 22, "bytes"), "c3": ("dcf", 64, 1 << 21, "u128"),
-                               "ht": ("halftree", 32, 1 << 20, "bytes"), "packed": ("dpf", 32, 1 << 21, "bytes"),
+                               "ht": ("halftree", 32, 1 << 20, "bytes"), "packed": ("dpf", 32, 1 << 21, "bytes"), "lm": ("dpf", 32, 1 << 22, "bytes"),
                                "vdpf": ("vdpf", 32, 1 << 20, "bytes"), "walk": ("grotto", 32, 1 << 20, "bytes")}[which]
         ctx = fss_b200.Context(scheme, n, group, prg="aes128_mmo")
         s0s, alphas, betas = inputs(k, n)
@@ -55,7 +55,11 @@ def main():
             r = ctx.gen(s0s, alphas, betas)
             cws, ocws = r if scheme == "halftree" else (r, None)
             ys = torch.empty((k, 4), dtype=torch.int32, device=dev)
-            if which == "packed":
+            if which == "lm":
+                lay = ctx.relayout(cws)
+                for _ in range(3):
+                    ctx.eval_levelmajor(0, seeds0, lay, xs, ocws, out=ys)
+            elif which == "packed":
                 rows = ctx.pack_rows(cws.cpu()).to(dev)
                 for _ in range(3):
                     ctx.eval_packed(0, seeds0, rows, xs, out=ys)
