@@ -358,6 +358,67 @@ static void VdpfHashes(const char *tag, HX xor_hash, HH hash) {
   EXPECT(!Vdpf::Verify(cuda::std::span<const int4, 4>(qa), cuda::std::span<const int4, 4>(qb)), tag);
   (void)pt;
 }
+// fss::gpu::VdpfRelayoutGpu + VdpfEvalPointGpu (point_eval_gpu.cuh:389-396, 513-526) against the batched key-major members
+static void VdpfGpuFreeFunctions() {
+  using Group = fss::group::Bytes;
+  using Prg = fss::prg::Aes128Mmo<2>;
+  using H = fss::hash::Blake3;
+  using Vdpf = fss::Vdpf<20, Group, Prg, H, H, uint32_t>;
+  const unsigned char *keys[2] = {k0, k1};
+  auto ctxs = Prg::CreateCtxs(keys);
+  Prg prg(ctxs);
+  const int4 iv0[2] = {{1, 2, 3, 4}, {5, 6, 7, 8}}, iv1[2] = {{9, 10, 11, 12}, {13, 14, 15, 16}};
+  Vdpf vdpf{prg, H{cuda::std::span<const int4, 2>(iv0, 2)}, H{cuda::std::span<const int4, 2>(iv1, 2)}};
+  const int nk = 333;
+  std::vector<int4> s0s(2 * nk), betas(nk), cs(4 * nk), ocws(nk), seeds(nk), y_a(nk), y_b(nk), pi_a(4 * nk), pi_b(4 * nk);
+  std::vector<uint32_t> alphas(nk), xs(nk);
+  std::vector<int32_t> status(nk);
+  std::vector<Vdpf::Cw> cws(size_t(nk) * 20);
+  for (int k = 0; k < nk; ++k) {
+    s0s[2 * k] = {k * 7 + 1, k, 3, (k * 5) & ~1};
+    s0s[2 * k + 1] = {k * 11 + 2, k, 9, (k * 3) & ~1};
+    betas[k] = {k, 1, 2, 4};
+    alphas[k] = (k * 2654435761u) & 0xfffffu;
+    xs[k] = k % 3 ? ((k * 40503u) & 0xfffffu) : alphas[k];
+    seeds[k] = s0s[2 * k + 1];
+  }
+  auto dev = [](const auto &v) {
+    using T = typename std::decay_t<decltype(v)>::value_type;
+    T *p = nullptr;
+    cudaMalloc(&p, sizeof(T) * v.size());
+    cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+    return p;
+  };
+  int4 *d_s0s = dev(s0s), *d_betas = dev(betas), *d_cs = dev(cs), *d_ocws = dev(ocws), *d_seeds = dev(seeds);
+  int4 *d_ya = dev(y_a), *d_yb = dev(y_b), *d_pa = dev(pi_a), *d_pb = dev(pi_b);
+  uint32_t *d_al = dev(alphas), *d_xs = dev(xs);
+  int32_t *d_st = dev(status);
+  Vdpf::Cw *d_cws = dev(cws);
+  vdpf.GenBatch(d_s0s, d_al, d_betas, d_cws, d_cs, d_ocws, d_st, nk);
+  vdpf.EvalBatch(true, d_seeds, d_cws, d_cs, d_ocws, d_xs, d_ya, d_pa, nk);
+  int4 *d_cw_s = nullptr;
+  uint32_t *d_extra = nullptr;
+  cudaMalloc(&d_cw_s, sizeof(int4) * 20 * nk);
+  cudaMalloc(&d_extra, sizeof(uint32_t) * nk);
+  fss::gpu::VdpfRelayoutGpu<20, Group, Prg, H, H, uint32_t>(d_cws, nk, d_cw_s, d_extra);
+  fss::gpu::VdpfEvalPointGpu(true, d_seeds, d_cw_s, d_extra, reinterpret_cast<const cuda::std::array<int4, 4> *>(d_cs), d_ocws,
+                             d_xs, d_yb, d_pb, nk, vdpf);
+  cudaDeviceSynchronize();
+  cudaMemcpy(y_a.data(), d_ya, sizeof(int4) * nk, cudaMemcpyDeviceToHost);
+  cudaMemcpy(y_b.data(), d_yb, sizeof(int4) * nk, cudaMemcpyDeviceToHost);
+  cudaMemcpy(pi_a.data(), d_pa, sizeof(int4) * 4 * nk, cudaMemcpyDeviceToHost);
+  cudaMemcpy(pi_b.data(), d_pb, sizeof(int4) * 4 * nk, cudaMemcpyDeviceToHost);
+  EXPECT(std::memcmp(y_a.data(), y_b.data(), sizeof(int4) * nk) == 0, "VdpfEvalPointGpu == EvalBatch (shares)");
+  EXPECT(std::memcmp(pi_a.data(), pi_b.data(), sizeof(int4) * 4 * nk) == 0, "VdpfEvalPointGpu == EvalBatch (hashes)");
+  int nonzero = 0;
+  for (int k = 0; k < nk; ++k) nonzero += !Eq(y_a[k], kZero);
+  EXPECT(nonzero > nk / 2, "VdpfEvalPointGpu wrote shares");
+  for (void *p : {(void *)d_s0s, (void *)d_betas, (void *)d_cs, (void *)d_ocws, (void *)d_seeds, (void *)d_ya, (void *)d_yb, (void *)d_pa,
+                  (void *)d_pb, (void *)d_al, (void *)d_xs, (void *)d_st, (void *)d_cws, (void *)d_cw_s, (void *)d_extra})
+    cudaFree(p);
+  Prg::FreeCtxs(ctxs);
+}
+
 static void VdpfSha256() {
   using S = fss::hash::Sha256;
   using B = fss::hash::Blake3;
@@ -382,6 +443,7 @@ int main() {
   try {
     VdpfN8();
     VdpfSha256();
+    VdpfGpuFreeFunctions();
     DpfN8();
     DcfN64();
     HalfTreeAndGrotto();
