@@ -3,6 +3,10 @@
 // helpers on CUDA `int4`.  Part of the B200 shim: same names and semantics, new code.
 #pragma once
 #include <cstdint>
+#include <thread>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 #include <cuda_runtime.h>
 
 #if defined(__CUDACC__)
@@ -20,6 +24,20 @@ FSS_SHIM_HD int4 SetLsb(int4 v, bool bit) {
   return v;
 }
 FSS_SHIM_HD bool GetLsb(int4 v) { return (v.w & 1) != 0; }
+
+// util.cuh:40-45: the recursion depth at which the reference's CPU EvalAll stops spawning OpenMP tasks (par_depth < 0:
+// log2 of the thread count, rounded up).  Kept for source compatibility; the evaluator here does not use it.
+inline int ResolveParDepth(int par_depth) {
+  if (par_depth >= 0) return par_depth;
+#if defined(_OPENMP)
+  const int threads = omp_get_max_threads();
+#else
+  const int threads = static_cast<int>(std::thread::hardware_concurrency());
+#endif
+  int d = 0;
+  while ((1 << d) < threads) ++d;
+  return d;
+}
 
 // Little-endian packing of a domain value into a block (util.cuh:47-64).
 template <typename In>
