@@ -91,3 +91,13 @@ def test_header_shim_compiles_with_plain_gxx(tmp_path, src, extra):
     import torch
     if not torch.cuda.is_available():   # fails loudly without a GPU: an exception from fssb200_ctx_create, never a CPU result
         assert r.returncode != 0 and "no such CUDA device" in (r.stdout + r.stderr)
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md maps every exported function of include/fssb200.h to the reference interface it replaces."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    syms = set(re.findall(r"\b(fssb200_[a-z0-9_]+)\(", open(os.path.join(root, "include", "fssb200.h")).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(s for s in syms if s not in doc)
+    assert not missing, missing
