@@ -6,7 +6,9 @@
  * most literal way (byte-wise FIPS-197 AES, recursive trees, unsigned __int128
  * group arithmetic): it shares no code and no table layout with the CUDA kernels it
  * checks.  PARITY PINNED against the compiled reference (oracle/_ref) and the
- * golden fixtures by tests/test_oracle.py.
+ * golden fixtures by tests/test_oracle.py; the VDPF part (Blake3 and SHA-256 hash
+ * plugins) by tests/test_vdpf.py against oracle/ref_vdpf.cpp, the reference-generated
+ * fixtures tests/golden/golden_vdpf{,_sha256}_v1.* and Python's hashlib.
  */
 #include "fss_oracle.h"
 
