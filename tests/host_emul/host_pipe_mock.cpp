@@ -250,6 +250,32 @@ int main(int argc, char **argv) {
     mockcuda::unregister_pinned(b_dpf.cws.data());
     mockcuda::unregister_pinned(b_dpf.xs.data());
   }
+  // balanced split with PAGEABLE inputs (every block is staged by the workers), and with two devices in host mode 1
+  for (int variant = 0; variant < 2; ++variant) {
+    const int ndev = variant == 0 ? 3 : 2;
+    std::vector<fssb200_ctx *> cs;
+    for (int d = 0; d < ndev; ++d) {
+      cs.push_back(MakeCtx(FSSB200_SCHEME_DPF, 32, 4));
+      if (variant == 1) fssb200_ctx_set_host_mode(cs.back(), 1);
+    }
+    if (variant == 1) {
+      mockcuda::register_pinned(b_dpf.seeds.data(), b_dpf.seeds.size());
+      mockcuda::register_pinned(b_dpf.cws.data(), b_dpf.cws.size());
+      mockcuda::register_pinned(b_dpf.xs.data(), b_dpf.xs.size());
+    }
+    std::vector<uint8_t> ys(16 * b_dpf.n);
+    std::vector<int> rcs(size_t(ndev), -1);
+    const long launches0 = g_kernel_launches.load();
+    const int rc = fssb200_eval_host_multi(cs.data(), ndev, 1, b_dpf.seeds.data(), b_dpf.cws.data(), nullptr, b_dpf.xs.data(), ys.data(),
+                                           b_dpf.n, rcs.data());
+    CHECK(rc == 0 && std::memcmp(ys.data(), b_dpf.want.data(), ys.size()) == 0, "balanced eval_host_multi variant %d rc=%d", variant, rc);
+    CHECK(g_kernel_launches.load() - launches0 >= 4, "balanced split (variant %d) did not split", variant);
+    if (variant == 1) {
+      mockcuda::unregister_pinned(b_dpf.seeds.data());
+      mockcuda::unregister_pinned(b_dpf.cws.data());
+      mockcuda::unregister_pinned(b_dpf.xs.data());
+    }
+  }
   unsetenv("FSSB200_MULTI_MIN_BLOCK_BITS");
   unsetenv("FSSB200_MULTI_MAX_BLOCK_BITS");
   // error path: the 2nd launch of a call fails -> the call returns the error, nothing stays in flight, the next call is fine
