@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small invocation of every kernel family, checked against the oracle -- the workload that
-tools/gpu_sanitize.sh runs under compute-sanitizer (memcheck / racecheck / synccheck / initcheck).
+`tools/gpu_session.sh sanitize` runs under compute-sanitizer (memcheck / racecheck / synccheck / initcheck).
 Sizes are ragged on purpose (tiles of 32 keys, 768-thread CTAs, TMA boxes that run off the tensor)."""
 import os
 import sys
