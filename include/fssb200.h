@@ -248,7 +248,8 @@ int fssb200_grotto_eval_walk(const fssb200_ctx *ctx, int party, const void *seed
  *   fssb200_vdpf_eval_all replaces `Vdpf::EvalAll` vdpf.cuh:294-342 (the reference has no
  *                         GPU version): ys[k][x] for the whole domain and the accumulated
  *                         proof pis[k].  The proof chain is sequential in x by definition
- *                         (:336-340), one warp walks it per key.
+ *                         (:336-340); 1 ... 32 lanes walk it per key (chosen from nkeys: many
+ *                         keys share a warp, few keys get a warp each).
  * Verify (vdpf.cuh:271-276) is a 64-byte comparison of two proofs; no entry point.
  *   cws : Cw[nkeys][n]      cs : int4[nkeys][4]      ocws : int4[nkeys]
  *   pis / pi_tildes : int4[nkeys][4] / int4[nkeys][m][4]      status : int32[nkeys]
@@ -288,7 +289,9 @@ int fssb200_hash(const fssb200_ctx *ctx, int which, const void *msgs, void *out,
 int fssb200_relayout(const fssb200_ctx *ctx, const void *cws, void *cw_s, void *cw_v, void *extra,
                      void *out_cw, size_t nkeys, void *stream);
 /* Replaces `fss::gpu::{Dpf,Dcf,HalfTreeDpf}EvalPointGpu` point_eval_gpu.cuh:416-492
- * on the layout above (ocws: Half-Tree only). */
+ * on the layout above (ocws: Half-Tree only).  The arrays reach shared memory through the TMA
+ * unit (2-D tensors [n][nkeys*4] of uint32, 4 levels x 32 keys per request); cw_s / cw_v must
+ * be 16-byte aligned. */
 int fssb200_eval_levelmajor(const fssb200_ctx *ctx, int party, const void *seeds, const void *cw_s,
                             const void *cw_v, const void *extra, const void *out_cw,
                             const void *ocws, const void *xs, void *ys, size_t nkeys,
