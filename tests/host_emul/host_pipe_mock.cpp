@@ -75,13 +75,145 @@ int fssb200_eval_packed(const fssb200_ctx *c, int party, const void *seeds, cons
                         void *ys, size_t nkeys, void *stream) {
   return EvalOp(c, party, seeds, rows, ocws, xs, ys, nkeys, stream, true);
 }
-// the other device entry points host_api.cu references: not exercised by this test
-int fssb200_gen(const fssb200_ctx *, const void *, const void *, const void *, void *, void *, size_t, void *) { return FSSB200_ESCHEME; }
-int fssb200_vdpf_gen(const fssb200_ctx *, const void *, const void *, const void *, void *, void *, void *, void *, size_t, void *) { return FSSB200_ESCHEME; }
-int fssb200_vdpf_eval(const fssb200_ctx *, int, const void *, const void *, const void *, const void *, const void *, void *, void *, size_t, void *) { return FSSB200_ESCHEME; }
-int fssb200_eval_levelmajor(const fssb200_ctx *, int, const void *, const void *, const void *, const void *, const void *, const void *, const void *, void *, size_t, void *) { return FSSB200_ESCHEME; }
-int fssb200_eval_all(const fssb200_ctx *, int, const void *, const void *, const void *, void *, size_t, uint64_t, uint64_t, void *) { return FSSB200_ESCHEME; }
-int fssb200_prg_gen(const fssb200_ctx *, const void *, void *, int, size_t, void *) { return FSSB200_ESCHEME; }
+// The other device entry points host_api.cu forwards to: every output byte is a digest of every input byte of its key, so
+// the chunked host loops (offsets inside a device set, strided gathers, double buffering, the D2H of each chunk) are
+// right only if the mock device saw what the caller passed.
+static uint64_t DigestBytes(uint64_t h, const uint8_t *p, size_t n) {
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) h = Mix(h, Load64(p + i));
+  for (; i < n; ++i) h = Mix(h, p[i]);
+  return h;
+}
+static void FillFrom(uint64_t h, uint8_t *out, size_t n) {
+  for (size_t i = 0; i < n; i += 8) {
+    h = Mix(h, i);
+    std::memcpy(out + i, &h, n - i < 8 ? n - i : 8);
+  }
+}
+// gen: cws[k] (ncw x 32 B) and ocws[k] from (s0s[k], alpha[k], beta[k])
+static void GenKey(const fssb200_ctx *c, const uint8_t *s0s, const uint8_t *alpha, const uint8_t *beta, uint8_t *cws, uint8_t *ocw) {
+  uint64_t h = DigestBytes(0x6e6, s0s, 32);
+  h = DigestBytes(h, alpha, size_t(c->p.in_bytes));
+  if (beta) h = DigestBytes(h, beta, 16);
+  FillFrom(h, cws, size_t(c->ncw) * 32);
+  if (ocw) FillFrom(Mix(h, 0x0c), ocw, 16);
+}
+int fssb200_gen(const fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *ocws, size_t nkeys,
+                void *stream) {
+  if (g_fail_after.load() >= 0 && g_fail_after.fetch_sub(1) == 0) return 700;
+  ++g_kernel_launches;
+  const size_t ib = size_t(c->p.in_bytes), cwb = size_t(c->ncw) * 32;
+  mockcuda::S(static_cast<cudaStream_t>(stream))->push([=] {
+    for (size_t k = 0; k < nkeys; ++k)
+      GenKey(c, static_cast<const uint8_t *>(s0s) + 32 * k, static_cast<const uint8_t *>(alphas) + ib * k,
+             betas ? static_cast<const uint8_t *>(betas) + 16 * k : nullptr, static_cast<uint8_t *>(cws) + cwb * k,
+             ocws ? static_cast<uint8_t *>(ocws) + 16 * k : nullptr);
+  });
+  return 0;
+}
+// vdpf gen: cws, cs (64 B), ocws, status; vdpf eval: ys, pis (64 B) from everything of the key
+static void VdpfGenKey(const fssb200_ctx *c, const uint8_t *s0s, const uint8_t *alpha, const uint8_t *beta, uint8_t *cws, uint8_t *cs,
+                       uint8_t *ocw, int32_t *status) {
+  uint64_t h = DigestBytes(DigestBytes(DigestBytes(0x7d9f, s0s, 32), alpha, size_t(c->p.in_bytes)), beta, 16);
+  FillFrom(h, cws, size_t(c->ncw) * 32);
+  FillFrom(Mix(h, 1), cs, 64);
+  FillFrom(Mix(h, 2), ocw, 16);
+  *status = int32_t(h & 1);
+}
+int fssb200_vdpf_gen(const fssb200_ctx *c, const void *s0s, const void *alphas, const void *betas, void *cws, void *cs, void *ocws,
+                     void *status, size_t nkeys, void *stream) {
+  ++g_kernel_launches;
+  const size_t ib = size_t(c->p.in_bytes), cwb = size_t(c->ncw) * 32;
+  mockcuda::S(static_cast<cudaStream_t>(stream))->push([=] {
+    for (size_t k = 0; k < nkeys; ++k)
+      VdpfGenKey(c, static_cast<const uint8_t *>(s0s) + 32 * k, static_cast<const uint8_t *>(alphas) + ib * k,
+                 static_cast<const uint8_t *>(betas) + 16 * k, static_cast<uint8_t *>(cws) + cwb * k, static_cast<uint8_t *>(cs) + 64 * k,
+                 static_cast<uint8_t *>(ocws) + 16 * k, static_cast<int32_t *>(status) + k);
+  });
+  return 0;
+}
+static void VdpfEvalKey(const fssb200_ctx *c, int party, const uint8_t *seed, const uint8_t *cws, const uint8_t *cs, const uint8_t *ocw,
+                        const uint8_t *x, uint8_t *y, uint8_t *pi) {
+  uint64_t h = DigestBytes(Mix(0xe7a1, uint64_t(party)), seed, 16);
+  h = DigestBytes(DigestBytes(DigestBytes(h, cws, size_t(c->ncw) * 32), cs, 64), ocw, 16);
+  h = DigestBytes(h, x, size_t(c->p.in_bytes));
+  FillFrom(h, y, 16);
+  FillFrom(Mix(h, 3), pi, 64);
+}
+int fssb200_vdpf_eval(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *cs, const void *ocws,
+                      const void *xs, void *ys, void *pis, size_t nkeys, void *stream) {
+  ++g_kernel_launches;
+  const size_t ib = size_t(c->p.in_bytes), cwb = size_t(c->ncw) * 32;
+  mockcuda::S(static_cast<cudaStream_t>(stream))->push([=] {
+    for (size_t k = 0; k < nkeys; ++k)
+      VdpfEvalKey(c, party, static_cast<const uint8_t *>(seeds) + 16 * k, static_cast<const uint8_t *>(cws) + cwb * k,
+                  static_cast<const uint8_t *>(cs) + 64 * k, static_cast<const uint8_t *>(ocws) + 16 * k,
+                  static_cast<const uint8_t *>(xs) + ib * k, static_cast<uint8_t *>(ys) + 16 * k, static_cast<uint8_t *>(pis) + 64 * k);
+  });
+  return 0;
+}
+// level-major eval: ys[k] from seed, x, every cw_s[i][k] (and cw_v), the key's control-bit words, out_cw, ocw
+static void LmKey(const fssb200_ctx *c, int party, size_t k, size_t nkeys, const uint8_t *seeds, const uint8_t *cw_s, const uint8_t *cw_v,
+                  const uint8_t *extra, const uint8_t *out_cw, const uint8_t *ocws, const uint8_t *xs, uint8_t *y) {
+  const size_t n = size_t(c->p.in_bits), nw = (n + 31) / 32;
+  uint64_t h = DigestBytes(Mix(0x1e7e1, uint64_t(party)), seeds + 16 * k, 16);
+  h = DigestBytes(h, xs + size_t(c->p.in_bytes) * k, size_t(c->p.in_bytes));
+  for (size_t i = 0; i < n; ++i) {
+    h = DigestBytes(h, cw_s + (i * nkeys + k) * 16, 16);
+    if (cw_v) h = DigestBytes(h, cw_v + (i * nkeys + k) * 16, 16);
+  }
+  if (extra)
+    for (size_t w = 0; w < nw; ++w) h = DigestBytes(h, extra + (w * nkeys + k) * 4, 4);
+  if (out_cw) h = DigestBytes(h, out_cw + 16 * k, 16);
+  if (ocws) h = DigestBytes(h, ocws + 16 * k, 16);
+  FillFrom(h, y, 16);
+}
+int fssb200_eval_levelmajor(const fssb200_ctx *c, int party, const void *seeds, const void *cw_s, const void *cw_v, const void *extra,
+                            const void *out_cw, const void *ocws, const void *xs, void *ys, size_t nkeys, void *stream) {
+  if (g_fail_after.load() >= 0 && g_fail_after.fetch_sub(1) == 0) return 700;
+  ++g_kernel_launches;
+  mockcuda::S(static_cast<cudaStream_t>(stream))->push([=] {
+    for (size_t k = 0; k < nkeys; ++k)
+      LmKey(c, party, k, nkeys, static_cast<const uint8_t *>(seeds), static_cast<const uint8_t *>(cw_s), static_cast<const uint8_t *>(cw_v),
+            static_cast<const uint8_t *>(extra), static_cast<const uint8_t *>(out_cw), static_cast<const uint8_t *>(ocws),
+            static_cast<const uint8_t *>(xs), static_cast<uint8_t *>(ys) + 16 * k);
+  });
+  return 0;
+}
+// full-domain: leaf x of key k = digest(key) mixed with x (16 B; Grotto: 1 byte)
+static uint64_t AllKeyDigest(const fssb200_ctx *c, int party, const uint8_t *seed, const uint8_t *cws, const uint8_t *ocw) {
+  uint64_t h = DigestBytes(Mix(0xa11, uint64_t(party)), seed, 16);
+  h = DigestBytes(h, cws, size_t(c->ncw) * 32);
+  return ocw ? DigestBytes(h, ocw, 16) : h;
+}
+static void AllLeaf(const fssb200_ctx *c, uint64_t hk, uint64_t x, uint8_t *out) {
+  const uint64_t v[2] = {Mix(hk, x), Mix(hk, ~x)};
+  std::memcpy(out, v, c->p.scheme == FSSB200_SCHEME_GROTTO ? 1 : 16);
+}
+int fssb200_eval_all(const fssb200_ctx *c, int party, const void *seeds, const void *cws, const void *ocws, void *ys, size_t nkeys,
+                     uint64_t leaf_begin, uint64_t leaf_count, void *stream) {
+  if (g_fail_after.load() >= 0 && g_fail_after.fetch_sub(1) == 0) return 700;
+  ++g_kernel_launches;
+  const size_t cwb = size_t(c->ncw) * 32, lb = c->p.scheme == FSSB200_SCHEME_GROTTO ? 1 : 16;
+  mockcuda::S(static_cast<cudaStream_t>(stream))->push([=] {
+    for (size_t k = 0; k < nkeys; ++k) {
+      const uint64_t hk = AllKeyDigest(c, party, static_cast<const uint8_t *>(seeds) + 16 * k, static_cast<const uint8_t *>(cws) + cwb * k,
+                                       ocws ? static_cast<const uint8_t *>(ocws) + 16 * k : nullptr);
+      for (uint64_t i = 0; i < leaf_count; ++i) AllLeaf(c, hk, leaf_begin + i, static_cast<uint8_t *>(ys) + (k * leaf_count + i) * lb);
+    }
+  });
+  return 0;
+}
+int fssb200_prg_gen(const fssb200_ctx *, const void *seeds, void *out, int mul, size_t nseeds, void *stream) {
+  ++g_kernel_launches;
+  mockcuda::S(static_cast<cudaStream_t>(stream))->push([=] {
+    for (size_t i = 0; i < nseeds; ++i)
+      for (int j = 0; j < mul; ++j)
+        FillFrom(Mix(DigestBytes(0x9e6, static_cast<const uint8_t *>(seeds) + 16 * i, 16), uint64_t(j)),
+                 static_cast<uint8_t *>(out) + (i * size_t(mul) + size_t(j)) * 16, 16);
+  });
+  return 0;
+}
 }
 
 // ---- scenarios ------------------------------------------------------------------------------------------------------------
@@ -125,7 +257,7 @@ static fssb200_ctx *MakeCtx(int scheme, int in_bits, int in_bytes) {
   c->p.scheme = scheme;
   c->p.in_bits = in_bits;
   c->p.in_bytes = in_bytes;
-  c->ncw = scheme == FSSB200_SCHEME_HALFTREE ? in_bits : in_bits + 1;
+  c->ncw = (scheme == FSSB200_SCHEME_HALFTREE || scheme == FSSB200_SCHEME_VDPF) ? in_bits : in_bits + 1;
   return c;
 }
 static void RunOne(fssb200_ctx *c, const Batch &b, int mode, bool pin_in, bool pin_out, const char *what) {
@@ -293,6 +425,136 @@ int main(int argc, char **argv) {
     mockcuda::unregister_pinned(b_dpf.cws.data());
     mockcuda::unregister_pinned(b_dpf.xs.data());
     RunOne(dpf, b_dpf, mode, true, true, "call after a failed call");
+  }
+  // ---- the other host entry points: chunked, double-buffered loops over the same arena pool -------------------------------
+  {
+    std::minstd_rand rng(99);
+    auto fill = [&](std::vector<uint8_t> &v, size_t bytes) {
+      v.resize(bytes);
+      for (auto &x : v) x = uint8_t(rng());
+    };
+    // gen: DPF n=32 and Half-Tree n=20 (separate output correction words), chunk sizes that leave a ragged tail
+    for (fssb200_ctx *c : {dpf, ht}) {
+      const size_t nk = 5003, cwb = size_t(c->ncw) * 32, ib = size_t(c->p.in_bytes);
+      const bool half = c->p.scheme == FSSB200_SCHEME_HALFTREE;
+      std::vector<uint8_t> s0s, al, be, cws(nk * cwb, 0xEE), ocws(half ? nk * 16 : 0, 0xEE), want_c(nk * cwb), want_o(half ? nk * 16 : 0);
+      fill(s0s, nk * 32); fill(al, nk * ib); fill(be, nk * 16);
+      for (size_t k = 0; k < nk; ++k)
+        GenKey(c, &s0s[32 * k], &al[ib * k], &be[16 * k], &want_c[cwb * k], half ? &want_o[16 * k] : nullptr);
+      for (size_t ck : {size_t(0), size_t(1000), size_t(4999), size_t(1)}) {
+        if (ck == 1 && c == ht) continue;  // (one key per chunk: once is enough)
+        fssb200_ctx_reserve_host(c, ck);
+        const size_t use = ck == 1 ? 37 : nk;
+        std::fill(cws.begin(), cws.end(), 0xEE);
+        const int rc = fssb200_gen_host(c, s0s.data(), al.data(), be.data(), cws.data(), half ? ocws.data() : nullptr, use);
+        CHECK(rc == 0 && std::memcmp(cws.data(), want_c.data(), use * cwb) == 0, "gen_host chunk %zu rc=%d", ck, rc);
+        if (half) CHECK(std::memcmp(ocws.data(), want_o.data(), use * 16) == 0, "gen_host ocws chunk %zu", ck);
+        CHECK(use == nk || cws[use * cwb] == 0xEE, "gen_host wrote past the batch");
+      }
+      fssb200_ctx_reserve_host(c, 0);
+    }
+    // prg_gen_host
+    for (int mul : {1, 2, 4}) {
+      const size_t ns = 3001;
+      std::vector<uint8_t> seeds, out(ns * 16 * size_t(mul), 0xEE), want(ns * 16 * size_t(mul));
+      fill(seeds, ns * 16);
+      for (size_t i = 0; i < ns; ++i)
+        for (int j = 0; j < mul; ++j) FillFrom(Mix(DigestBytes(0x9e6, &seeds[16 * i], 16), uint64_t(j)), &want[(i * size_t(mul) + size_t(j)) * 16], 16);
+      const int rc = fssb200_prg_gen_host(dpf, seeds.data(), out.data(), mul, ns);
+      CHECK(rc == 0 && out == want, "prg_gen_host mul=%d rc=%d", mul, rc);
+    }
+    // eval_all_host: several keys, leaf ranges (granule 1 in the mock), Half-Tree ocws, Grotto bytes
+    fssb200_ctx *ea_dpf = MakeCtx(FSSB200_SCHEME_DPF, 12, 2), *ea_ht = MakeCtx(FSSB200_SCHEME_HALFTREE, 10, 2),
+                *ea_gr = MakeCtx(FSSB200_SCHEME_GROTTO, 11, 2);
+    for (fssb200_ctx *c : {ea_dpf, ea_ht, ea_gr}) {
+      const size_t nk = 5, cwb = size_t(c->ncw) * 32, lb = c->p.scheme == FSSB200_SCHEME_GROTTO ? 1 : 16;
+      const bool half = c->p.scheme == FSSB200_SCHEME_HALFTREE, grotto = c->p.scheme == FSSB200_SCHEME_GROTTO;
+      const uint64_t N = uint64_t(1) << c->p.in_bits;
+      std::vector<uint8_t> seeds, cws, ocws;
+      fill(seeds, nk * 16); fill(cws, nk * cwb); fill(ocws, nk * 16);
+      for (auto range : {std::pair<uint64_t, uint64_t>(0, 0), std::pair<uint64_t, uint64_t>(N / 4, N / 2), std::pair<uint64_t, uint64_t>(N - 7, 7)}) {
+        if (grotto && range.first) continue;  // (Grotto: the scan needs the domain from leaf 0)
+        const uint64_t cnt = range.second ? range.second : N - range.first;
+        std::vector<uint8_t> ys(nk * cnt * lb + 16, 0xEE);
+        const int rc = fssb200_eval_all_host(c, 1, seeds.data(), cws.data(), half ? ocws.data() : nullptr, ys.data(), nk, range.first, range.second);
+        size_t bad = 0;
+        for (size_t k = 0; k < nk && rc == 0; ++k) {
+          const uint64_t hk = AllKeyDigest(c, 1, &seeds[16 * k], &cws[cwb * k], half ? &ocws[16 * k] : nullptr);
+          for (uint64_t i = 0; i < cnt; ++i) {
+            uint8_t w[16];
+            AllLeaf(c, hk, range.first + i, w);
+            bad += std::memcmp(w, &ys[(k * cnt + i) * lb], lb) != 0;
+          }
+        }
+        CHECK(rc == 0 && bad == 0 && ys[nk * cnt * lb] == 0xEE, "eval_all_host scheme %d range %llu+%llu rc=%d bad=%zu", c->p.scheme,
+              (unsigned long long)range.first, (unsigned long long)range.second, rc, bad);
+      }
+      CHECK(fssb200_eval_all_host(c, 1, seeds.data(), cws.data(), ocws.data(), seeds.data(), 1, N, 0) == FSSB200_ERANGE, "eval_all_host range check");
+    }
+    // eval_levelmajor_host: strided gathers of [level][key] arrays, chunks with a ragged tail; DPF (extra + out_cw), DCF (cw_v + out_cw),
+    // Half-Tree (extra + ocws), and a 100-level domain (4 control-bit words per key)
+    fssb200_ctx *lm_wide = MakeCtx(FSSB200_SCHEME_DPF, 100, 16);
+    for (fssb200_ctx *c : {dpf, dcf, ht, lm_wide}) {
+      const size_t nk = 4001, n = size_t(c->p.in_bits), nw = (n + 31) / 32, ib = size_t(c->p.in_bytes);
+      const bool isdcf = c->p.scheme == FSSB200_SCHEME_DCF, half = c->p.scheme == FSSB200_SCHEME_HALFTREE;
+      std::vector<uint8_t> seeds, cw_s, cw_v, extra, out_cw, ocws, xs, want(nk * 16);
+      fill(seeds, nk * 16); fill(cw_s, n * nk * 16); fill(cw_v, n * nk * 16); fill(extra, nw * nk * 4); fill(out_cw, nk * 16);
+      fill(ocws, nk * 16); fill(xs, nk * ib);
+      for (size_t k = 0; k < nk; ++k)
+        LmKey(c, 1, k, nk, seeds.data(), cw_s.data(), isdcf ? cw_v.data() : nullptr, isdcf ? nullptr : extra.data(),
+              half ? nullptr : out_cw.data(), half ? ocws.data() : nullptr, xs.data(), &want[16 * k]);
+      for (size_t ck : {size_t(0), size_t(1500), size_t(4000)}) {
+        fssb200_ctx_reserve_host(c, ck);
+        std::vector<uint8_t> ys(nk * 16, 0xEE);
+        const int rc = fssb200_eval_levelmajor_host(c, 1, seeds.data(), cw_s.data(), isdcf ? cw_v.data() : nullptr, isdcf ? nullptr : extra.data(),
+                                                    half ? nullptr : out_cw.data(), half ? ocws.data() : nullptr, xs.data(), ys.data(), nk);
+        CHECK(rc == 0 && ys == want, "eval_levelmajor_host scheme %d n=%zu chunk %zu rc=%d", c->p.scheme, n, ck, rc);
+      }
+      fssb200_ctx_reserve_host(c, 0);
+    }
+    // an injected launch error in the chunked loops: reported, nothing left in flight, the next call is fine
+    {
+      const size_t nk = 3000, cwb = size_t(dpf->ncw) * 32;
+      std::vector<uint8_t> s0s, al, be, cws(nk * cwb);
+      fill(s0s, nk * 32); fill(al, nk * 4); fill(be, nk * 16);
+      fssb200_ctx_reserve_host(dpf, 1000);
+      g_fail_after.store(1);
+      const int rc = fssb200_gen_host(dpf, s0s.data(), al.data(), be.data(), cws.data(), nullptr, nk);
+      g_fail_after.store(-1);
+      CHECK(rc == 700, "gen_host: injected launch error not reported: rc = %d", rc);
+      CHECK(fssb200_gen_host(dpf, s0s.data(), al.data(), be.data(), cws.data(), nullptr, nk) == 0, "gen_host after a failed call");
+      fssb200_ctx_reserve_host(dpf, 0);
+    }
+    // VDPF host calls
+    fssb200_ctx *vd = MakeCtx(FSSB200_SCHEME_VDPF, 24, 4);
+    {
+      const size_t nk = 2503, cwb = size_t(vd->ncw) * 32;
+      std::vector<uint8_t> s0s, al, be, xs, cws(nk * cwb, 0xEE), cs(nk * 64), ocws(nk * 16), ys(nk * 16), pis(nk * 64);
+      std::vector<int32_t> status(nk, -1);
+      fill(s0s, nk * 32); fill(al, nk * 4); fill(be, nk * 16); fill(xs, nk * 4);
+      fssb200_ctx_reserve_host(vd, 600);
+      int rc = fssb200_vdpf_gen_host(vd, s0s.data(), al.data(), be.data(), cws.data(), cs.data(), ocws.data(), status.data(), nk);
+      size_t bad = 0;
+      for (size_t k = 0; k < nk && rc == 0; ++k) {
+        std::vector<uint8_t> wc(cwb), wcs(64), wo(16);
+        int32_t ws = -1;
+        VdpfGenKey(vd, &s0s[32 * k], &al[4 * k], &be[16 * k], wc.data(), wcs.data(), wo.data(), &ws);
+        bad += std::memcmp(wc.data(), &cws[cwb * k], cwb) != 0 || std::memcmp(wcs.data(), &cs[64 * k], 64) != 0 ||
+            std::memcmp(wo.data(), &ocws[16 * k], 16) != 0 || ws != status[k];
+      }
+      CHECK(rc == 0 && bad == 0, "vdpf_gen_host rc=%d bad=%zu", rc, bad);
+      std::vector<uint8_t> seeds(nk * 16);
+      for (size_t k = 0; k < nk; ++k) std::memcpy(&seeds[16 * k], &s0s[32 * k + 16], 16);
+      rc = fssb200_vdpf_eval_host(vd, 1, seeds.data(), cws.data(), cs.data(), ocws.data(), xs.data(), ys.data(), pis.data(), nk);
+      bad = 0;
+      for (size_t k = 0; k < nk && rc == 0; ++k) {
+        uint8_t wy[16], wp[64];
+        VdpfEvalKey(vd, 1, &seeds[16 * k], &cws[cwb * k], &cs[64 * k], &ocws[16 * k], &xs[4 * k], wy, wp);
+        bad += std::memcmp(wy, &ys[16 * k], 16) != 0 || std::memcmp(wp, &pis[64 * k], 64) != 0;
+      }
+      CHECK(rc == 0 && bad == 0, "vdpf_eval_host rc=%d bad=%zu", rc, bad);
+      fssb200_ctx_reserve_host(vd, 0);
+    }
   }
   // arena pool: what is cached is bounded; trim frees everything the pool holds
   uint64_t dev_b = 0, pin_b = 0;
