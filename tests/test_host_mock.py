@@ -2,7 +2,7 @@
 worker crew, staging ring, piece / chunk hand-offs, adaptive direct pieces, arena pool, multi-device host call (equal and
 balanced split), the chunked loops of gen / prg_gen / eval_all / eval_levelmajor / VDPF host calls, error paths -- with
 "kernels" that digest every byte of every key, so a result is right only if the data reached the mock device intact and in
-the format the launch claimed.  The same binary also runs under ThreadSanitizer and under AddressSanitizer (the mock
+the format the launch claimed.  The same binary also runs under ThreadSanitizer and under AddressSanitizer + UBSan (the mock
 device memory is plain heap memory: an offset error inside a device set is an ASAN report).
 (The real kernels behind the same entry points are covered by the -m gpu tests.)"""
 import os
@@ -37,9 +37,9 @@ def test_host_pipeline_is_tsan_clean(tmp_path):
     assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_host_pipeline_is_asan_clean(tmp_path):
+def test_host_pipeline_is_asan_and_ubsan_clean(tmp_path):
     exe = str(tmp_path / "host_pipe_mock_asan")
-    build(exe, ["-fsanitize=address", "-fno-omit-frame-pointer"])
+    build(exe, ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"])
     r = subprocess.run([exe, "quick"], capture_output=True, text=True, timeout=1500,
                        env=dict(os.environ, FSSB200_PACK_THREADS="6", ASAN_OPTIONS="detect_leaks=0 exitcode=67"))
     assert "AddressSanitizer" not in r.stderr, r.stderr[-6000:]
