@@ -328,6 +328,51 @@ int emul_grotto_walk(const fssb200_params *p, int party, size_t nkeys, const voi
   return 0;
 }
 
+// The tile accessors of kernels.cuh (CwTileT / CwLmTile) fetch chunk c of a key's correction words when the scheme body calls
+// begin_level(j) with j == c << lpc_bits, and request the NEXT chunk (or the next tile's chunk 0) at the same time: a body that
+// skips a chunk boundary, visits one twice or stops before the last chunk leaves the prefetch pipeline out of step with the next
+// tile (the Grotto walk did, before its trailing begin_level(n)).  This records the boundaries a body really visits.
+struct CwCounting {
+  CwKeyMajor inner;
+  int lpc_bits;
+  int *chunks;  // out: chunk index of every boundary visited, in call order
+  int *count;
+  int cap;
+  FSS_HD blk s(int i) const { return inner.s(i); }
+  FSS_HD blk v(int i) const { return inner.v(i); }
+  FSS_HD uint32_t flag(int i) const { return inner.flag(i); }
+  FSS_HD blk out_s(int n) const { return inner.out_s(n); }
+  FSS_HD blk out_v(int n) const { return inner.out_v(n); }
+  FSS_HD void begin_level(int j) const {
+    if (j & ((1 << lpc_bits) - 1)) return;
+    if (*count < cap) chunks[*count] = j >> lpc_bits;
+    ++*count;
+  }
+  FSS_HD void done_level(int) const {}
+};
+// Runs the point-evaluation body of p's scheme on one all-zero key and returns how many chunk boundaries it visited
+// (chunks[0..) = their indices).  Bytes group, the scheme's PRG.
+int emul_chunk_sequence(const fssb200_params *p, int lpc_bits, int *chunks, int cap) {
+  EmuCtx c;
+  make_ctx(*p, c);
+  std::vector<uint8_t> key(size_t(c.ncw + 1) * 32, 0);
+  blk cs[4] = {zero_blk(), zero_blk(), zero_blk(), zero_blk()}, pi[4];
+  int count = 0;
+  const CwCounting cw{CwKeyMajor{key.data()}, lpc_bits, chunks, &count, cap};
+  const InVal x = load_in(key.data(), c.in_bytes);
+  const blk s0 = zero_blk();
+  const auto pc = lane_ctx<kPrgChaCha>(0);
+  switch (p->scheme) {
+    case FSSB200_SCHEME_DPF: dpf_eval_body<kGrpBytes, kPrgChaCha>(c.keys, c.ga, pc, c.n, 0u, s0, x, cw); break;
+    case FSSB200_SCHEME_DCF: dcf_eval_body<kGrpBytes, kPrgChaCha>(c.keys, c.ga, pc, c.n, 0u, s0, x, cw); break;
+    case FSSB200_SCHEME_HALFTREE: ht_eval_body<kGrpBytes, kPrgChaCha>(c.keys, c.ga, pc, c.n, 0u, s0, x, cw, zero_blk()); break;
+    case FSSB200_SCHEME_VDPF: vdpf_eval_body<kGrpBytes, kPrgChaCha>(c.keys, c.ga, pc, c.n, 0u, s0, x, cw, zero_blk(), cs, pi); break;
+    case FSSB200_SCHEME_GROTTO: grotto_walk_body<kPrgChaCha>(c.keys, pc, c.n, c.in_bytes, 0u, s0, x, cw); break;
+    default: return -1;
+  }
+  return count;
+}
+
 int emul_hash(const fssb200_params *p, int which, size_t n, const void *msgs, void *out) {
   EmuCtx c;
   make_ctx(*p, c);

@@ -24,7 +24,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "fss_b200", "csrc")
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC] + [os.path.join(CSRC, f) for f in ("common.cuh", "aes.cuh", "blake3.cuh", "prg.cuh", "group.cuh",
-                                                          "schemes.cuh")]
+                                                          "schemes.cuh", "sha256.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", "-w", "-I/usr/local/cuda/include",
                         SRC, "-o", LIB], check=True)
@@ -168,3 +168,23 @@ def test_grotto_walk_reconstructs_like_the_reference(emu, orc, prg):
             l0 = orc.grotto_lookup(p, orc.grotto_preprocess(p, 0, s0s[:, 0], cws), xs)
             l1 = orc.grotto_lookup(p, orc.grotto_preprocess(p, 1, s0s[:, 1], cws), xs)
             assert np.array_equal(w0 ^ w1, l0 ^ l1), (n, in_bytes, prg)
+
+
+def test_tile_chunk_sequence_of_every_scheme_body(emu):
+    """The TMA tile accessors (kernels.cuh: CwTileT, CwLmTile) request chunk c + 1 -- or the next tile's chunk 0 -- while the
+    scheme body consumes chunk c, so a body must visit the chunk boundaries 0, 1, ..., nchunks - 1 exactly once each and in
+    order, for EVERY domain size, or the per-warp pipeline is out of step from the next tile on (the first Grotto walk was:
+    its body never touched entry n).  nchunks is what point_kernel computes for the mode."""
+    import ctypes
+    buf = (ctypes.c_int * 256)()
+    for scheme in ("dpf", "dcf", "halftree", "vdpf", "grotto"):
+        for n in range(1, 129):
+            p = Params(scheme=scheme, in_bits=n, prg="chacha")
+            cp, ncw = p.c(), p.ncw
+            lpcs = {1}                                   # key-major tiles, modes 4 / 5: two levels per chunk
+            if scheme in ("dpf", "halftree", "vdpf"):
+                lpcs.add(2)                              # packed rows (mode 6) and level-major tiles (mode 7): four levels
+            for lpc in sorted(lpcs):                     # (DCF level-major tiles: two levels = lpc 1, covered above)
+                cnt = emu.emul_chunk_sequence(ctypes.byref(cp), lpc, buf, 256)
+                want = (ncw + (1 << lpc) - 1) >> lpc
+                assert cnt == want and list(buf[:cnt]) == list(range(want)), (scheme, n, lpc, cnt, list(buf[:min(cnt, 8)]))
