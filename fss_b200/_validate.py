@@ -1,8 +1,10 @@
 """Argument validation of the fss_crypto-compatible front-end.
 
-Mirrors the reference's validators (fss_crypto/_validate.py:16-108) -- same function names,
-exception types and message formats, because test/test_validation.py pins them -- extended
-with the batched shapes ``(N, ...)`` this package adds.
+The reference's validators (fss_crypto/_validate.py:16-108) are a public contract: its
+test/test_validation.py imports them by name and pins exception types and message formats.
+Here they are generated from two rule tables (allowed spellings; int32 tensor shapes) so that
+the single-key shapes of the reference and the batched ``(N, ...)`` shapes this package adds
+go through the same two checkers.
 """
 from __future__ import annotations
 
@@ -10,69 +12,88 @@ from numbers import Integral
 
 import torch
 
-_VALID_GROUPS = ("bytes", "uint")
-_VALID_PRGS = ("chacha", "aes128_mmo")
-_VALID_PRGS_BY_SCHEME = {"dpf": _VALID_PRGS, "dcf": _VALID_PRGS}
-_VALID_PREDS = ("lt", "gt")
+# argument -> allowed spellings (reference _validate.py:7-13)
+_CHOICES = {
+    "group": ("bytes", "uint"),
+    "prg": ("chacha", "aes128_mmo"),
+    "pred": ("lt", "gt"),
+    "party": (0, 1),
+}
+# scheme -> PRGs it can be instantiated with (reference _validate.py:9-12)
+_PRGS_OF = {"dpf": _CHOICES["prg"], "dcf": _CHOICES["prg"]}
+# argument -> shape of its int32 tensor; in_bits-dependent entries are callables
+_INT32_SHAPES = {
+    "s0": (4,),
+    "s0s": (2, 4),
+    "beta": (4,),
+    "cws": lambda in_bits: (in_bits + 1, 8),
+}
+
+
+def _require_choice(name: str, value, allowed, shown=None) -> None:
+    if value not in allowed:
+        raise ValueError(f"{name} must be {shown or f'one of {allowed}'}, got {value if name == 'party' else repr(value)}")
+
+
+def _require_int32(name: str, t: torch.Tensor, shape, shown=None) -> None:
+    """``t`` is int32 and ``t.shape`` equals ``shape`` where ``shape`` has an int, anything where it has None."""
+    ok = t.dtype == torch.int32 and t.dim() == len(shape) and all(
+        want is None or want == got for want, got in zip(shape, t.shape))
+    if not ok:
+        shown = shown if shown is not None else tuple(shape)
+        raise TypeError(f"{name} must be a {shown} int32 tensor, got shape {tuple(t.shape)} dtype {t.dtype}")
 
 
 def validate_in_bits(in_bits: int) -> None:
-    if not (1 <= in_bits <= 128):
+    if in_bits < 1 or in_bits > 128:
         raise ValueError(f"in_bits must be between 1 and 128, got {in_bits}")
 
 
 def validate_group(group: str) -> None:
-    if group not in _VALID_GROUPS:
-        raise ValueError(f"group must be one of {_VALID_GROUPS}, got {group!r}")
+    _require_choice("group", group, _CHOICES["group"])
 
 
 def validate_prg(prg: str, scheme: str) -> None:
-    valid = _VALID_PRGS_BY_SCHEME.get(scheme)
-    if valid is None:
-        raise ValueError(f"scheme must be one of {tuple(_VALID_PRGS_BY_SCHEME)}, got {scheme!r}")
-    if prg not in valid:
-        raise ValueError(f"prg must be one of {valid}, got {prg!r}")
+    _require_choice("scheme", scheme, _PRGS_OF, f"one of {tuple(_PRGS_OF)}")
+    _require_choice("prg", prg, _PRGS_OF[scheme])
 
 
 def validate_pred(pred: str) -> None:
-    if pred not in _VALID_PREDS:
-        raise ValueError(f"pred must be one of {_VALID_PREDS}, got {pred!r}")
+    _require_choice("pred", pred, _CHOICES["pred"])
 
 
 def validate_party(party: int) -> None:
-    if party not in (0, 1):
-        raise ValueError(f"party must be 0 or 1, got {party}")
-
-
-def _shape_err(name: str, want, t: torch.Tensor) -> TypeError:
-    return TypeError(f"{name} must be a {want} int32 tensor, got shape {tuple(t.shape)} dtype {t.dtype}")
+    _require_choice("party", party, _CHOICES["party"], "0 or 1")
 
 
 def validate_s0(s0: torch.Tensor) -> None:
-    if s0.shape != (4,) or s0.dtype != torch.int32:
-        raise _shape_err("s0", "(4,)", s0)
+    _require_int32("s0", s0, _INT32_SHAPES["s0"])
 
 
 def validate_s0s(s0s: torch.Tensor) -> None:
-    if s0s.shape != (2, 4) or s0s.dtype != torch.int32:
-        raise _shape_err("s0s", "(2, 4)", s0s)
+    _require_int32("s0s", s0s, _INT32_SHAPES["s0s"])
 
 
 def validate_beta(beta: torch.Tensor) -> None:
-    if beta.shape != (4,) or beta.dtype != torch.int32:
-        raise _shape_err("beta", "(4,)", beta)
+    _require_int32("beta", beta, _INT32_SHAPES["beta"])
 
 
 def validate_cws(cws: torch.Tensor, in_bits: int) -> None:
-    expected = (in_bits + 1, 8)
-    if cws.shape != expected or cws.dtype != torch.int32:
-        raise _shape_err("cws", expected, cws)
+    _require_int32("cws", cws, _INT32_SHAPES["cws"](in_bits))
+
+
+def validate_batched(name: str, t: torch.Tensor, tail: tuple) -> int:
+    """Batched extension (not in the reference): ``t`` must be int32 with shape ``(N, *tail)``; returns N."""
+    tail = tuple(tail)
+    _require_int32(name, t, (None,) + tail, ("N",) + tail)
+    return int(t.shape[0])
 
 
 def validate_domain_value(name: str, value: int, in_bits: int) -> None:
+    """A point of the input domain: a real integer (bool is rejected) below 2^in_bits."""
     if isinstance(value, bool) or not isinstance(value, Integral):
         raise TypeError(f"{name} must be an integer, got {type(value).__name__}")
-    if value < 0 or value >= (1 << in_bits):
+    if not 0 <= value < (1 << in_bits):
         raise ValueError(f"{name} must be in [0, 2^{in_bits}), got {value}")
 
 
@@ -81,24 +102,14 @@ def validate_alpha(alpha: int, in_bits: int) -> None:
 
 
 def validate_device_match(*tensors: torch.Tensor) -> None:
-    devices = {t.device for t in tensors}
-    if len(devices) > 1:
-        dev_list = ", ".join(str(d) for d in sorted(devices, key=str))
+    seen = sorted({str(t.device) for t in tensors})
+    if len(seen) > 1:
         raise RuntimeError(
-            f"expected all tensors to be on the same device, but found at least two devices, {dev_list}!")
+            f"expected all tensors to be on the same device, but found at least two devices, {', '.join(seen)}!")
 
 
 def validate_cpu_only(*tensors: torch.Tensor, fn_name: str = "") -> None:
+    head = f"{fn_name} expects" if fn_name else "expected"
     for t in tensors:
         if t.device.type != "cpu":
-            prefix = f"{fn_name} expects" if fn_name else "expected"
-            raise RuntimeError(f"{prefix} all tensors to be on cpu, but found tensor on {t.device}")
-
-
-# ---- batched extensions (not in the reference) ---------------------------------------------------
-
-def validate_batched(name: str, t: torch.Tensor, tail: tuple) -> int:
-    """``t`` must be int32 with shape ``(N, *tail)``; returns N."""
-    if t.dim() != len(tail) + 1 or tuple(t.shape[1:]) != tuple(tail) or t.dtype != torch.int32:
-        raise _shape_err(name, ("N",) + tuple(tail), t)
-    return int(t.shape[0])
+            raise RuntimeError(f"{head} all tensors to be on cpu, but found tensor on {t.device}")
