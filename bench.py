@@ -88,12 +88,13 @@ def synth_c2(nkeys: int, seed: int):
     return s0s, alphas, betas, xs
 
 
-def cpu_dpf_eval_rate(engine, nkeys: int, threads: int, repeats: int = 1):
-    """Reference Dpf::Eval (dpf.cuh:170-214, Aes128Mmo<2> = OpenSSL AES-NI) over nkeys keys on `threads` host
+def cpu_dpf_eval_rate(engine, nkeys: int, threads: int, repeats: int = 1, prg: str = "aes128_mmo"):
+    """Reference Dpf::Eval (dpf.cuh:170-214, Aes128Mmo<2> = OpenSSL AES-NI; prg="aes128_mmo_raw": Aes128MmoRaw<2>, the
+    reference's own AES-NI intrinsics, SURVEY.md section 8d's "fair AES-NI ceiling") over nkeys keys on `threads` host
     threads, one PRG context set per thread.  Returns (evals/s, seconds per pass)."""
     import numpy as np
     from oracle import Params
-    p = Params(scheme="dpf", in_bits=N_BITS, group="bytes", prg="aes128_mmo")
+    p = Params(scheme="dpf", in_bits=N_BITS, group="bytes", prg=prg)
     s0s, alphas, betas, xs = synth_c2(nkeys, 42)
     cws = engine.gen(p, s0s, alphas, betas, threads=threads)
     seeds = np.ascontiguousarray(s0s[:, 0])
@@ -874,6 +875,15 @@ def run_own_arm(args) -> None:
                         "sample": f"{sample} of the 2^22 keys, best of 3 passes ({secs:.2f} s each), reference "
                                   f"Dpf::Eval with Aes128Mmo<2> (OpenSSL AES-NI), one EVP ctx set per thread",
                         "single_thread_value": rate1}
+        if eng.kind == "reference":   # (ii) of SURVEY.md section 8d: the same Eval with the reference's raw AES-NI PRG
+            try:
+                rate_raw, _ = cpu_dpf_eval_rate(eng, sample, threads, 2, prg="aes128_mmo_raw")
+                cpu_baseline["aesni_raw_value"] = rate_raw
+                cpu_baseline["aesni_raw_note"] = ("reference Dpf::Eval with Aes128MmoRaw<2> (AES-NI intrinsics, no EVP call "
+                                                  "overhead), same sample and threads: the CPU ceiling, not the PRG north_star names")
+            except Exception as e:   # an engine built without the raw PRG: the headline baseline stands on its own
+                cpu_baseline["aesni_raw_value"] = None
+                cpu_baseline["aesni_raw_note"] = f"unavailable: {e}"
 
     if rank == 0:
         roofline["kernels"] = extra   # (the driver keeps `roofline`; `extra` is kept for older readers)
