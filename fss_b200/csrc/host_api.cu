@@ -1152,30 +1152,38 @@ int fssb200_eval_all_host(fssb200_ctx *c, int party, const void *seeds, const vo
   if (grotto && leaf_begin != 0) return FSSB200_ERANGE;
   if (nkeys == 0) return 0;
   const size_t cwb = size_t(c->ncw) * 32, leaf_bytes = grotto ? 1 : 16;
-  // key material of one key (seed + cws + ocw) at the front of each set, leaves behind it
-  const size_t hdr = align_up(16 + cwb + 16, 256);
   // 64 MiB of leaves per set (Grotto: the scan needs whole keys)
-  uint64_t leaves_per_chunk = grotto ? leaf_count : std::min<uint64_t>(leaf_count, (uint64_t(64) << 20) / leaf_bytes);
+  const uint64_t set_leaves = (uint64_t(std::min(4096, std::max(1, env_int("FSSB200_ALL_SET_MB", 64)))) << 20) / leaf_bytes;
+  uint64_t leaves_per_chunk = grotto ? leaf_count : std::min<uint64_t>(leaf_count, set_leaves);
   leaves_per_chunk = std::max<uint64_t>(granule, leaves_per_chunk / granule * granule);
-  const size_t set_bytes = align_up(hdr + leaves_per_chunk * leaf_bytes, 256);
-  const bool many = nkeys > 1 || leaf_count > leaves_per_chunk;
+  // Small domains: one launch and one copy each way serve as many whole keys as fit the set (the leaves of consecutive keys
+  // are contiguous in `ys` exactly when a chunk holds whole ranges).  Large domains: one key at a time, range by range.
+  size_t kc = 1;
+  if (leaves_per_chunk == leaf_count)
+    kc = size_t(std::min<uint64_t>(chunk_pref(c, nkeys, 65536), std::max<uint64_t>(1, set_leaves / leaf_count)));
+  // key material of the chunk's keys (seeds | cws | ocws) at the front of each set, leaves behind it
+  const size_t off_cws = align_up(kc * 16, 256), off_ocws = off_cws + align_up(kc * cwb, 256),
+               hdr = off_ocws + align_up(kc * 16, 256);
+  const size_t set_bytes = align_up(hdr + std::max<uint64_t>(leaves_per_chunk, kc * leaf_count) * leaf_bytes, 256);
+  const bool many = nkeys > kc || leaf_count > leaves_per_chunk;
   ArenaLease L(c->p.device, set_bytes * (many ? 2 : 1), 0);
   if (!L.a) return L.rc;
   Arena &A = *L.a;
   int rc = 0;
   size_t chunk = 0;
-  for (size_t k = 0; k < nkeys && !rc; ++k) {
+  for (size_t k0 = 0; k0 < nkeys && !rc; k0 += kc) {
+    const size_t k = std::min(kc, nkeys - k0);
     for (uint64_t l0 = 0; l0 < leaf_count && !rc; l0 += leaves_per_chunk, ++chunk) {
-      const uint64_t cnt = std::min<uint64_t>(leaves_per_chunk, leaf_count - l0);
+      const uint64_t cnt = std::min<uint64_t>(leaves_per_chunk, leaf_count - l0);  // (k > 1 only with cnt == leaf_count)
       const int b = int(chunk & 1);
       cudaStream_t s = A.stream[b];
-      uint8_t *d_seed = A.dev + size_t(b) * set_bytes, *d_cws = d_seed + 16, *d_ocw = d_cws + cwb, *d_ys = d_seed + hdr;
-      TRY_BREAK(H2D(d_seed, static_cast<const uint8_t *>(seeds) + k * 16, 16, s));
-      TRY_BREAK(H2D(d_cws, static_cast<const uint8_t *>(cws) + k * cwb, cwb, s));
-      if (half) TRY_BREAK(H2D(d_ocw, static_cast<const uint8_t *>(ocws) + k * 16, 16, s));
-      rc = fssb200_eval_all(c, party, d_seed, d_cws, half ? d_ocw : nullptr, d_ys, 1, leaf_begin + l0, cnt, s);
+      uint8_t *d_seed = A.dev + size_t(b) * set_bytes, *d_cws = d_seed + off_cws, *d_ocw = d_seed + off_ocws, *d_ys = d_seed + hdr;
+      TRY_BREAK(H2D(d_seed, static_cast<const uint8_t *>(seeds) + k0 * 16, k * 16, s));
+      TRY_BREAK(H2D(d_cws, static_cast<const uint8_t *>(cws) + k0 * cwb, k * cwb, s));
+      if (half) TRY_BREAK(H2D(d_ocw, static_cast<const uint8_t *>(ocws) + k0 * 16, k * 16, s));
+      rc = fssb200_eval_all(c, party, d_seed, d_cws, half ? d_ocw : nullptr, d_ys, k, leaf_begin + l0, cnt, s);
       if (rc) break;
-      TRY_BREAK(D2H(static_cast<uint8_t *>(ys) + (k * leaf_count + l0) * leaf_bytes, d_ys, cnt * leaf_bytes, s));
+      TRY_BREAK(D2H(static_cast<uint8_t *>(ys) + (k0 * leaf_count + l0) * leaf_bytes, d_ys, k * cnt * leaf_bytes, s));
     }
   }
   return L.drain(rc);

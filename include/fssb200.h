@@ -338,6 +338,9 @@ void fssb200_host_trim(void);
 int fssb200_host_cached_bytes(uint64_t *device_bytes, uint64_t *pinned_bytes);
 int fssb200_eval_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
                       const void *ocws, const void *xs, void *ys, size_t nkeys);
+/* ys = [nkeys][leaf_count] in host memory.  Sets of 64 MiB of leaves (FSSB200_ALL_SET_MB): a small
+ * domain's keys go as many whole keys per launch and copy as fit one set (at most the keys per chunk
+ * of fssb200_ctx_reserve_host), a large domain's one key at a time in leaf ranges. */
 int fssb200_eval_all_host(fssb200_ctx *ctx, int party, const void *seeds, const void *cws,
                           const void *ocws, void *ys, size_t nkeys, uint64_t leaf_begin,
                           uint64_t leaf_count);

@@ -466,7 +466,15 @@ int main(int argc, char **argv) {
     // eval_all_host: several keys, leaf ranges (granule 1 in the mock), Half-Tree ocws, Grotto bytes
     fssb200_ctx *ea_dpf = MakeCtx(FSSB200_SCHEME_DPF, 12, 2), *ea_ht = MakeCtx(FSSB200_SCHEME_HALFTREE, 10, 2),
                 *ea_gr = MakeCtx(FSSB200_SCHEME_GROTTO, 11, 2);
-    for (fssb200_ctx *c : {ea_dpf, ea_ht, ea_gr}) {
+    // geometries: every key in one launch | groups of 2 + a ragged last group | one key at a time in ranges of 1 MiB of leaves
+    // (n = 17: 2 MiB per key, two ranges) -- (keys-per-chunk cap, FSSB200_ALL_SET_MB, in_bits of the DPF / Half-Tree contexts)
+    fssb200_ctx *ea_big = MakeCtx(FSSB200_SCHEME_DPF, 17, 4), *ea_big_ht = MakeCtx(FSSB200_SCHEME_HALFTREE, 17, 4);
+    struct AllGeo { size_t cap; const char *set_mb; bool big; };
+    for (const AllGeo geo : {AllGeo{0, "64", false}, AllGeo{2, "64", false}, AllGeo{0, "1", true}})
+    for (fssb200_ctx *c : {geo.big ? ea_big : ea_dpf, geo.big ? ea_big_ht : ea_ht, ea_gr}) {
+      setenv("FSSB200_ALL_SET_MB", geo.set_mb, 1);
+      fssb200_ctx_reserve_host(c, geo.cap);
+      const long launches0 = g_kernel_launches.load();
       const size_t nk = 5, cwb = size_t(c->ncw) * 32, lb = c->p.scheme == FSSB200_SCHEME_GROTTO ? 1 : 16;
       const bool half = c->p.scheme == FSSB200_SCHEME_HALFTREE, grotto = c->p.scheme == FSSB200_SCHEME_GROTTO;
       const uint64_t N = uint64_t(1) << c->p.in_bits;
@@ -490,6 +498,13 @@ int main(int argc, char **argv) {
               (unsigned long long)range.first, (unsigned long long)range.second, rc, bad);
       }
       CHECK(fssb200_eval_all_host(c, 1, seeds.data(), cws.data(), ocws.data(), seeds.data(), 1, N, 0) == FSSB200_ERANGE, "eval_all_host range check");
+      // launches of the three (Grotto: one) ranges: 1 per range with every key in one chunk, 3 with groups of 2, 2, 1
+      const long launches = g_kernel_launches.load() - launches0, ranges = grotto ? 1 : 3;
+      if (!geo.big) CHECK(launches == ranges * (geo.cap ? 3 : 1), "eval_all_host scheme %d cap %zu: %ld launches", c->p.scheme, geo.cap, launches);
+      // 1 MiB sets: the whole range = 2 chunks per key, the half range = 1 per key, the 7-leaf range = one launch for all keys
+      if (geo.big && !grotto) CHECK(launches == long(nk) * 3 + 1, "eval_all_host scheme %d ranges: %ld launches", c->p.scheme, launches);
+      fssb200_ctx_reserve_host(c, 0);
+      unsetenv("FSSB200_ALL_SET_MB");
     }
     // eval_levelmajor_host: strided gathers of [level][key] arrays, chunks with a ragged tail; DPF (extra + out_cw), DCF (cw_v + out_cw),
     // Half-Tree (extra + ocws), and a 100-level domain (4 control-bit words per key)
