@@ -226,6 +226,37 @@ def test_host_entry_points(dev, orc):
     assert np.array_equal(N(ya), orc.evalall(p2, 0, s0s[:, 0], oc, threads=8))
 
 
+@pytest.mark.parametrize("scheme,n,group,nkeys,cap,set_mb", [
+    ("dpf", 10, "u64", 7, 0, None),       # every key in one launch
+    ("dpf", 10, "bytes", 7, 3, None),     # groups of 3, 3, 1 keys
+    ("halftree", 9, "u32", 5, 2, None),   # ... with per-key ocws
+    ("grotto", 11, "bytes", 5, 2, None),  # ... byte leaves + the scan
+    ("dcf", 12, "u128", 4, 0, None),
+    ("dpf", 18, "u64", 3, 0, "1"),        # 1 MiB sets: one key at a time, 4 leaf ranges each
+    ("dpf", 17, "bytes", 3, 0, "4"),      # 4 MiB sets: two whole keys per launch, then one
+])
+def test_eval_all_host_geometries(dev, orc, monkeypatch, scheme, n, group, nkeys, cap, set_mb):
+    """fssb200_eval_all_host: whole keys per launch for small domains, leaf ranges of one key for large ones."""
+    p = Params(scheme=scheme, in_bits=n, group=group, hash_key=HASH_KEY_BENCH)
+    ctx = mkctx(p)
+    ctx.reserve_host(cap)
+    if set_mb:
+        monkeypatch.setenv("FSSB200_ALL_SET_MB", set_mb)
+    s0s, alphas, betas, _ = synth_inputs(p, nkeys, seed=40 + n)
+    o = orc.gen(p, s0s, alphas, None if scheme == "grotto" else betas)
+    oc, ooc = o if scheme == "halftree" else (o, None)
+    H = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32))
+    for party in (0, 1):
+        got = ctx.eval_all(party, H(s0s[:, party]), H(oc), None if ooc is None else H(ooc))
+        assert got.device.type == "cpu"
+        want = orc.evalall(p, party, s0s[:, party], oc, ooc, threads=8)
+        assert np.array_equal(N(got, want.dtype), want), party
+    g = ctx.granule()
+    if (1 << n) > g and scheme != "grotto":
+        got = ctx.eval_all(0, H(s0s[:, 0]), H(oc), None if ooc is None else H(ooc), leaf_begin=g, leaf_count=g)
+        assert np.array_equal(N(got, want.dtype), orc.evalall(p, 0, s0s[:, 0], oc, ooc, threads=8)[:, g:2 * g])
+
+
 # ---- packed rows (compact key format) and the packing host path -----------------------------------------------------
 
 @pytest.mark.parametrize("scheme,n,group,prg,nkeys", [
