@@ -29,13 +29,13 @@ def test_reference_group_axioms_on_the_shim_groups():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,at_least", [("dpf", 10), ("dcf", 7), ("half_tree_dpf", 27), ("grotto_dcf", 5), ("vdpf", 8)])
+@pytest.mark.parametrize("name,at_least", [("dpf", 10), ("dcf", 7), ("half_tree_dpf", 27), ("grotto_dcf", 5), ("vdpf", 8), ("vdmpf", 7)])
 def test_reference_gtest_suite_passes_against_this_library(name, at_least):
     assert run(name) >= at_least
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["dpf_dcf_cpu", "half_tree_dpf_cpu", "grotto_dcf_cpu", "vdpf_cpu", "dpf_dcf_gpu"])
+@pytest.mark.parametrize("name", ["dpf_dcf_cpu", "half_tree_dpf_cpu", "grotto_dcf_cpu", "vdpf_cpu", "vdmpf_cpu", "dpf_dcf_gpu"])
 def test_reference_sample_runs_against_this_library(name):
     """The reference's samples/*.cu, unmodified, built against include/ of this repository.  dpf_dcf_gpu.cu is the
     documented in-kernel usage (README.md:198-242): `dpf.Gen` / `dpf.Eval` called per thread inside the sample's own
@@ -50,3 +50,16 @@ def test_reference_sample_runs_against_this_library(name):
     assert "? no" not in out and not re.search(r"\?\s+NO\b", out) and not re.search(r"mismatches[^\n]*: [1-9]", out), out
     for m in re.finditer(r"Verification: (\d+)/(\d+) correct", out):
         assert m.group(1) == m.group(2), out
+
+
+@pytest.mark.gpu
+def test_reference_cpu_gpu_parity_check_runs_against_this_library():
+    """check_evalall_gpu.cu (the only CPU == GPU check in the reference's tree), unmodified:
+    the free functions fss::gpu::DpfEvalAllGpu / HalfTreeDpfEvalAllGpu on device arrays against the members' EvalAll on host
+    arrays (n = 20, Uint<uint64_t>, ChaCha), and the reconstruction of the device outputs at / off alpha."""
+    exe = os.path.join(BIN, "check_evalall_gpu")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs the reference checkout: make -C oracle reftests)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL PASS" in r.stdout and "FAIL" not in r.stdout.replace("FAILURES", ""), r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.stdout.count("PASS") >= 6, r.stdout

@@ -1,0 +1,99 @@
+"""The multi-point scheme on top of the VDPF batch (include/fss/vdmpf.cuh, cuckoo_hash.cuh, prp.cuh, prp/aes128_feistel.cuh;
+reference vdmpf.cuh:80-279, cuckoo_hash.cuh, prp/aes128_feistel.cuh).
+
+* The PRP and the cuckoo hashing are host code: tests/cpp/prp_cuckoo_parity.cpp must print, line for line, what the SAME
+  source prints when compiled against the reference's unmodified headers (tests/golden/prp_cuckoo_v1.txt).
+* Gen / BatchEval (tests/cpp/vdmpf_parity.cpp: key digests, output shares, proofs of four parameter sets) against
+  tests/golden/vdmpf_v1.txt -- on the CPU with the inner-VDPF batches answered by the oracle
+  (tests/host_emul/fake_backend.cpp: this checks the HOST logic of the shim -- table, grouping, gathers, proof chains), and
+  on the B200 (-m gpu) with libfssb200.so.
+* The reference's own src/vdmpf_test.cu and samples/vdmpf_cpu.cu, unmodified, against include/ of this repository: here over
+  the fake backend where the reference checkout exists, on the B200 through tests/test_ref_gtests.py."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "tests", "cpp")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+INC = ["-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include"]
+GOMP = ["-L/usr/lib/gcc/x86_64-linux-gnu/13", "-lgomp"]
+ORACLE = ["-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
+REF = "/root/reference"
+GTEST_INC = os.path.join(REF, "third_party/fss-v0.7.0/fss-v0.7.0/third_party/googletest/googletest/include")
+GTEST_LIB = os.path.join(ROOT, "oracle", "_ref", "gtest", "lib")
+
+
+def sh(*cmd):
+    subprocess.run(list(cmd), check=True)
+
+
+def fake_backend(tmp_path):
+    obj = str(tmp_path / "fake_backend.o")
+    sh("g++", "-std=c++17", "-O1", "-w", "-I", "/usr/local/cuda/include", "-c", os.path.join(ROOT, "tests", "host_emul", "fake_backend.cpp"),
+       "-o", obj)
+    return obj
+
+
+def test_prp_and_cuckoo_hash_match_the_reference(tmp_path):
+    exe = str(tmp_path / "prp_cuckoo")
+    sh("g++", "-std=c++20", "-O1", "-w", "-x", "c++", *INC, os.path.join(CPP, "prp_cuckoo_parity.cpp"), "-o", exe)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
+    assert out == open(os.path.join(GOLDEN, "prp_cuckoo_v1.txt")).read()
+    assert "bijection=1" in out and out.count("rc=0") >= 40 and out.count("rc=1") >= 40  # both outcomes of the walk are pinned
+
+
+def test_golden_files_are_the_reference_output(tmp_path):
+    if not os.path.isdir(os.path.join(REF, "include", "fss")):
+        pytest.skip("reference checkout not present")
+    before = {n: open(os.path.join(GOLDEN, n)).read() for n in ("vdmpf_v1.txt", "prp_cuckoo_v1.txt")}
+    subprocess.run(["python", os.path.join(ROOT, "oracle", "make_golden_vdmpf.py")], check=True, capture_output=True)
+    for n, text in before.items():
+        assert open(os.path.join(GOLDEN, n)).read() == text, n
+    assert before["vdmpf_v1.txt"].count("verify=1") == 12 and "tries=2" in before["vdmpf_v1.txt"]
+
+
+def test_vdmpf_host_logic_over_the_oracle_backend(tmp_path):
+    """Gen / BatchEval of the shim with the inner VDPF batches computed by the oracle: bit-identical keys, shares and proofs,
+    and the work reaches the backend as BATCHES (one Gen batch per Gen, one Eval batch per BatchEval)."""
+    exe = str(tmp_path / "vdmpf_parity")
+    sh("g++", "-std=c++20", "-O1", "-fopenmp", "-w", "-x", "c++", *INC, os.path.join(CPP, "vdmpf_parity.cpp"), "-x", "none",
+       fake_backend(tmp_path), "-o", exe, *ORACLE, *GOMP)
+    r = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600)
+    assert r.stdout == open(os.path.join(GOLDEN, "vdmpf_v1.txt")).read()
+    m = re.search(r"vdpf_gen_host batches: (\d+), vdpf_eval_host batches: (\d+), vdpf_prove batches: (\d+)", r.stderr)
+    # 4 parameter sets x 2 Gen tries (the first fails in the cuckoo walk before any key is generated) -> 4 Gen batches;
+    # 4 x 2 parties x 2 non-empty BatchEval calls -> 16 Eval batches; the empty call evaluates nothing
+    assert m and int(m.group(1)) == 4 and int(m.group(2)) == 16, r.stderr
+
+
+@pytest.mark.parametrize("what", ["vdmpf_test", "vdmpf_cpu"])
+def test_reference_vdmpf_sources_over_the_oracle_backend(tmp_path, what):
+    """The reference's gtest suite / sample of the scheme, unmodified, on the shim headers + the CPU backend."""
+    if not os.path.isdir(os.path.join(REF, "include", "fss")) or not os.path.exists(os.path.join(GTEST_LIB, "libgtest.a")):
+        pytest.skip("reference checkout / googletest build not present")
+    exe, obj = str(tmp_path / what), str(tmp_path / (what + ".o"))
+    if what == "vdmpf_test":
+        sh("g++", "-std=c++20", "-O1", "-fopenmp", "-w", "-x", "c++", *INC, "-I", GTEST_INC, "-c", os.path.join(REF, "src", "vdmpf_test.cu"), "-o", obj)
+        sh("g++", obj, fake_backend(tmp_path), os.path.join(GTEST_LIB, "libgtest_main.a"), os.path.join(GTEST_LIB, "libgtest.a"), "-o", exe,
+           *ORACLE, *GOMP, "-lpthread")
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "[  PASSED  ] 7 tests" in r.stdout and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    else:
+        sh("g++", "-std=c++20", "-O1", "-fopenmp", "-w", "-x", "c++", *INC, "-c", os.path.join(REF, "samples", "vdmpf_cpu.cu"), "-o", obj)
+        sh("g++", obj, fake_backend(tmp_path), "-o", exe, *ORACLE, *GOMP, "-lpthread")
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and r.stdout.count("mismatches: 0") == 2, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_vdmpf_on_the_gpu_matches_the_reference(tmp_path):
+    """The same program on the B200: every inner VDPF batch runs in the sm_100a kernels behind the C ABI."""
+    exe = str(tmp_path / "vdmpf_parity")
+    sh("g++", "-std=c++20", "-O1", "-fopenmp", "-w", "-x", "c++", *INC, os.path.join(CPP, "vdmpf_parity.cpp"), "-o", exe, "-L",
+       os.path.join(ROOT, "fss_b200"), "-lfssb200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "fss_b200"), *GOMP)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.stdout == open(os.path.join(GOLDEN, "vdmpf_v1.txt")).read()
