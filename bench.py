@@ -107,6 +107,57 @@ def cpu_dpf_eval_rate(engine, nkeys: int, threads: int, repeats: int = 1, prg: s
     return nkeys / best, best
 
 
+def cpu_other_rates(engine, threads: int) -> dict:
+    """The reference's CPU path for the other BASELINE configs, timed beside the GPU rows of `roofline.kernels` (SURVEY.md
+    section 8d "CPU baseline timing"): C3 = Dcf::Eval n=64 Uint<u128, 2^127> Aes128Mmo<4> over a bounded key sample, C4 =
+    Dpf::EvalAll at the CPU-sized n=24 (2^28 leaves take ~16 s per key and core), one key per thread, one PRG context set per
+    thread.  Numpy inputs only: no Python integer conversion inside the timed calls."""
+    import numpy as np
+    from oracle import Params
+    out = {}
+    rng = np.random.default_rng(7)
+
+    def keys(p, k):
+        s0s = rng.integers(0, 2 ** 32, size=(k, 2, 4), dtype=np.uint64).astype(np.uint32)
+        s0s[:, :, 3] &= 0xFFFFFFFE
+        betas = rng.integers(0, 2 ** 32, size=(k, 4), dtype=np.uint64).astype(np.uint32)
+        betas[:, 3] &= 0xFFFFFFFE
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[p.in_bytes]
+        hi = 1 << p.in_bits
+        alphas = rng.integers(0, hi, size=k, dtype=np.uint64).astype(dt)
+        xs = rng.integers(0, hi, size=k, dtype=np.uint64).astype(dt)
+        xs[::16] = alphas[::16]
+        return s0s, alphas, betas, xs
+
+    def best_of(fn, n=2):
+        best = None
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+        return best
+
+    p3 = Params(scheme="dcf", in_bits=64, group="u128", prg="aes128_mmo")
+    k3 = 1 << 16
+    s0s, alphas, betas, xs = keys(p3, k3)
+    cws = engine.gen(p3, s0s, alphas, betas, threads=threads)
+    seeds = np.ascontiguousarray(s0s[:, 0])
+    t3 = best_of(lambda: engine.eval(p3, 0, seeds, cws, xs, threads=threads))
+    out["c3_dcf_eval_n64_u127"] = {"value": k3 / t3, "unit": "evals/s", "cores": threads,
+                                   "sample": f"{k3} keys, reference Dcf::Eval with Aes128Mmo<4>, best of 2 passes ({t3:.2f} s each)"}
+    p4 = Params(scheme="dpf", in_bits=24, group="bytes", prg="aes128_mmo")
+    k4 = max(1, min(threads, 4))
+    s0s, alphas, betas, _ = keys(p4, k4)
+    cws = engine.gen(p4, s0s, alphas, betas, threads=k4)
+    seeds = np.ascontiguousarray(s0s[:, 0])
+    t4 = best_of(lambda: engine.evalall(p4, 0, seeds, cws, threads=k4), 1)
+    out["c4_dpf_evalall_n24"] = {"value": k4 * (1 << 24) / t4, "unit": "leaves/s", "cores": k4,
+                                 "sample": f"{k4} keys x 2^24 leaves (the CPU-sized domain of SURVEY.md section 8d), reference "
+                                           f"Dpf::EvalAll, one key per thread, one pass ({t4:.2f} s, includes allocating the output)"}
+    return out
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -875,6 +926,10 @@ def run_own_arm(args) -> None:
                         "sample": f"{sample} of the 2^22 keys, best of 3 passes ({secs:.2f} s each), reference "
                                   f"Dpf::Eval with Aes128Mmo<2> (OpenSSL AES-NI), one EVP ctx set per thread",
                         "single_thread_value": rate1}
+        try:
+            cpu_baseline["others"] = cpu_other_rates(eng, threads)
+        except Exception as e:   # (an engine without these instantiations: the headline baseline stands on its own)
+            cpu_baseline["others"] = {"unavailable": str(e)}
         if eng.kind == "reference":   # (ii) of SURVEY.md section 8d: the same Eval with the reference's raw AES-NI PRG
             try:
                 rate_raw, _ = cpu_dpf_eval_rate(eng, sample, threads, 2, prg="aes128_mmo_raw")
