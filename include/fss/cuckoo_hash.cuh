@@ -68,11 +68,24 @@ struct PrpHash {
     const __uint128_t bs = static_cast<__uint128_t>(b_size);
     return {static_cast<int>(y / bs), static_cast<int>(y % bs)};
   }
-  // The kappa candidate places of every element, element-major: out[i * kappa + k].
+  // The kappa candidate places of every element, element-major: out[i * kappa + k].  The calls are independent; large
+  // batches (the inputs of a BatchEval) are spread over the host's cores when the translation unit is built with OpenMP,
+  // every thread with its own copy of the PRP (a PRP object may keep per-seed state and need not be thread-safe).
   std::vector<std::pair<int, int>> Locations(int4 sigma, std::span<const In> xs, __uint128_t n, int b_size) {
     std::vector<std::pair<int, int>> out(xs.size() * size_t(kappa));
-    for (size_t i = 0; i < xs.size(); ++i)
-      for (int k = 0; k < kappa; ++k) out[i * size_t(kappa) + size_t(k)] = Locate(sigma, xs[i], k, n, b_size);
+    const long long count = static_cast<long long>(xs.size());
+#if defined(_OPENMP)
+#pragma omp parallel if (count >= 2048)
+    {
+      PrpHash local{prp};
+#pragma omp for schedule(static)
+      for (long long i = 0; i < count; ++i)
+        for (int k = 0; k < kappa; ++k) out[size_t(i) * size_t(kappa) + size_t(k)] = local.Locate(sigma, xs[size_t(i)], k, n, b_size);
+    }
+#else
+    for (long long i = 0; i < count; ++i)
+      for (int k = 0; k < kappa; ++k) out[size_t(i) * size_t(kappa) + size_t(k)] = Locate(sigma, xs[size_t(i)], k, n, b_size);
+#endif
     return out;
   }
 };

@@ -111,6 +111,7 @@ int main() {
     H h(cuda::std::span<const int4, 2>(iv, 2));
     fss::Vdmpf<16, 64, 13, G, P, H, H, fss::prp::Aes128Feistel, uint16_t> v{prg, h, h, prp};
     Run<decltype(v), uint16_t, 16, 13>("bytes/chacha/blake3 n=16", v, 64, 300);
+    Run<decltype(v), uint16_t, 16, 13>("bytes/chacha/blake3 n=16, a batch of 6000 inputs", v, 50, 6000);
     Run<decltype(v), uint16_t, 16, 13>("bytes/chacha/blake3 n=16 (fewer points than the key is sized for)", v, 31, 40);
   }
   {

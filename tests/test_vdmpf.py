@@ -52,7 +52,7 @@ def test_golden_files_are_the_reference_output(tmp_path):
     subprocess.run(["python", os.path.join(ROOT, "oracle", "make_golden_vdmpf.py")], check=True, capture_output=True)
     for n, text in before.items():
         assert open(os.path.join(GOLDEN, n)).read() == text, n
-    assert before["vdmpf_v1.txt"].count("verify=1") == 12 and "tries=2" in before["vdmpf_v1.txt"]
+    assert before["vdmpf_v1.txt"].count("verify=1") == 15 and "tries=2" in before["vdmpf_v1.txt"]
 
 
 def test_vdmpf_host_logic_over_the_oracle_backend(tmp_path):
@@ -64,9 +64,9 @@ def test_vdmpf_host_logic_over_the_oracle_backend(tmp_path):
     r = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600)
     assert r.stdout == open(os.path.join(GOLDEN, "vdmpf_v1.txt")).read()
     m = re.search(r"vdpf_gen_host batches: (\d+), vdpf_eval_host batches: (\d+), vdpf_prove batches: (\d+)", r.stderr)
-    # 4 parameter sets x 2 Gen tries (the first fails in the cuckoo walk before any key is generated) -> 4 Gen batches;
-    # 4 x 2 parties x 2 non-empty BatchEval calls -> 16 Eval batches; the empty call evaluates nothing
-    assert m and int(m.group(1)) == 4 and int(m.group(2)) == 16, r.stderr
+    # 5 runs x 2 Gen tries (the first fails in the cuckoo walk before any key is generated) -> 5 Gen batches;
+    # 5 x 2 parties x 2 non-empty BatchEval calls -> 20 Eval batches; the empty call evaluates nothing
+    assert m and int(m.group(1)) == 5 and int(m.group(2)) == 20, r.stderr
 
 
 @pytest.mark.parametrize("what", ["vdmpf_test", "vdmpf_cpu"])
