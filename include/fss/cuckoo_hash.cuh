@@ -13,6 +13,7 @@
 // give up after ch_retry evictions) is the reference's, draw for draw.
 #pragma once
 #include <cassert>
+#include <cstddef>
 #include <random>
 #include <span>
 #include <utility>

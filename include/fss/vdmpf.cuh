@@ -14,6 +14,7 @@
 //     same number of inputs form one batch) and the chain over the m buckets is one more such call.
 // Outputs and proofs are bit-identical to the reference's for the same key and inputs (tests/test_vdmpf.py).
 #pragma once
+#include <algorithm>
 #include <cassert>
 #include <cstddef>
 #include <cstring>
