@@ -4,9 +4,15 @@
 // (fss/cuckoo_hash.cuh, fss/vdmpf.cuh) is written against it.
 #pragma once
 #include <concepts>
+#include <utility>
 #include <cuda_runtime.h>
 
+namespace fss::b200 {
+// what `prp.Permu(seed, value, domain_size)` returns for a non-const plugin object (PRPs may cache per-seed state)
+template <typename P>
+using PermuResult = decltype(std::declval<P &>().Permu(std::declval<int4>(), std::declval<__uint128_t>(), std::declval<__uint128_t>()));
+}  // namespace fss::b200
+
+// A plugin is Permutable when that call is well-formed and yields a 128-bit unsigned value.
 template <typename Prp>
-concept Permutable = requires(Prp prp, int4 seed, __uint128_t x, __uint128_t domain) {
-  { prp.Permu(seed, x, domain) } -> std::same_as<__uint128_t>;
-};
+concept Permutable = requires { typename fss::b200::PermuResult<Prp>; } && std::same_as<fss::b200::PermuResult<Prp>, __uint128_t>;
