@@ -28,6 +28,47 @@ def test_reference_group_axioms_on_the_shim_groups():
     assert run("group") >= 30
 
 
+GOMP = ["-L/usr/lib/gcc/x86_64-linux-gnu/13", "-lgomp"]
+
+
+def link_over_the_oracle_backend(tmp_path, obj, exe, extra=()):
+    """Links a test object of the reference (built against include/ of this repository by oracle/Makefile) with
+    tests/host_emul/fake_backend.cpp: the C ABI answered by the oracle on the CPU instead of libfssb200.so."""
+    fake = str(tmp_path / "fake_backend.o")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-w", "-I", "/usr/local/cuda/include", "-c",
+                    os.path.join(ROOT, "tests", "host_emul", "fake_backend.cpp"), "-o", fake], check=True)
+    subprocess.run(["g++", obj, fake, *extra, "-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
+                    *GOMP, "-lpthread", "-o", exe], check=True)
+
+
+@pytest.mark.parametrize("name,tests", [("dpf", 11), ("dcf", 7), ("half_tree_dpf", 27), ("grotto_dcf", 5), ("vdpf", 8), ("vdmpf", 7)])
+def test_reference_gtest_suite_on_the_cpu_over_the_oracle_backend(tmp_path, name, tests):
+    """The header shim's host side without a GPU: the reference's suites, unmodified, with every C-ABI batch answered by the
+    oracle.  What this pins is the shim -- parameter marshalling for every scheme x group x PRG the suites instantiate, key
+    layouts, the multi-point host logic; the kernels behind the same calls are pinned by the -m gpu run of the same sources."""
+    obj = os.path.join(BIN, name + "_test.o")
+    gtest = os.path.join(ROOT, "oracle", "_ref", "gtest", "lib")
+    if not os.path.exists(obj) or not os.path.exists(os.path.join(gtest, "libgtest.a")):
+        pytest.skip(f"{obj} not built (needs the reference checkout: make -C oracle reftests)")
+    exe = str(tmp_path / (name + "_test_cpu"))
+    link_over_the_oracle_backend(tmp_path, obj, exe, [os.path.join(gtest, "libgtest_main.a"), os.path.join(gtest, "libgtest.a")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and f"[  PASSED  ] {tests} tests" in r.stdout and "FAILED" not in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["dpf_dcf_cpu", "half_tree_dpf_cpu", "grotto_dcf_cpu", "vdpf_cpu", "vdmpf_cpu"])
+def test_reference_sample_on_the_cpu_over_the_oracle_backend(tmp_path, name):
+    obj = os.path.join(BIN, "sample_" + name + ".o")
+    if not os.path.exists(obj):
+        pytest.skip(f"{obj} not built (needs the reference checkout: make -C oracle reftests)")
+    exe = str(tmp_path / ("sample_" + name + "_cpu"))
+    link_over_the_oracle_backend(tmp_path, obj, exe)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    out = r.stdout
+    assert r.returncode == 0 and "===" in out, out[-3000:] + r.stderr[-2000:]
+    assert "? no" not in out and not re.search(r"\?\s+NO\b", out) and not re.search(r"mismatches[^\n]*: [1-9]", out), out
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,at_least", [("dpf", 10), ("dcf", 7), ("half_tree_dpf", 27), ("grotto_dcf", 5), ("vdpf", 8), ("vdmpf", 7)])
 def test_reference_gtest_suite_passes_against_this_library(name, at_least):
