@@ -1,6 +1,6 @@
 // SPDX-License-Identifier: Apache-2.0
-// fss/b200/generic.cuh -- the plugin-generic form of the hot path: DPF / DCF key generation and point evaluation
-// written ONLY against the reference's plugin concepts
+// fss/b200/generic.cuh -- the plugin-generic form of the hot path: DPF / DCF / Half-Tree / VDPF key generation and point
+// evaluation written ONLY against the reference's plugin concepts
 //     Groupable  (group.cuh:39-45):  default ctor = zero, a + b, -a, Group::From(int4), a.Into()
 //     Prgable    (prg.cuh:20-23):    prg.Gen(int4) -> cuda::std::array<int4, mul>
 // so that ANY user-defined Group / Prg that satisfies them works, both
@@ -21,6 +21,7 @@
 #include <stdexcept>
 #include <string>
 #include <cuda/std/array>
+#include <cuda/std/tuple>
 #include <fss/group.cuh>
 #include <fss/prg.cuh>
 #include <fss/util.cuh>
@@ -209,6 +210,66 @@ FSS_SHIM_HD void HalfTreeGen(Prg &prg, int4 hash_key, Cw cws[], int4 &ocw, const
   Group v = Group::From(Clamp(b_buf)) + (-Group::From(Clamp(leaf0))) + Group::From(Clamp(leaf1));   // :168-170
   if (util::GetLsb(leaf1)) v = -v;
   ocw = v.Into();
+}
+
+// ---- VDPF (verifiable DPF) ----------------------------------------------------------------------------------------------
+// The DPF walk without an output entry in `cws` (the output correction word travels separately) plus one XorHash of
+// (point, final seed) per party / evaluation (vdpf.cuh:101-180, 195-246).  XorHash: `xh.Hash(tuple<int4, const int4>)`
+// -> 4 blocks (hash.cuh).
+template <typename XorHash>
+FSS_SHIM_HD cuda::std::array<int4, 4> PointHash(XorHash &xh, int4 point, int4 seed) {
+  return xh.Hash(cuda::std::tuple<int4, const int4>{point, seed});
+}
+
+// Vdpf::Gen: 0, or 1 when both parties end on the same control bit (the caller draws new seeds).  `cs` is written in
+// both cases, `ocw` only on success -- as the reference does (vdpf.cuh:167-179).
+template <int in_bits, typename Group, typename In, typename Prg, typename XorHash, typename Cw>
+FSS_SHIM_HD int VdpfGen(Prg &prg, XorHash &xh, Cw cws[], cuda::std::array<int4, 4> &cs, int4 &ocw, const int4 s0s[2], In a, int4 b_buf) {
+  static_assert(sizeof(Cw) == 32, "Vdpf::Cw is {int4 s; bool tr} padded to 32 bytes (vdpf.cuh:77-80)");
+  int4 n[2] = {Clamp(s0s[0]), util::SetLsb(s0s[1], true)};  // packed nodes: seed | t
+  for (int i = 0; i < in_bits; ++i) {
+    const bool right = BitMsbFirst(a, in_bits, i);
+    auto g0 = prg.Gen(Clamp(n[0]));
+    auto g1 = prg.Gen(Clamp(n[1]));
+    const int lose = right ? 0 : 1, keep = right ? 1 : 0;
+    const int4 s_cw = Clamp(util::Xor(g0[lose], g1[lose]));
+    const bool t_cw[2] = {bool(util::GetLsb(g0[0]) ^ util::GetLsb(g1[0]) ^ right ^ true), bool(util::GetLsb(g0[1]) ^ util::GetLsb(g1[1]) ^ right)};
+    const int4 cw_keep = util::SetLsb(s_cw, t_cw[keep]);
+    n[0] = Masked(g0[keep], util::GetLsb(n[0]), cw_keep);
+    n[1] = Masked(g1[keep], util::GetLsb(n[1]), cw_keep);
+    int4 *raw = reinterpret_cast<int4 *>(&cws[i]);  // both halves of the 32-byte slot (the padding is defined: zero)
+    raw[0] = util::SetLsb(s_cw, t_cw[0]);
+    raw[1] = int4{t_cw[1] ? 1 : 0, 0, 0, 0};
+  }
+  const int4 point = util::Pack(a);
+  const auto h0 = PointHash(xh, point, Clamp(n[0])), h1 = PointHash(xh, point, Clamp(n[1]));
+  for (int j = 0; j < 4; ++j) cs[j] = util::Xor(h0[j], h1[j]);
+  if (util::GetLsb(n[0]) == util::GetLsb(n[1])) return 1;
+  Group v = Group::From(Clamp(b_buf)) + (-Group::From(Clamp(n[0]))) + Group::From(Clamp(n[1]));
+  if (util::GetLsb(n[1])) v = -v;
+  ocw = v.Into();
+  return 0;
+}
+
+// Vdpf::Eval: the share through `y`, the corrected per-point hash returned.
+template <int in_bits, typename Group, typename In, typename Prg, typename XorHash, typename Cw>
+FSS_SHIM_HD cuda::std::array<int4, 4> VdpfEval(Prg &prg, XorHash &xh, bool b, int4 s0, const Cw cws[], const int4 cs[4], int4 ocw, In x,
+    int4 &y) {
+  int4 node = util::SetLsb(s0, b);
+  for (int i = 0; i < in_bits; ++i) {
+    const bool right = BitMsbFirst(x, in_bits, i);
+    auto g = prg.Gen(Clamp(node));
+    const int4 cw = util::SetLsb(cws[i].s, right ? bool(cws[i].tr) : util::GetLsb(cws[i].s));
+    node = Masked(right ? g[1] : g[0], util::GetLsb(node), cw);
+  }
+  const bool t = util::GetLsb(node);
+  Group share = Group::From(Clamp(node));
+  if (t) share = share + Group::From(ocw);
+  if (b) share = -share;
+  y = share.Into();
+  auto pi = PointHash(xh, util::Pack(x), Clamp(node));
+  for (int j = 0; j < 4; ++j) pi[j] = Masked(pi[j], t, cs[j]);
+  return pi;
 }
 
 // ---- batched kernels for user-defined plugins (instantiated in the user's translation unit) --------------------------

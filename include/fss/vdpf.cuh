@@ -1,10 +1,14 @@
 // SPDX-License-Identifier: Apache-2.0
 // fss/vdpf.cuh -- verifiable DPF (reference vdpf.cuh:63-403): same class template, template parameter list, member
-// signatures and `Cw` layout; every member evaluates on the B200 through the C ABI (include/fssb200.h,
-// fssb200_vdpf_*).  Added: batched members taking device arrays.
+// signatures and `Cw` layout; every HOST call evaluates on the B200 through the C ABI (include/fssb200.h,
+// fssb200_vdpf_*).  `Gen` and `Eval` are also callable per thread inside the user's own kernels, like the reference's
+// `__host__ __device__` members (its src/bench_gpu.cu does: VdpfGenKernel / VdpfEvalKernel), through the plugin-generic
+// templates of fss/b200/generic.cuh -- with plugins whose members are device-callable (prg::ChaCha, hash::Blake3).
+// Added: batched members taking device arrays.
 #pragma once
 #include <sys/types.h>
 #include <vector>
+#include <fss/b200/generic.cuh>
 #include <fss/b200/runtime.hpp>
 #include <fss/group.cuh>
 #include <fss/hash.cuh>
@@ -41,17 +45,25 @@ public:
 
   // ---- the reference's single-key members (host arrays) ----
   // vdpf.cuh:101: returns 1 if t0 == t1 at the end (resample the seeds and retry)
-  int Gen(Cw cws[], cuda::std::array<int4, 4> &cs, int4 &ocw, cuda::std::span<const int4, 2> s0s, In a, int4 b_buf) const {
+  FSS_SHIM_HD int Gen(Cw cws[], cuda::std::array<int4, 4> &cs, int4 &ocw, cuda::std::span<const int4, 2> s0s, In a, int4 b_buf) const {
+#if defined(__CUDA_ARCH__)
+    return b200::generic::VdpfGen<in_bits, Group, In>(const_cast<Prg &>(prg), const_cast<XorHash &>(xor_hash), cws, cs, ocw, s0s.data(), a, b_buf);
+#else
     int32_t status = 0;
     b200::Check(fssb200_vdpf_gen_host(Context(), s0s.data(), &a, &b_buf, cws, cs.data(), &ocw, &status, 1), "Vdpf::Gen");
     return status;
+#endif
   }
   // vdpf.cuh:195: y share through `y`, corrected per-point hash returned
-  cuda::std::array<int4, 4> Eval(bool b, int4 s0, cuda::std::span<const Cw> cws, cuda::std::span<const int4, 4> cs,
+  FSS_SHIM_HD cuda::std::array<int4, 4> Eval(bool b, int4 s0, cuda::std::span<const Cw> cws, cuda::std::span<const int4, 4> cs,
       int4 ocw, In x, int4 &y) const {
+#if defined(__CUDA_ARCH__)
+    return b200::generic::VdpfEval<in_bits, Group, In>(const_cast<Prg &>(prg), const_cast<XorHash &>(xor_hash), b, s0, cws.data(), cs.data(), ocw, x, y);
+#else
     cuda::std::array<int4, 4> pi{};
     b200::Check(fssb200_vdpf_eval_host(Context(), b, &s0, cws.data(), cs.data(), &ocw, &x, &y, pi.data(), 1), "Vdpf::Eval");
     return pi;
+#endif
   }
   // vdpf.cuh:259
   void Prove(cuda::std::span<const cuda::std::array<int4, 4>> pi_tildes, cuda::std::span<const int4, 4> cs,
