@@ -1,10 +1,11 @@
 // SPDX-License-Identifier: Apache-2.0
-// TEST INFRASTRUCTURE ONLY.  The sliver of the Google Benchmark interface the reference's src/bench_gpu.cu uses (the library
+// TEST INFRASTRUCTURE ONLY.  The sliver of the Google Benchmark interface the reference's src/bench_gpu.cu and src/bench_cpu.cu use (the library
 // itself is fetched from the network by the reference's CMake and is not available offline): a State that runs a fixed
-// number of manually timed iterations, BENCHMARK(fn)->Name(..)->UseManualTime() registration, and a main() that runs every
+// number of iterations (timed by SetIterationTime when the benchmark calls it, else by the wall clock of the loop body), BENCHMARK(fn)->Name(..)->UseManualTime() registration, and a main() that runs every
 // registered benchmark and prints one line each.  Own code; it only has to be enough to build that file UNMODIFIED against
 // include/ of this repository (oracle/Makefile: refbench) so that the reference's own benchmark harness runs on this library.
 #pragma once
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -19,15 +20,22 @@ class State {
   struct Iterator {
     State *s;
     bool operator!=(Sentinel) const { return s->left_ > 0; }
-    void operator++() { --s->left_; }
+    void operator++() {  // end of one iteration: without a manual time, the wall clock of the loop body counts
+      if (!s->manual_) s->Record(std::chrono::duration<double>(std::chrono::steady_clock::now() - s->started_).count());
+      s->manual_ = false;
+      --s->left_;
+      s->started_ = std::chrono::steady_clock::now();
+    }
     int operator*() const { return 0; }
   };
-  Iterator begin() { return Iterator{this}; }
+  Iterator begin() {
+    started_ = std::chrono::steady_clock::now();
+    return Iterator{this};
+  }
   Sentinel end() { return Sentinel{}; }
   void SetIterationTime(double seconds) {
-    total_ += seconds;
-    ++timed_;
-    if (best_ < 0 || seconds < best_) best_ = seconds;
+    manual_ = true;
+    Record(seconds);
   }
   long long iterations() const { return timed_; }
   void SetItemsProcessed(long long items) { items_ = items; }
@@ -37,11 +45,28 @@ class State {
   int timed() const { return timed_; }
 
  private:
+  void Record(double seconds) {
+    total_ += seconds;
+    ++timed_;
+    if (best_ < 0 || seconds < best_) best_ = seconds;
+  }
+  std::chrono::steady_clock::time_point started_{};
+  bool manual_ = false;
   int left_;
   int timed_ = 0;
   long long items_ = 0;
   double total_ = 0, best_ = -1;
 };
+
+// keeps `value` alive in the eyes of the optimiser (what the real library's function of this name is for)
+template <typename T>
+inline void DoNotOptimize(T const &value) {
+  asm volatile("" : : "r,m"(value) : "memory");
+}
+template <typename T>
+inline void DoNotOptimize(T &value) {
+  asm volatile("" : "+r,m"(value) : : "memory");
+}
 
 namespace internal {
 struct Benchmark {
@@ -76,7 +101,7 @@ inline int RunAll(int argc, char **argv) {
     State st(iters);
     b->fn(st);
     const double per_iter = st.timed() ? double(st.items_processed()) / st.timed() : 0.0;
-    std::printf("%-44s mean %12.3f us   best %12.3f us   %14.0f items/s   (%d iterations, manual time)\n", b->name.c_str(),
+    std::printf("%-44s mean %12.3f us   best %12.3f us   %14.0f items/s   (%d iterations)\n", b->name.c_str(),
         st.mean_seconds() * 1e6, st.best_seconds() * 1e6, st.mean_seconds() > 0 ? per_iter / st.mean_seconds() : 0.0, st.timed());
     std::fflush(stdout);
   }

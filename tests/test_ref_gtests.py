@@ -104,3 +104,18 @@ def test_reference_cpu_gpu_parity_check_runs_against_this_library():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL PASS" in r.stdout and "FAIL" not in r.stdout.replace("FAILURES", ""), r.stdout[-3000:] + r.stderr[-2000:]
     assert r.stdout.count("PASS") >= 6, r.stdout
+
+
+def test_reference_cpu_benchmark_on_the_cpu_over_the_oracle_backend(tmp_path):
+    """The reference's src/bench_cpu.cu (Google Benchmark harness: oracle/gbench_stub stands in for the library the reference
+    fetches from the network), unmodified, on the shim headers: built by oracle/Makefile, linked here with the oracle-backed
+    C ABI, a subset of its 32 benchmarks run once -- every scheme's Gen, and the OpenMP loop over keys calling Dpf::Eval."""
+    obj, main_o = os.path.join(BIN, "bench_cpu.o"), os.path.join(BIN, "gbench_main.o")
+    if not os.path.exists(obj) or not os.path.exists(main_o):
+        pytest.skip(f"{obj} not built (needs the reference checkout: make -C oracle reftests)")
+    exe = str(tmp_path / "bench_cpu_cpu")
+    link_over_the_oracle_backend(tmp_path, obj, exe, [main_o])
+    for flt, at_least in (("Gen", 8), ("BM_DpfEval_Uint_Aes/14", 1)):
+        r = subprocess.run([exe, flt], capture_output=True, text=True, timeout=600, env=dict(os.environ, FSS_BENCH_ITERS="1"))
+        lines = [l for l in r.stdout.splitlines() if l.startswith("BM_")]
+        assert r.returncode == 0 and len(lines) >= at_least and all("(1 iterations)" in l for l in lines), r.stdout[-3000:] + r.stderr[-2000:]
