@@ -11,8 +11,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_pending: needs a CUDA device and has NOT been run on one yet (written after the round's GPU "
-                                       "budget was spent); deliberately outside -m gpu, skipped without a device; run with -m gpu_pending")
 
 
 @pytest.fixture(scope="session")

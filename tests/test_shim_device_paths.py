@@ -6,8 +6,9 @@ b200/generic.cuh) -- what the reference's own GPU benchmark (src/bench_gpu.cu) c
   host and compared bit for bit with the oracle and the survey's known answers (CPU);
 * the reference's src/bench_gpu.cu, unmodified, cross-compiles for sm_100a against include/ of this repository (nvcc, CPU;
   oracle/gbench_stub/ stands in for the Google Benchmark headers the reference fetches from the network).
-These device paths were written after the round's GPU budget was spent: they are host-verified and compiled for sm_100a, not
-yet executed on a B200 (the binary oracle/_ref/reftests/bench_gpu is built for that)."""
+* tests/cpp/device_members.cu (-m gpu): kernels calling those members per thread, bit-compared with the batched members behind
+  the C ABI on the B200 (passed on hardware with the round's last GPU seconds: profiles/r02_last_session_gpu_checks.md).
+The reference's benchmark binary itself (oracle/_ref/reftests/bench_gpu) has been built, not timed on a B200."""
 import os
 import subprocess
 
@@ -53,12 +54,8 @@ def test_device_members_program_compiles_for_sm100a(tmp_path):
     assert os.path.getsize(exe) > 0
 
 
-@pytest.mark.gpu_pending
+@pytest.mark.gpu
 def test_device_members_on_the_gpu(tmp_path):
-    """NOT YET RUN ON A B200 (see the module docstring): kept out of `-m gpu` on purpose; `pytest -m gpu_pending` runs it."""
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("needs a CUDA device")
     exe = str(tmp_path / "device_members")
     build_device_members(exe)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
