@@ -1,5 +1,5 @@
 // SPDX-License-Identifier: Apache-2.0
-// TEST INFRASTRUCTURE ONLY.  The sliver of the Google Benchmark interface the reference's src/bench_gpu.cu and src/bench_cpu.cu use (the library
+// TEST INFRASTRUCTURE ONLY.  The sliver of the Google Benchmark interface the reference's src/bench_gpu.cu, src/bench_cpu.cu and third_party/fss/bench.cu use (the library
 // itself is fetched from the network by the reference's CMake and is not available offline): a State that runs a fixed
 // number of iterations (timed by SetIterationTime when the benchmark calls it, else by the wall clock of the loop body), BENCHMARK(fn)->Name(..)->UseManualTime() registration, and a main() that runs every
 // registered benchmark and prints one line each.  Own code; it only has to be enough to build that file UNMODIFIED against
@@ -88,6 +88,8 @@ inline Benchmark *Register(void (*fn)(State &), const char *name) {
   return b;
 }
 }  // namespace internal
+
+inline internal::Benchmark *RegisterBenchmark(const char *name, void (*fn)(State &)) { return internal::Register(fn, name); }
 
 // Runs every registered benchmark whose name contains `filter` (argv[1], optional): 2 warm-up + FSS_BENCH_ITERS (10) iterations.
 inline int RunAll(int argc, char **argv) {

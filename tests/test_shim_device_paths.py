@@ -40,6 +40,14 @@ def test_reference_gpu_benchmark_compiles_unmodified_for_sm100a(tmp_path):
         assert kernel in sass, kernel
 
 
+def test_reference_benchmark_programs_are_built():
+    """oracle/Makefile builds the reference's three benchmark programs, unmodified, against include/ + libfssb200.so."""
+    if not os.path.isdir(os.path.join(REF, "include", "fss")):
+        pytest.skip("reference checkout not present")
+    for name in ("bench_gpu", "bench_cpu", "bench_xlib"):
+        assert os.path.getsize(os.path.join(ROOT, "oracle", "_ref", "reftests", name)) > 0, name
+
+
 def build_device_members(out):
     subprocess.run(["nvcc", "-std=c++20", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-I", os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "cpp", "device_members.cu"), "-o", out, "-L", os.path.join(ROOT, "fss_b200"), "-lfssb200",
