@@ -12,6 +12,8 @@
 #   host      lscpu / numactl / nvidia-smi topo of the box       -> gpurun_out/host.txt
 #   fuzz      tests/test_gpu_fuzz.py with $FUZZ_CASES cases (default 1500) and seed $FUZZ_SEED  -> gpurun_out/fuzz.log
 #   sanitize  compute-sanitizer ($SAN_TOOLS) over tools/sanitize_cases.py ($SAN_CASES) -> gpurun_out/sanitize_<tool>.log
+#   refbench  the reference's own benchmark programs, unmodified, on this library (oracle/_ref/reftests/bench_{gpu,xlib,cpu};
+#             $REFBENCH_FILTER = substring of the benchmark names, FSS_BENCH_ITERS iterations) -> gpurun_out/refbench_<name>.txt
 set -u
 mkdir -p gpurun_out
 for step in "$@"; do
@@ -52,6 +54,12 @@ for step in "$@"; do
         timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_cases.py ${SAN_CASES:-walk pipeline packed} \
           > gpurun_out/sanitize_$tool.log 2>&1
         echo "sanitize $tool rc=$?"; tail -4 gpurun_out/sanitize_$tool.log
+      done ;;
+    refbench)
+      for b in bench_gpu bench_xlib bench_cpu; do
+        [ -x oracle/_ref/reftests/$b ] || { echo "$b not built (make -C oracle reftests, needs the reference checkout)"; continue; }
+        FSS_BENCH_ITERS=${FSS_BENCH_ITERS:-10} timeout 600 oracle/_ref/reftests/$b ${REFBENCH_FILTER:-} > gpurun_out/refbench_$b.txt 2>&1
+        echo "refbench $b rc=$?"; tail -5 gpurun_out/refbench_$b.txt
       done ;;
     *) echo "unknown step $step" ;;
   esac
