@@ -540,6 +540,28 @@ int main(int argc, char **argv) {
       CHECK(fssb200_gen_host(dpf, s0s.data(), al.data(), be.data(), cws.data(), nullptr, nk) == 0, "gen_host after a failed call");
       fssb200_ctx_reserve_host(dpf, 0);
     }
+    {  // ... and in the key-group loop of eval_all_host (groups of 2 keys: the second launch fails)
+      const size_t nk = 5, cwb = size_t(ea_ht->ncw) * 32, N = size_t(1) << ea_ht->p.in_bits;
+      std::vector<uint8_t> seeds, cws, ocws, ys(nk * N * 16, 0xEE);
+      fill(seeds, nk * 16); fill(cws, nk * cwb); fill(ocws, nk * 16);
+      fssb200_ctx_reserve_host(ea_ht, 2);
+      g_fail_after.store(1);
+      const int rc = fssb200_eval_all_host(ea_ht, 0, seeds.data(), cws.data(), ocws.data(), ys.data(), nk, 0, 0);
+      g_fail_after.store(-1);
+      CHECK(rc == 700, "eval_all_host: injected launch error not reported: rc = %d", rc);
+      CHECK(fssb200_eval_all_host(ea_ht, 0, seeds.data(), cws.data(), ocws.data(), ys.data(), nk, 0, 0) == 0, "eval_all_host after a failed call");
+      size_t bad = 0;
+      for (size_t k = 0; k < nk; ++k) {
+        const uint64_t hk = AllKeyDigest(ea_ht, 0, &seeds[16 * k], &cws[cwb * k], &ocws[16 * k]);
+        for (uint64_t i = 0; i < N; ++i) {
+          uint8_t w[16];
+          AllLeaf(ea_ht, hk, i, w);
+          bad += std::memcmp(w, &ys[(k * N + i) * 16], 16) != 0;
+        }
+      }
+      CHECK(bad == 0, "eval_all_host after a failed call: %zu wrong leaves", bad);
+      fssb200_ctx_reserve_host(ea_ht, 0);
+    }
     // VDPF host calls
     fssb200_ctx *vd = MakeCtx(FSSB200_SCHEME_VDPF, 24, 4);
     {
