@@ -1,8 +1,8 @@
-"""The reference's OWN googletest suites (src/{dpf,dcf,half_tree_dpf,grotto_dcf,vdpf,group}_test.cu), compiled UNMODIFIED --
+"""The reference's OWN googletest suites (src/{dpf,dcf,half_tree_dpf,grotto_dcf,vdpf,vdmpf,group}_test.cu), compiled UNMODIFIED --
 but against this repository's header tree and linked with libfssb200.so (oracle/Makefile: `make reftests`, built in the
 container where the reference checkout is; the binaries travel to the GPU box under oracle/_ref/reftests/).  A user of the
 reference switches by changing one include path and one library; this is that switch applied to the reference's own
-tests: 33 group-axiom tests on the CPU, 70 scheme tests (reconstruction at / off alpha, EvalAll, Grotto edge cases, VDPF
+tests: 33 group-axiom tests on the CPU, 65 scheme tests (11 + 7 + 27 + 5 + 8 + 7: reconstruction at / off alpha, EvalAll, Grotto edge cases, VDPF / VDMPF
 verification; ChaCha, Aes128Mmo and Aes128Soft PRGs; Bytes / Uint64 / Uint127 groups; in_bits = 1) on the B200."""
 import os
 import re
